@@ -1,0 +1,69 @@
+/*
+ * ORACLE — TEST INFRASTRUCTURE ONLY.  Not part of the shipped product path.
+ *
+ * CPU restatement (plain C11) of the rusty-kaspa transaction-validation hot path
+ * (SURVEY.md §8a), used as the parity checker for the CUDA kernels and as the
+ * "port" CPU baseline.  Only tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline / --impl reference legs may load it.  Every function cites the
+ * reference file:line it follows.
+ *
+ * Parity pinning: hashes, tx-id/tx-hash, sighash, the mainnet Schnorr P2PK and
+ * 2-of-4 P2SH multisig KATs and the 224-input simpa fixture are pinned by the
+ * reference's own vectors (tests/golden/*.json, tests/test_oracle_golden.py).
+ * ECDSA verdicts and the Schnorr edge encodings (r>=p, s>=n, off-curve pk) are
+ * NOT covered by any stored vector in the reference: for those "parity
+ * unpinned" — they are cross-checked against an independent big-int restatement
+ * (oracle/pyref.py) and OpenSSL (`cryptography`) only.
+ */
+#ifndef OK_ORACLE_H
+#define OK_ORACLE_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- hashes (ok_hash.c) ---- */
+typedef struct { uint32_t st[8]; uint64_t len; uint8_t buf[64]; } ok_sha256_ctx;
+void ok_sha256_init(ok_sha256_ctx* c);
+void ok_sha256_update(ok_sha256_ctx* c, const void* data, size_t n);
+void ok_sha256_final(ok_sha256_ctx* c, uint8_t out[32]);
+void ok_sha256(const void* data, size_t n, uint8_t out[32]);
+void ok_sha256_domain(const char* domain, const void* data, size_t n, uint8_t out[32]);
+
+typedef struct { uint64_t h[8]; uint64_t t[2]; uint8_t buf[128]; size_t fill; size_t outlen; } ok_blake2b_ctx;
+void ok_blake2b_init(ok_blake2b_ctx* c, size_t outlen, const void* key, size_t keylen);
+void ok_blake2b_update(ok_blake2b_ctx* c, const void* data, size_t n);
+void ok_blake2b_final(ok_blake2b_ctx* c, uint8_t* out);
+void ok_blake2b_keyed(const char* domain, const void* data, size_t n, uint8_t out[32]);
+void ok_blake2b_256(const void* data, size_t n, uint8_t out[32]);
+
+/* ---- secp256k1 (ok_secp256k1.c) ---- */
+/* Per-item verdicts: the reference distinguishes a parse error
+ * (script aborts with InvalidSignature) from a well-formed but wrong signature. */
+enum { OK_SIG_INVALID = 0, OK_SIG_VALID = 1, OK_SIG_PK_PARSE_ERR = 2, OK_SIG_SIG_PARSE_ERR = 3 };
+
+void ok_secp_init(void); /* builds the generator table once; idempotent, thread-safe after first call */
+int ok_schnorr_verify(const uint8_t pk32[32], const uint8_t msg32[32], const uint8_t sig64[64]);
+int ok_ecdsa_verify(const uint8_t pk33[33], const uint8_t msg32[32], const uint8_t sig64[64]);
+/* batch forms: SoA, nthreads >= 1 worker threads with contiguous static chunks
+ * (mirrors rayon par_iter over a slice, consensus/src/pipeline/virtual_processor/utxo_validation.rs:269-277) */
+void ok_schnorr_verify_batch(const uint8_t* pk32, const uint8_t* msg32, const uint8_t* sig64, size_t n, uint8_t* status, int nthreads);
+void ok_ecdsa_verify_batch(const uint8_t* pk33, const uint8_t* msg32, const uint8_t* sig64, size_t n, uint8_t* status, int nthreads);
+
+/* test-vector generation helpers (BIP-340 signing with aux=0^32; ECDSA with a
+ * SHA-256 derived nonce and low-S normalisation).  Return 1 on success. */
+int ok_schnorr_pubkey(const uint8_t seckey32[32], uint8_t pk32[32]);
+int ok_schnorr_sign(const uint8_t seckey32[32], const uint8_t msg32[32], uint8_t sig64[64]);
+int ok_ecdsa_pubkey(const uint8_t seckey32[32], uint8_t pk33[33]);
+int ok_ecdsa_sign(const uint8_t seckey32[32], const uint8_t msg32[32], uint8_t sig64[64]);
+/* low-level probes used by the cross-checks against oracle/pyref.py */
+int ok_ec_mul_xy(const uint8_t scalar32[32], const uint8_t px32[32], const uint8_t py32[32], uint8_t outx[32], uint8_t outy[32]);
+void ok_fe_mul_bytes(const uint8_t a[32], const uint8_t b[32], uint8_t out[32]);
+void ok_sc_mul_bytes(const uint8_t a[32], const uint8_t b[32], uint8_t out[32]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,52 @@
+"""ctypes loader for libkgv.so (the C-ABI drop-in boundary, include/kgv.h).
+
+There is deliberately no fallback: if the CUDA library is missing or no device is usable the
+import of a context fails loudly.  Nothing under oracle/ is ever touched from here.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libkgv.so")
+
+KGV_OK = 0
+SIG_INVALID, SIG_VALID, SIG_PK_PARSE_ERR, SIG_SIG_PARSE_ERR = 0, 1, 2, 3
+
+# every symbol include/kgv.h declares: (name, restype, argtypes)
+_c = ctypes
+_u8p = _c.c_void_p  # raw addresses (host or device)
+SYMBOLS = [
+    ("kgv_create", _c.c_int, [_c.c_int, _c.c_uint32, _c.POINTER(_c.c_void_p)]),
+    ("kgv_destroy", None, [_c.c_void_p]),
+    ("kgv_set_stream", _c.c_int, [_c.c_void_p, _c.c_void_p]),
+    ("kgv_synchronize", _c.c_int, [_c.c_void_p]),
+    ("kgv_last_error", _c.c_char_p, [_c.c_void_p]),
+    ("kgv_launch_count", _c.c_uint64, [_c.c_void_p]),
+    ("kgv_schnorr_verify", _c.c_int, [_c.c_void_p, _u8p, _u8p, _u8p, _c.c_size_t, _u8p]),
+    ("kgv_ecdsa_verify", _c.c_int, [_c.c_void_p, _u8p, _u8p, _u8p, _c.c_size_t, _u8p]),
+    ("kgv_status_to_bitmap", _c.c_int, [_c.c_void_p, _u8p, _c.c_size_t, _u8p]),
+    ("kgv_gtable_entry", _c.c_int, [_c.c_void_p, _c.c_int, _c.c_uint32, _u8p]),
+]
+
+_lib = None
+
+
+class KgvError(RuntimeError):
+    pass
+
+
+def load():
+    """Loads libkgv.so (built by __graft_entry__.build()). Raises if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise KgvError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                       "(there is no CPU fallback)")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, res, args in SYMBOLS:
+        fn = getattr(lib, name)  # AttributeError if the ABI lost a symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib

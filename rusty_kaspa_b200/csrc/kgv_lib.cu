@@ -1,0 +1,333 @@
+// kgv_lib.cu — kernels and C ABI of libkgv.so (see include/kgv.h).
+//
+// Hand-written CUDA for sm_100a.  No CPU fallback: every entry point needs a CUDA device.
+#include "../../include/kgv.h"
+#include "kgv_internal.h"
+#include "kgv_verify.cuh"
+
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+
+using namespace kgv;
+
+// ---------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------
+// per-thread table in shared memory, word-major / thread-minor: every access of a warp hits 32
+// consecutive banks whatever entry each lane selects
+struct SmemTab {
+  uint32_t* base;  // smem + threadIdx.x
+  __device__ __forceinline__ void put(int e, int w, uint32_t v) { base[(e * 16 + w) * KGV_BLOCK] = v; }
+  __device__ __forceinline__ uint32_t get(int e, int w) const { return base[(e * 16 + w) * KGV_BLOCK]; }
+};
+
+// 256-bit read-only load (LDG.E.256 on sm_100a)
+__device__ __forceinline__ void ldg256(uint32_t* w, const void* p) {
+  asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+               : "l"(p));
+}
+// streaming variant for the signature triples (read once)
+__device__ __forceinline__ void ldg256_stream(uint32_t* w, const void* p) {
+  asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+               : "l"(p));
+}
+
+// generator table entry: 64 bytes, 64-byte aligned: two 256-bit loads
+struct GLoadDev {
+  __device__ __forceinline__ void operator()(fe& x, fe& y, const uint32_t* entry) const {
+    ldg256(x.v, entry);
+    ldg256(y.v, entry + 8);
+  }
+};
+
+// 32 big-endian bytes -> 8 numeric words (w[0] most significant)
+template <bool ALIGNED>
+__device__ __forceinline__ void load_be32(uint32_t* w, const uint8_t* p) {
+  if (ALIGNED) {
+    ldg256_stream(w, p);
+#pragma unroll
+    for (int i = 0; i < 8; i++) w[i] = bswap32(w[i]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+      w[i] = ((uint32_t)p[4 * i] << 24) | ((uint32_t)p[4 * i + 1] << 16) | ((uint32_t)p[4 * i + 2] << 8) | (uint32_t)p[4 * i + 3];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_build_gtab(uint32_t* __restrict__ gtab) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 2u * 65536u) return;
+  uint32_t v = t & 0xFFFFu;
+  uint32_t which = t >> 16;
+  uint32_t* out = gtab + (size_t)t * 16;
+  if (v == 0) {
+#pragma unroll
+    for (int i = 0; i < 16; i++) out[i] = 0;
+    return;
+  }
+  const fe gx = {KGV_GX_LIMBS}, gy = {KGV_GY_LIMBS}, hx = {KGV_G128X_LIMBS}, hy = {KGV_G128Y_LIMBS};
+  fe x, y;
+  if (which == 0) gtab_entry(x, y, v, gx, gy);
+  else gtab_entry(x, y, v, hx, hy);
+#pragma unroll
+  for (int i = 0; i < 8; i++) { out[i] = x.v[i]; out[8 + i] = y.v[i]; }
+}
+
+template <bool ALIGNED>
+__global__ void __launch_bounds__(KGV_BLOCK, KGV_BLOCKS_PER_SM)
+k_schnorr_verify(const uint8_t* __restrict__ pk, const uint8_t* __restrict__ msg, const uint8_t* __restrict__ sig, size_t n,
+                 uint8_t* __restrict__ status, const uint32_t* __restrict__ gtab) {
+  extern __shared__ uint32_t smem[];
+  size_t i = (size_t)blockIdx.x * KGV_BLOCK + threadIdx.x;
+  if (i >= n) return;
+  uint32_t pkw[8], mw[8], sw[16];
+  load_be32<ALIGNED>(pkw, pk + 32 * i);
+  load_be32<ALIGNED>(mw, msg + 32 * i);
+  load_be32<ALIGNED>(sw, sig + 64 * i);
+  load_be32<ALIGNED>(sw + 8, sig + 64 * i + 32);
+  SmemTab tab{smem + threadIdx.x};
+  status[i] = schnorr_verify_core(pkw, mw, sw, tab, gtab, GLoadDev());
+}
+
+template <bool ALIGNED>
+__global__ void __launch_bounds__(KGV_BLOCK, KGV_BLOCKS_PER_SM)
+k_ecdsa_verify(const uint8_t* __restrict__ pk, const uint8_t* __restrict__ msg, const uint8_t* __restrict__ sig, size_t n,
+               uint8_t* __restrict__ status, const uint32_t* __restrict__ gtab) {
+  extern __shared__ uint32_t smem[];
+  size_t i = (size_t)blockIdx.x * KGV_BLOCK + threadIdx.x;
+  if (i >= n) return;
+  uint32_t pkw[8], mw[8], sw[16];
+  const uint8_t* kp = pk + 33 * i;  // 33-byte stride: never word aligned
+  uint32_t tag = kp[0];
+  load_be32<false>(pkw, kp + 1);
+  load_be32<ALIGNED>(mw, msg + 32 * i);
+  load_be32<ALIGNED>(sw, sig + 64 * i);
+  load_be32<ALIGNED>(sw + 8, sig + 64 * i + 32);
+  SmemTab tab{smem + threadIdx.x};
+  status[i] = ecdsa_verify_core(tag, pkw, mw, sw, tab, gtab, GLoadDev());
+}
+
+__global__ void k_status_to_bitmap(const uint8_t* __restrict__ status, size_t n, uint8_t* __restrict__ bitmap) {
+  size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t nbytes = (n + 7) / 8;
+  if (b >= nbytes) return;
+  uint32_t bits = 0;
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    size_t i = 8 * b + j;
+    if (i < n && status[i] == KGV_ST_VALID) bits |= 1u << j;
+  }
+  bitmap[b] = (uint8_t)bits;
+}
+
+// ---------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------
+#define CK(call)                                                                                  \
+  do {                                                                                            \
+    cudaError_t e_ = (call);                                                                      \
+    if (e_ != cudaSuccess) {                                                                      \
+      char b_[256];                                                                               \
+      snprintf(b_, sizeof b_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+      ctx->err = b_;                                                                              \
+      return KGV_ERR_CUDA;                                                                        \
+    }                                                                                             \
+  } while (0)
+
+static int fail_arg(kgv_ctx* ctx, const char* msg) {
+  if (ctx) ctx->err = msg;
+  return KGV_ERR_ARG;
+}
+
+// 1 = device-accessible pointer, 0 = host pointer
+int kgv_ptr_is_device(const void* p) {
+  cudaPointerAttributes a;
+  cudaError_t e = cudaPointerGetAttributes(&a, p);
+  if (e != cudaSuccess) { (void)cudaGetLastError(); return 0; }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+int kgv_reserve(kgv_ctx* ctx, uint8_t** buf, size_t* cap, size_t need) {
+  if (*cap >= need) return KGV_OK;
+  if (*buf) { CK(cudaStreamSynchronize(ctx->stream)); CK(cudaFree(*buf)); *buf = nullptr; *cap = 0; }
+  size_t want = need + need / 4 + 4096;
+  cudaError_t e = cudaMalloc((void**)buf, want);
+  if (e != cudaSuccess) { ctx->err = std::string("cudaMalloc failed: ") + cudaGetErrorString(e); (void)cudaGetLastError(); return KGV_ERR_NOMEM; }
+  *cap = want;
+  return KGV_OK;
+}
+
+extern "C" int kgv_create(int device, uint32_t flags, kgv_ctx** out) {
+  (void)flags;
+  if (!out) return KGV_ERR_ARG;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) {
+    (void)cudaGetLastError();
+    return KGV_ERR_CUDA;  // no CUDA device: there is no CPU path
+  }
+  kgv_ctx* ctx = new kgv_ctx();
+  ctx->device = device;
+  auto body = [&]() -> int {
+    CK(cudaSetDevice(device));
+    CK(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+    ctx->stream = ctx->own_stream;
+    CK(cudaMalloc((void**)&ctx->gtab, (size_t)2 * 65536 * 16 * sizeof(uint32_t)));
+    k_build_gtab<<<(2 * 65536) / 128, 128, 0, ctx->stream>>>(ctx->gtab);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    const int smem = KGV_BLOCK * 128 * (int)sizeof(uint32_t);
+    CK(cudaFuncSetAttribute(k_schnorr_verify<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CK(cudaFuncSetAttribute(k_schnorr_verify<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CK(cudaFuncSetAttribute(k_ecdsa_verify<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CK(cudaFuncSetAttribute(k_ecdsa_verify<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return KGV_OK;
+  };
+  int rc = body();
+  if (rc != KGV_OK) {
+    fprintf(stderr, "kgv_create: %s\n", ctx->err.c_str());
+    delete ctx;
+    return rc;
+  }
+  *out = ctx;
+  return KGV_OK;
+}
+
+extern "C" void kgv_destroy(kgv_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->gtab) cudaFree(ctx->gtab);
+  if (ctx->d_in) cudaFree(ctx->d_in);
+  if (ctx->d_out) cudaFree(ctx->d_out);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  delete ctx;
+}
+
+extern "C" int kgv_set_stream(kgv_ctx* ctx, void* cuda_stream) {
+  if (!ctx) return KGV_ERR_ARG;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+  return KGV_OK;
+}
+
+extern "C" int kgv_synchronize(kgv_ctx* ctx) {
+  if (!ctx) return KGV_ERR_ARG;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return KGV_OK;
+}
+
+extern "C" const char* kgv_last_error(const kgv_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+extern "C" uint64_t kgv_launch_count(const kgv_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ---------------------------------------------------------------------------------------------
+// signature verification entry points
+// ---------------------------------------------------------------------------------------------
+static int verify_common(kgv_ctx* ctx, const uint8_t* pk, size_t pk_stride, const uint8_t* msg, const uint8_t* sig, size_t n,
+                         uint8_t* status, bool ecdsa) {
+  if (!ctx) return KGV_ERR_ARG;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  if (n == 0) return KGV_OK;
+  if (!pk || !msg || !sig || !status) return fail_arg(ctx, "null buffer");
+  CK(cudaSetDevice(ctx->device));
+  int dev = kgv_ptr_is_device(pk);
+  if (kgv_ptr_is_device(msg) != dev || kgv_ptr_is_device(sig) != dev || kgv_ptr_is_device(status) != dev)
+    return fail_arg(ctx, "all buffers of one call must be host pointers or all device pointers");
+  const uint8_t *dpk = pk, *dmsg = msg, *dsig = sig;
+  uint8_t* dst = status;
+  if (!dev) {
+    size_t off_msg = (pk_stride * n + 255) & ~(size_t)255;
+    size_t off_sig = off_msg + 32 * n;
+    int rc = kgv_reserve(ctx, &ctx->d_in, &ctx->d_in_cap, off_sig + 64 * n);
+    if (rc) return rc;
+    rc = kgv_reserve(ctx, &ctx->d_out, &ctx->d_out_cap, n);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(ctx->d_in, pk, pk_stride * n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_in + off_msg, msg, 32 * n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_in + off_sig, sig, 64 * n, cudaMemcpyHostToDevice, ctx->stream));
+    dpk = ctx->d_in; dmsg = ctx->d_in + off_msg; dsig = ctx->d_in + off_sig; dst = ctx->d_out;
+  }
+  const int smem = KGV_BLOCK * 128 * (int)sizeof(uint32_t);
+  unsigned blocks = (unsigned)((n + KGV_BLOCK - 1) / KGV_BLOCK);
+  bool aligned = (((uintptr_t)dmsg | (uintptr_t)dsig | (ecdsa ? 0 : (uintptr_t)dpk)) & 31) == 0;
+  if (ecdsa) {
+    if (aligned) k_ecdsa_verify<true><<<blocks, KGV_BLOCK, smem, ctx->stream>>>(dpk, dmsg, dsig, n, dst, ctx->gtab);
+    else k_ecdsa_verify<false><<<blocks, KGV_BLOCK, smem, ctx->stream>>>(dpk, dmsg, dsig, n, dst, ctx->gtab);
+  } else {
+    if (aligned) k_schnorr_verify<true><<<blocks, KGV_BLOCK, smem, ctx->stream>>>(dpk, dmsg, dsig, n, dst, ctx->gtab);
+    else k_schnorr_verify<false><<<blocks, KGV_BLOCK, smem, ctx->stream>>>(dpk, dmsg, dsig, n, dst, ctx->gtab);
+  }
+  CK(cudaGetLastError());
+  ctx->launches++;
+  if (!dev) {
+    CK(cudaMemcpyAsync(status, dst, n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  return KGV_OK;
+}
+
+extern "C" int kgv_schnorr_verify(kgv_ctx* ctx, const uint8_t* pk32, const uint8_t* msg32, const uint8_t* sig64, size_t n, uint8_t* status) {
+  return verify_common(ctx, pk32, 32, msg32, sig64, n, status, false);
+}
+extern "C" int kgv_ecdsa_verify(kgv_ctx* ctx, const uint8_t* pk33, const uint8_t* msg32, const uint8_t* sig64, size_t n, uint8_t* status) {
+  return verify_common(ctx, pk33, 33, msg32, sig64, n, status, true);
+}
+
+extern "C" int kgv_status_to_bitmap(kgv_ctx* ctx, const uint8_t* status, size_t n, uint8_t* bitmap) {
+  if (!ctx) return KGV_ERR_ARG;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  if (n == 0) return KGV_OK;
+  if (!status || !bitmap) return fail_arg(ctx, "null buffer");
+  CK(cudaSetDevice(ctx->device));
+  int dev = kgv_ptr_is_device(status);
+  if (kgv_ptr_is_device(bitmap) != dev) return fail_arg(ctx, "all buffers of one call must be host pointers or all device pointers");
+  size_t nbytes = (n + 7) / 8;
+  const uint8_t* dsrc = status;
+  uint8_t* ddst = bitmap;
+  if (!dev) {
+    int rc = kgv_reserve(ctx, &ctx->d_in, &ctx->d_in_cap, n);
+    if (rc) return rc;
+    rc = kgv_reserve(ctx, &ctx->d_out, &ctx->d_out_cap, nbytes);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(ctx->d_in, status, n, cudaMemcpyHostToDevice, ctx->stream));
+    dsrc = ctx->d_in; ddst = ctx->d_out;
+  }
+  k_status_to_bitmap<<<(unsigned)((nbytes + 255) / 256), 256, 0, ctx->stream>>>(dsrc, n, ddst);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  if (!dev) {
+    CK(cudaMemcpyAsync(bitmap, ddst, nbytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  return KGV_OK;
+}
+
+extern "C" int kgv_gtable_entry(kgv_ctx* ctx, int which, uint32_t v, uint8_t out_xy[64]) {
+  if (!ctx) return KGV_ERR_ARG;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  if ((which != 0 && which != 1) || v == 0 || v > 65535 || !out_xy) return fail_arg(ctx, "bad table index");
+  CK(cudaSetDevice(ctx->device));
+  uint32_t w[16];
+  CK(cudaMemcpyAsync(w, ctx->gtab + ((size_t)which * 65536 + v) * 16, sizeof w, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  for (int c = 0; c < 2; c++)
+    for (int i = 0; i < 8; i++) {
+      uint32_t limb = w[c * 8 + 7 - i];
+      out_xy[c * 32 + 4 * i] = (uint8_t)(limb >> 24);
+      out_xy[c * 32 + 4 * i + 1] = (uint8_t)(limb >> 16);
+      out_xy[c * 32 + 4 * i + 2] = (uint8_t)(limb >> 8);
+      out_xy[c * 32 + 4 * i + 3] = (uint8_t)limb;
+    }
+  return KGV_OK;
+}

@@ -1,0 +1,126 @@
+"""Host-side Python mirror of the signature-verification boundary.
+
+`GpuContext` owns a kgv_ctx (one per device).  `verify_schnorr_batch` / `verify_ecdsa_batch` are the
+batch equivalents of the reference's per-signature `check_schnorr_signature` / `check_ecdsa_signature`
+(crypto/txscript/src/lib.rs:574-643): they return the tri-state verdict per triple that the script
+engine needs (valid / invalid / pubkey-parse-error / sig-parse-error).
+
+Buffers may be numpy arrays (host path: H2D + kernel + D2H inside the call) or torch CUDA tensors
+(device path: enqueued on the current torch stream, no copies, no sync).
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+
+
+def _addr_and_keepalive(buf, nbytes, writable=False):
+    """Returns (address, is_device, keepalive) for a numpy array / torch tensor / bytes-like."""
+    try:
+        import torch
+    except Exception:  # pragma: no cover
+        torch = None
+    if torch is not None and isinstance(buf, torch.Tensor):
+        if not buf.is_contiguous():
+            raise ValueError("tensor must be contiguous")
+        if buf.numel() * buf.element_size() < nbytes:
+            raise ValueError("tensor too small")
+        return buf.data_ptr(), buf.is_cuda, buf
+    arr = np.ascontiguousarray(buf) if not isinstance(buf, np.ndarray) else buf
+    if not arr.flags["C_CONTIGUOUS"]:
+        raise ValueError("array must be C-contiguous")
+    if arr.nbytes < nbytes:
+        raise ValueError("array too small")
+    if writable and not arr.flags["WRITEABLE"]:
+        raise ValueError("output array must be writable")
+    return arr.ctypes.data, False, arr
+
+
+class GpuContext:
+    """One per device; wraps kgv_create/kgv_destroy. Fails loudly without a CUDA device."""
+
+    def __init__(self, device=0):
+        self._lib = _lib.load()
+        h = ctypes.c_void_p()
+        rc = self._lib.kgv_create(int(device), 0, ctypes.byref(h))
+        if rc != 0 or not h:
+            raise _lib.KgvError(f"kgv_create(device={device}) failed with {rc}: no usable CUDA device (no CPU fallback)")
+        self._h = h
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.kgv_destroy(self._h)
+            self._h = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise _lib.KgvError(f"kgv call failed ({rc}): {self._lib.kgv_last_error(self._h).decode()}")
+
+    def use_stream(self, cuda_stream_handle):
+        self._check(self._lib.kgv_set_stream(self._h, ctypes.c_void_p(cuda_stream_handle)))
+
+    def use_torch_stream(self):
+        import torch
+        self.use_stream(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def synchronize(self):
+        self._check(self._lib.kgv_synchronize(self._h))
+
+    @property
+    def launch_count(self):
+        return int(self._lib.kgv_launch_count(self._h))
+
+    # -- signature batches -------------------------------------------------------------------
+    def _verify(self, fn, pk, pk_stride, msg, sig, n, status):
+        if status is None:
+            status = np.empty(n, dtype=np.uint8)
+        a_pk, d0, k0 = _addr_and_keepalive(pk, pk_stride * n)
+        a_msg, d1, k1 = _addr_and_keepalive(msg, 32 * n)
+        a_sig, d2, k2 = _addr_and_keepalive(sig, 64 * n)
+        a_st, d3, k3 = _addr_and_keepalive(status, n, writable=True)
+        self._check(fn(self._h, a_pk, a_msg, a_sig, n, a_st))
+        return status
+
+    def verify_schnorr_batch(self, pk32, msg32, sig64, n=None, status=None):
+        """status[i] in {0 invalid, 1 valid, 2 pubkey parse error} for BIP-340 triples (SoA buffers)."""
+        if n is None:
+            n = _nbytes(pk32) // 32
+        return self._verify(self._lib.kgv_schnorr_verify, pk32, 32, msg32, sig64, n, status)
+
+    def verify_ecdsa_batch(self, pk33, msg32, sig64, n=None, status=None):
+        """status[i] in {0,1,2,3} for ECDSA triples with 33-byte compressed keys (SoA buffers)."""
+        if n is None:
+            n = _nbytes(pk33) // 33
+        return self._verify(self._lib.kgv_ecdsa_verify, pk33, 33, msg32, sig64, n, status)
+
+    def status_to_bitmap(self, status, n=None, bitmap=None):
+        if n is None:
+            n = _nbytes(status)
+        if bitmap is None:
+            bitmap = np.empty((n + 7) // 8, dtype=np.uint8)
+        a_st, _, k0 = _addr_and_keepalive(status, n)
+        a_bm, _, k1 = _addr_and_keepalive(bitmap, (n + 7) // 8, writable=True)
+        self._check(self._lib.kgv_status_to_bitmap(self._h, a_st, n, a_bm))
+        return bitmap
+
+    def gtable_entry(self, which, v):
+        out = (ctypes.c_uint8 * 64)()
+        self._check(self._lib.kgv_gtable_entry(self._h, which, v, ctypes.addressof(out)))
+        b = bytes(out)
+        return int.from_bytes(b[:32], "big"), int.from_bytes(b[32:], "big")
+
+
+def _nbytes(buf):
+    if hasattr(buf, "nbytes"):
+        return int(buf.nbytes)
+    if hasattr(buf, "numel"):
+        return int(buf.numel() * buf.element_size())
+    return len(buf)
