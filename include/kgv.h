@@ -56,9 +56,11 @@ typedef struct kgv_ctx kgv_ctx;
 /* One context per device.  Builds the generator window tables (8 MiB, L2 resident) on the GPU. */
 int kgv_create(int device, uint32_t flags, kgv_ctx** out);
 void kgv_destroy(kgv_ctx* ctx);
-/* Run all subsequent work of this context on the given cudaStream_t (NULL = the context's own
- * stream).  Lets a caller bracket kernels with its own events (bench.py passes torch's stream). */
+/* Run all subsequent work of this context on the given cudaStream_t (NULL = CUDA's default
+ * stream, as for any cudaStream_t).  Lets a caller bracket kernels with its own events (bench.py
+ * passes torch's stream).  kgv_reset_stream goes back to the context's private stream. */
 int kgv_set_stream(kgv_ctx* ctx, void* cuda_stream);
+int kgv_reset_stream(kgv_ctx* ctx);
 int kgv_synchronize(kgv_ctx* ctx);
 const char* kgv_last_error(const kgv_ctx* ctx);
 /* Number of kernel launches this context has issued so far (bench.py's gpu_launches). */
@@ -82,6 +84,14 @@ int kgv_status_to_bitmap(kgv_ctx* ctx, const uint8_t* status, size_t n, uint8_t*
 /* Test / audit hook: affine coordinates (x||y, 32-byte big-endian each) of entry v (1..65535) of
  * generator table `which` (0: v*G, 1: v*2^128*G) as built on the device. */
 int kgv_gtable_entry(kgv_ctx* ctx, int which, uint32_t v, uint8_t out_xy[64]);
+
+/* Test / audit hook: verifies ONE Schnorr triple (host pointers) on the device and returns the
+ * traced intermediates: trace_words[stage*16 + i], KGV_TRACE_STAGES stages of 16 u32 words
+ * (stage numbering in csrc/kgv_verify.cuh).  tests/ compare it with the host build of the same
+ * device code to localise a divergence. */
+#define KGV_TRACE_STAGES 32
+int kgv_debug_schnorr_trace(kgv_ctx* ctx, const uint8_t* pk32, const uint8_t* msg32, const uint8_t* sig64, uint32_t* trace_words,
+                            uint8_t* status);
 
 #ifdef __cplusplus
 }

@@ -19,6 +19,7 @@ SYMBOLS = [
     ("kgv_create", _c.c_int, [_c.c_int, _c.c_uint32, _c.POINTER(_c.c_void_p)]),
     ("kgv_destroy", None, [_c.c_void_p]),
     ("kgv_set_stream", _c.c_int, [_c.c_void_p, _c.c_void_p]),
+    ("kgv_reset_stream", _c.c_int, [_c.c_void_p]),
     ("kgv_synchronize", _c.c_int, [_c.c_void_p]),
     ("kgv_last_error", _c.c_char_p, [_c.c_void_p]),
     ("kgv_launch_count", _c.c_uint64, [_c.c_void_p]),
@@ -26,7 +27,9 @@ SYMBOLS = [
     ("kgv_ecdsa_verify", _c.c_int, [_c.c_void_p, _u8p, _u8p, _u8p, _c.c_size_t, _u8p]),
     ("kgv_status_to_bitmap", _c.c_int, [_c.c_void_p, _u8p, _c.c_size_t, _u8p]),
     ("kgv_gtable_entry", _c.c_int, [_c.c_void_p, _c.c_int, _c.c_uint32, _u8p]),
+    ("kgv_debug_schnorr_trace", _c.c_int, [_c.c_void_p, _u8p, _u8p, _u8p, _u8p, _u8p]),
 ]
+TRACE_STAGES = 32
 
 _lib = None
 

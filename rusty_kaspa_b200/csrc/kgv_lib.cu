@@ -115,6 +115,27 @@ k_ecdsa_verify(const uint8_t* __restrict__ pk, const uint8_t* __restrict__ msg, 
   status[i] = ecdsa_verify_core(tag, pkw, mw, sw, tab, gtab, GLoadDev());
 }
 
+// audit/debug: one signature, every traced intermediate written to dbg[stage*16 ..]
+struct DevTrace {
+  uint32_t* out;
+  __device__ __forceinline__ void operator()(int stage, const uint32_t* w, int n) const {
+    for (int i = 0; i < n && i < 16; i++) out[stage * 16 + i] = w[i];
+  }
+};
+__global__ void __launch_bounds__(KGV_BLOCK, KGV_BLOCKS_PER_SM)
+k_schnorr_trace(const uint8_t* __restrict__ pk, const uint8_t* __restrict__ msg, const uint8_t* __restrict__ sig,
+                uint8_t* __restrict__ status, const uint32_t* __restrict__ gtab, uint32_t* __restrict__ dbg) {
+  extern __shared__ uint32_t smem[];
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  uint32_t pkw[8], mw[8], sw[16];
+  load_be32<false>(pkw, pk);
+  load_be32<false>(mw, msg);
+  load_be32<false>(sw, sig);
+  load_be32<false>(sw + 8, sig + 32);
+  SmemTab tab{smem + threadIdx.x};
+  status[0] = schnorr_verify_core(pkw, mw, sw, tab, gtab, GLoadDev(), DevTrace{dbg});
+}
+
 __global__ void k_status_to_bitmap(const uint8_t* __restrict__ status, size_t n, uint8_t* __restrict__ bitmap) {
   size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t nbytes = (n + 7) / 8;
@@ -216,7 +237,14 @@ extern "C" void kgv_destroy(kgv_ctx* ctx) {
 extern "C" int kgv_set_stream(kgv_ctx* ctx, void* cuda_stream) {
   if (!ctx) return KGV_ERR_ARG;
   std::lock_guard<std::mutex> g(ctx->mu);
-  ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+  ctx->stream = (cudaStream_t)cuda_stream;  // NULL is CUDA's default stream, exactly as in cudaStream_t
+  return KGV_OK;
+}
+
+extern "C" int kgv_reset_stream(kgv_ctx* ctx) {
+  if (!ctx) return KGV_ERR_ARG;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  ctx->stream = ctx->own_stream;
   return KGV_OK;
 }
 
@@ -310,6 +338,32 @@ extern "C" int kgv_status_to_bitmap(kgv_ctx* ctx, const uint8_t* status, size_t 
     CK(cudaMemcpyAsync(bitmap, ddst, nbytes, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
   }
+  return KGV_OK;
+}
+
+extern "C" int kgv_debug_schnorr_trace(kgv_ctx* ctx, const uint8_t* pk32, const uint8_t* msg32, const uint8_t* sig64, uint32_t* trace_words,
+                                       uint8_t* status) {
+  if (!ctx) return KGV_ERR_ARG;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  if (!pk32 || !msg32 || !sig64 || !trace_words || !status) return fail_arg(ctx, "null buffer");
+  CK(cudaSetDevice(ctx->device));
+  const size_t tw = KGV_TRACE_STAGES * 16 * sizeof(uint32_t);
+  int rc = kgv_reserve(ctx, &ctx->d_in, &ctx->d_in_cap, 256);
+  if (rc) return rc;
+  rc = kgv_reserve(ctx, &ctx->d_out, &ctx->d_out_cap, tw + 256);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(ctx->d_in, pk32, 32, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->d_in + 32, msg32, 32, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->d_in + 64, sig64, 64, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemsetAsync(ctx->d_out, 0, tw + 256, ctx->stream));
+  const int smem = KGV_BLOCK * 128 * (int)sizeof(uint32_t);
+  CK(cudaFuncSetAttribute(k_schnorr_trace, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  k_schnorr_trace<<<1, KGV_BLOCK, smem, ctx->stream>>>(ctx->d_in, ctx->d_in + 32, ctx->d_in + 64, ctx->d_out + tw, ctx->gtab, (uint32_t*)ctx->d_out);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  CK(cudaMemcpyAsync(trace_words, ctx->d_out, tw, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(status, ctx->d_out + tw, 1, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
   return KGV_OK;
 }
 

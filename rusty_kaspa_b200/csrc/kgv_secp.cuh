@@ -35,6 +35,12 @@ struct gej {
   bool inf;
 };
 
+// Optional intermediate-value tracing (audit/debug kernels and the host unit tests use it to
+// compare device and host executions stage by stage); NoTrace compiles to nothing.
+struct NoTrace {
+  KGV_HD void operator()(int /*stage*/, const uint32_t* /*words*/, int /*n*/) const {}
+};
+
 // ------------------------------------------------------------------------------------------
 // scalars (mod n): only what verification needs
 // ------------------------------------------------------------------------------------------
@@ -386,16 +392,20 @@ KGV_HD void build_odd_table(Tab& tab, fe& zs, const fe& px, const fe& py) {
 // ------------------------------------------------------------------------------------------
 // gtab: [2][65536][16] u32 — affine (x limbs, y limbs) of v*G and v*2^128*G; entry 0 unused.
 // GLoad is a functor  void operator()(fe& x, fe& y, const uint32_t* entry)  (vectorised loads on device).
-template <class Tab, class GLoad>
+template <class Tab, class GLoad, class Trace = NoTrace>
 KGV_HD void ecmult_double(gej& R, fe& zs, const fe& px, const fe& py, const uint32_t* kP, const uint32_t* kG, Tab& tab,
-                          const uint32_t* gtab, GLoad gload) {
+                          const uint32_t* gtab, GLoad gload, Trace trace = Trace()) {
   const fe beta = {KGV_BETA_LIMBS};
   uint32_t m1[5], m2[5], h1[5], h2[5];
   bool neg1, neg2, fix1, fix2;
   glv_split(m1, neg1, m2, neg2, kP);
   recode_signed_odd(h1, fix1, m1);
   recode_signed_odd(h2, fix2, m2);
+  trace(10, m1, 5); trace(11, m2, 5);
+  { uint32_t f[4] = {neg1, neg2, fix1, fix2}; trace(12, f, 4); }
   build_odd_table(tab, zs, px, py);
+  trace(13, zs.v, 8);
+  { uint32_t e0[16]; for (int w = 0; w < 16; w++) e0[w] = tab.get(7, w); trace(14, e0, 16); }
   fe zs2, zs3;
   fe_sqr(zs2, zs);
   fe_mul(zs3, zs2, zs);
@@ -440,6 +450,7 @@ KGV_HD void ecmult_double(gej& R, fe& zs, const fe& px, const fe& py, const uint
       }
     }
   }
+  trace(15, R.x.v, 8); trace(16, R.y.v, 8); trace(17, R.z.v, 8);
   // parity corrections: m was replaced by m+1 => subtract one base point
   if (fix1) {
     fe ex, ey;

@@ -20,13 +20,15 @@ KGV_HD bool fe_words_lt_p(const uint32_t* v) {
 }
 
 // BIP-340 verification. pkw/mw: 8 big-endian words, sigw: 16 big-endian words (r || s).
-template <class Tab, class GLoad>
+template <class Tab, class GLoad, class Trace = NoTrace>
 KGV_HD uint8_t schnorr_verify_core(const uint32_t* pkw, const uint32_t* mw, const uint32_t* sigw, Tab& tab, const uint32_t* gtab,
-                                   GLoad gload) {
+                                   GLoad gload, Trace trace = Trace()) {
   fe px, py, rx;
   limbs_from_be_words(px.v, pkw);
   if (!fe_words_lt_p(px.v)) return KGV_ST_PK_PARSE;      // x >= p
+  trace(1, px.v, 8);
   if (!ge_lift_x(py, px, false)) return KGV_ST_PK_PARSE;  // not on the curve
+  trace(2, py.v, 8);
   limbs_from_be_words(rx.v, sigw);
   if (!fe_words_lt_p(rx.v)) return KGV_ST_INVALID;        // r >= p
   uint32_t s[8], e[8], k[8], ew[8];
@@ -37,10 +39,13 @@ KGV_HD uint8_t schnorr_verify_core(const uint32_t* pkw, const uint32_t* mw, cons
   for (int i = 0; i < 8; i++) e[7 - i] = ew[i];
   sc_reduce_once(e);
   sc_neg(k, e);                                           // R = s*G - e*P
+  trace(3, e, 8); trace(4, k, 8); trace(5, s, 8);
   gej R;
   fe zs;
-  ecmult_double(R, zs, px, py, k, s, tab, gtab, gload);
+  ecmult_double(R, zs, px, py, k, s, tab, gtab, gload, trace);
+  { uint32_t f[1] = {R.inf}; trace(18, f, 1); }
   if (R.inf) return KGV_ST_INVALID;
+  trace(19, R.x.v, 8); trace(20, R.y.v, 8); trace(21, R.z.v, 8);
   fe zt, zi, zi2, ax, ay;
   fe_mul(zt, R.z, zs);
   fe_inv(zi, zt);
@@ -49,8 +54,9 @@ KGV_HD uint8_t schnorr_verify_core(const uint32_t* pkw, const uint32_t* mw, cons
   fe_mul(ay, R.y, zi2);
   fe_mul(ay, ay, zi);
   fe_normalize(ay);
-  if (ay.v[0] & 1u) return KGV_ST_INVALID;                // y(R) odd
   fe_normalize(ax);
+  trace(22, ax.v, 8); trace(23, ay.v, 8);
+  if (ay.v[0] & 1u) return KGV_ST_INVALID;                // y(R) odd
   bool eq = true;
 #pragma unroll
   for (int i = 0; i < 8; i++) eq = eq && (ax.v[i] == rx.v[i]);

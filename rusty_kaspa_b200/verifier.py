@@ -111,6 +111,15 @@ class GpuContext:
         self._check(self._lib.kgv_status_to_bitmap(self._h, a_st, n, a_bm))
         return bitmap
 
+    def debug_schnorr_trace(self, pk32, msg32, sig64):
+        """(status, trace[32][16] uint32) of one triple verified on the device (audit hook)."""
+        tr = np.zeros((_lib.TRACE_STAGES, 16), dtype=np.uint32)
+        st = np.zeros(1, dtype=np.uint8)
+        bufs = [np.frombuffer(bytes(b), dtype=np.uint8).copy() for b in (pk32, msg32, sig64)]
+        self._check(self._lib.kgv_debug_schnorr_trace(self._h, bufs[0].ctypes.data, bufs[1].ctypes.data, bufs[2].ctypes.data,
+                                                      tr.ctypes.data, st.ctypes.data))
+        return int(st[0]), tr
+
     def gtable_entry(self, which, v):
         out = (ctypes.c_uint8 * 64)()
         self._check(self._lib.kgv_gtable_entry(self._h, which, v, ctypes.addressof(out)))

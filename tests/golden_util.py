@@ -1,0 +1,52 @@
+"""Helpers shared by the golden-vector tests: fixture loading and the tx dict <-> bytes conventions."""
+import gzip
+import json
+import os
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load(name):
+    path = os.path.join(GOLDEN, name)
+    if name.endswith(".gz"):
+        with gzip.open(path, "rt") as f:
+            return json.load(f)
+    with open(path) as f:
+        return json.load(f)
+
+
+def tx_from_json(t):
+    """hex strings -> bytes, in the dict layout oracle/pyref.py uses"""
+    return {"version": t["version"],
+            "inputs": [{"txid": bytes.fromhex(i["txid"]), "index": i["index"], "sigscript": bytes.fromhex(i["sigscript"]),
+                        "sequence": i["sequence"], "sig_op_count": i["sig_op_count"]} for i in t["inputs"]],
+            "outputs": [{"value": o["value"], "spk_version": o["spk_version"], "script": bytes.fromhex(o["script"])} for o in t["outputs"]],
+            "lock_time": t["lock_time"], "subnetwork_id": bytes.fromhex(t["subnetwork_id"]), "gas": t["gas"],
+            "payload": bytes.fromhex(t["payload"]), "mass": t.get("mass", 0)}
+
+
+def entry_from_json(e):
+    return {"amount": e["amount"], "spk_version": e["spk_version"], "script": bytes.fromhex(e["script"]),
+            "block_daa_score": e.get("block_daa_score", 0), "is_coinbase": e.get("is_coinbase", False)}
+
+
+def apply_sighash_action(tx, entries, action, arg):
+    """consensus/core/src/hashing/sighash.rs:655-679"""
+    if action == "Output":
+        tx["outputs"][arg]["value"] = 100
+    elif action == "Input":
+        tx["inputs"][arg]["index"] = 2
+    elif action == "AmountSpent":
+        entries[arg]["amount"] = 666
+    elif action == "PrevScriptPublicKey":
+        entries[arg]["script"] = entries[arg]["script"] + bytes([1, 2, 3])
+    elif action == "Sequence":
+        tx["inputs"][arg]["sequence"] = 12345
+    elif action == "Payload":
+        tx["payload"] = bytes([6, 6, 6, 4, 2, 0, 1, 3, 3, 7])
+    elif action == "Gas":
+        tx["gas"] = 1234
+    elif action == "SubnetworkId":
+        tx["subnetwork_id"] = bytes([6, 6, 6, 4, 2, 0, 1, 3, 3, 7]) + bytes(10)
+    else:
+        assert action == "NoAction"

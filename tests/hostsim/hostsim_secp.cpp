@@ -29,6 +29,18 @@ int hs_schnorr_verify(const uint8_t* pk, const uint8_t* msg, const uint8_t* sig)
   HostTab tab;
   return schnorr_verify_core(pkw, mw, sw, tab, (const uint32_t*)nullptr, HostGLoad());
 }
+struct HostTrace {
+  uint32_t* out;
+  void operator()(int stage, const uint32_t* w, int n) const { for (int i = 0; i < n && i < 16; i++) out[stage * 16 + i] = w[i]; }
+};
+// same layout as kgv_debug_schnorr_trace: out[32][16]
+int hs_schnorr_trace(const uint8_t* pk, const uint8_t* msg, const uint8_t* sig, uint32_t* out) {
+  uint32_t pkw[8], mw[8], sw[16];
+  be_words(pkw, pk, 8); be_words(mw, msg, 8); be_words(sw, sig, 16);
+  HostTab tab;
+  memset(out, 0, 32 * 16 * 4);
+  return schnorr_verify_core(pkw, mw, sw, tab, (const uint32_t*)nullptr, HostGLoad(), HostTrace{out});
+}
 int hs_ecdsa_verify(const uint8_t* pk33, const uint8_t* msg, const uint8_t* sig) {
   uint32_t pkw[8], mw[8], sw[16];
   be_words(pkw, pk33 + 1, 8); be_words(mw, msg, 8); be_words(sw, sig, 16);
