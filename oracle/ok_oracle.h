@@ -9,7 +9,7 @@
  *
  * Parity pinning: hashes, tx-id/tx-hash, sighash, the mainnet Schnorr P2PK and
  * 2-of-4 P2SH multisig KATs and the 224-input simpa fixture are pinned by the
- * reference's own vectors (tests/golden/*.json, tests/test_oracle_golden.py).
+ * reference's own vectors (tests/golden/ *.json, tests/test_oracle_golden.py).
  * ECDSA verdicts and the Schnorr edge encodings (r>=p, s>=n, off-curve pk) are
  * NOT covered by any stored vector in the reference: for those "parity
  * unpinned" — they are cross-checked against an independent big-int restatement
