@@ -7,7 +7,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libkgv.so")
+# KGV_LIB lets the tuning scripts in tools/ point at an alternative build of the same CUDA library
+LIB_PATH = os.environ.get("KGV_LIB", os.path.join(_HERE, "libkgv.so"))
 
 KGV_OK = 0
 SIG_INVALID, SIG_VALID, SIG_PK_PARSE_ERR, SIG_SIG_PARSE_ERR = 0, 1, 2, 3

@@ -421,7 +421,10 @@ KGV_HD void fe_reduce_wide(fe& r, const uint32_t* t) {
 // operands by value: ptxas keeps everything in registers across the call (no stack traffic), and
 // the kernels shrink from ~1.4 MB of straight-line SASS to a few tens of KB that stay in the
 // instruction cache.  The host unit-test build simply inlines them.
-#if defined(__CUDACC__)
+#ifndef KGV_NOINLINE_MUL
+#define KGV_NOINLINE_MUL 1
+#endif
+#if defined(__CUDACC__) && KGV_NOINLINE_MUL
 __device__ __noinline__ fe fe_mul_call(fe a, fe b) {
   fe r;
   uint32_t t[16];
@@ -514,7 +517,7 @@ KGV_HD void sqr_wide(uint32_t* t, const uint32_t* a) {
   for (int i = 0; i < 16; i++) t[i] = x[i];
 }
 
-#if defined(__CUDACC__)
+#if defined(__CUDACC__) && KGV_NOINLINE_MUL
 __device__ __noinline__ fe fe_sqr_call(fe a) {
   fe r;
   uint32_t t[16];

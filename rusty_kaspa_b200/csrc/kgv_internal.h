@@ -5,8 +5,12 @@
 #include <mutex>
 #include <string>
 
+#ifndef KGV_BLOCK
 #define KGV_BLOCK 128         // threads per block of the verification kernels
+#endif
+#ifndef KGV_BLOCKS_PER_SM
 #define KGV_BLOCKS_PER_SM 3   // 3 x 64 KiB of per-thread tables in shared memory
+#endif
 
 struct kgv_ctx {
   int device = 0;

@@ -250,7 +250,7 @@ KGV_HD void recoded_digit(const uint32_t* h, int i, uint32_t& idx, bool& neg) {
 // group law, Jacobian coordinates on y^2 = x^3 + b (a = 0; b never appears in the formulas,
 // so the same code runs on the isomorphic curves used for the per-thread tables)
 // ------------------------------------------------------------------------------------------
-KGV_HD void gej_double(gej& r) {
+KGV_HD void gej_double_body(gej& r) {
   if (r.inf) return;
   fe A, B, C, D, E, t;
   fe_sqr(A, r.x);
@@ -273,10 +273,20 @@ KGV_HD void gej_double(gej& r) {
   fe_sub(r.y, t, C);   // Y3 = E (D - X3) - 8 Y^4
 }
 
+#ifndef KGV_NOINLINE_POINT
+#define KGV_NOINLINE_POINT 1
+#endif
+#if defined(__CUDACC__) && KGV_NOINLINE_POINT
+__device__ __noinline__ gej gej_double_call(gej r) { gej_double_body(r); return r; }
+KGV_HD void gej_double(gej& r) { r = gej_double_call(r); }
+#else
+KGV_HD void gej_double(gej& r) { gej_double_body(r); }
+#endif
+
 // r += (bx,by) with the addend affine and never the point at infinity.  Handles r = inf,
 // r == addend (doubling) and r == -addend (result infinity).  If hout != nullptr it receives
 // the factor by which Z was multiplied (H), used by the table builder.
-KGV_HD void gej_add_ge(gej& r, const fe& bx, const fe& by, fe* hout = nullptr) {
+KGV_HD void gej_add_ge_body(gej& r, const fe& bx, const fe& by, fe* hout) {
   if (r.inf) {
     r.x = bx;
     r.y = by;
@@ -295,7 +305,7 @@ KGV_HD void gej_add_ge(gej& r, const fe& bx, const fe& by, fe* hout = nullptr) {
   if (fe_is_zero(h)) {
     if (hout) fe_set_u32(*hout, 1);
     if (fe_is_zero(rr)) {
-      gej_double(r);
+      gej_double_body(r);
       if (hout) fe_dbl(*hout, r.y);  // not used by the table builder (cannot happen there)
     } else {
       r.inf = true;
@@ -317,6 +327,16 @@ KGV_HD void gej_add_ge(gej& r, const fe& bx, const fe& by, fe* hout = nullptr) {
   fe_mul(hhh, r.y, hhh);
   fe_sub(r.y, t, hhh);    // Y3 = R (V - X3) - Y1 H^3
 }
+
+#if defined(__CUDACC__) && KGV_NOINLINE_POINT
+__device__ __noinline__ gej gej_add_ge_call(gej r, fe bx, fe by) { gej_add_ge_body(r, bx, by, nullptr); return r; }
+KGV_HD void gej_add_ge(gej& r, const fe& bx, const fe& by, fe* hout = nullptr) {
+  if (hout) gej_add_ge_body(r, bx, by, hout);
+  else r = gej_add_ge_call(r, bx, by);
+}
+#else
+KGV_HD void gej_add_ge(gej& r, const fe& bx, const fe& by, fe* hout = nullptr) { gej_add_ge_body(r, bx, by, hout); }
+#endif
 
 // y^2 = x^3 + 7: solve for y with the requested parity.  false if x is not on the curve.
 // x must be canonical (< p).

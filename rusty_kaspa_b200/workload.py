@@ -168,3 +168,70 @@ def tile_triples(pk, msg, sig, kind, n):
     reps = (n + len(pk) - 1) // len(pk)
     f = lambda a: np.ascontiguousarray(np.tile(a, (reps, 1))[:n])
     return f(pk), f(msg), f(sig), np.tile(kind, reps)[:n].copy()
+
+
+def ecdsa_triples(n, seed=0x6B61737061, n_keys=65536, n_nonces=65536, frac_bitflip=0.01, frac_adversarial=0.01, pools=None):
+    """ECDSA (pk33, msg32, sig64) triples for BASELINE config 4, same pool technique:
+    r = x(k_j*G) mod n, s = k_j^-1 (m + r*d_i) mod n, normalised to low S.
+    Adversarial kinds: high S, r >= n, s >= n, r = 0, s = 0, bad key tag, x(pk) >= p, off-curve pk."""
+    rng = np.random.default_rng(seed ^ 0xEC)
+    n_keys = min(n_keys, max(1, n))
+    n_nonces = min(n_nonces, max(1, n))
+    if pools is None:
+        pools = (ScalarPointPool(n_keys, seed, b"keys"), ScalarPointPool(n_nonces, seed, b"nonces"))
+    keys, nonces = pools
+    kinv = getattr(nonces, "inv", None)
+    if kinv is None:
+        kinv = nonces.inv = [pow(k, -1, N) for k in nonces.scalars]
+    msgs = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+    ki = rng.integers(0, keys.count, size=n)
+    ni = rng.integers(0, nonces.count, size=n)
+    u = rng.random(n)
+    kind = np.zeros(n, dtype=np.uint8)
+    kind[u < frac_bitflip + frac_adversarial] = KIND_ADVERSARIAL
+    kind[u < frac_bitflip] = KIND_BITFLIP
+    msg_bytes = msgs.tobytes()
+    pk_out = bytearray(33 * n)
+    sig_out = bytearray(64 * n)
+    half = N // 2
+    for i in range(n):
+        d = keys.scalars[ki[i]]
+        pkb = b"\x02" + keys.xs[ki[i]]  # pool points have even y
+        r = int.from_bytes(nonces.xs[ni[i]], "big") % N
+        m = int.from_bytes(msg_bytes[32 * i:32 * i + 32], "big") % N
+        s = kinv[ni[i]] * (m + r * d) % N
+        if s > half:
+            s = N - s
+        if kind[i] == KIND_ADVERSARIAL:
+            c = int(rng.integers(0, 8))
+            if c == 0:
+                s = N - s                       # high S: well-formed, rejected by verify
+            elif c == 1:
+                r = N + int(rng.integers(0, 2**62))  # r >= n: parse error
+            elif c == 2:
+                s = N + int(rng.integers(0, 2**62))  # s >= n: parse error
+            elif c == 3:
+                r = 0
+            elif c == 4:
+                s = 0
+            elif c == 5:
+                pkb = bytes([int(rng.choice([0, 1, 4, 6, 7, 0xFF]))]) + pkb[1:]
+            elif c == 6:
+                pkb = pkb[:1] + (P + int(rng.integers(0, 2**32 + 977))).to_bytes(32, "big")
+            else:
+                pkb = pkb[:1] + _non_residue_x(rng).to_bytes(32, "big")
+        pk_out[33 * i:33 * i + 33] = pkb
+        sig_out[64 * i:64 * i + 32] = r.to_bytes(32, "big")
+        sig_out[64 * i + 32:64 * i + 64] = s.to_bytes(32, "big")
+    pk = np.frombuffer(bytes(pk_out), dtype=np.uint8).reshape(n, 33).copy()
+    sig = np.frombuffer(bytes(sig_out), dtype=np.uint8).reshape(n, 64).copy()
+    for i in np.nonzero(kind == KIND_BITFLIP)[0]:
+        pos = int(rng.integers(0, 129 * 8))
+        byte, bit = pos >> 3, pos & 7
+        if byte < 33:
+            pk[i, byte] ^= 1 << bit
+        elif byte < 65:
+            msgs[i, byte - 33] ^= 1 << bit
+        else:
+            sig[i, byte - 65] ^= 1 << bit
+    return pk, msgs, sig, kind
