@@ -81,6 +81,73 @@ int kgv_ecdsa_verify(kgv_ctx* ctx, const uint8_t* pk33, const uint8_t* msg32, co
  * bitmap has (n+7)/8 bytes.  This is the per-shard payload of the multi-GPU all-gather. */
 int kgv_status_to_bitmap(kgv_ctx* ctx, const uint8_t* status, size_t n, uint8_t* bitmap);
 
+/* ------------------------------------------------------------------------------------------------
+ * Flat SoA transaction batches (little-endian, fixed-size records + one byte arena).
+ * Mirror of the reference data model: Transaction consensus/core/src/tx.rs:165-185,
+ * TransactionInput :93-101, TransactionOutpoint :72-77, TransactionOutput :121-125, UtxoEntry :49-57,
+ * ScriptPublicKey tx/script_public_key.rs:22-25.  Offsets point into `bytes`.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct {
+  uint32_t first_input, n_inputs;   /* range in inputs[]  */
+  uint32_t first_output, n_outputs; /* range in outputs[] */
+  uint64_t lock_time, gas;
+  uint64_t mass;                    /* committed storage mass (tx.mass()) */
+  uint32_t payload_off, payload_len;
+  uint16_t version;
+  uint8_t subnetwork_id[20];
+  uint8_t flags;                    /* bit 0: coinbase (informational; derived from subnetwork_id) */
+  uint8_t pad_;
+} kgv_tx; /* 72 bytes */
+typedef struct {
+  uint8_t prev_txid[32];
+  uint32_t prev_index;
+  uint32_t sigscript_off, sigscript_len;
+  uint8_t sig_op_count;
+  uint8_t pad_[3];
+  uint64_t sequence;
+} kgv_input; /* 56 bytes */
+typedef struct {
+  uint64_t value;
+  uint32_t script_off, script_len;
+  uint16_t spk_version;
+  uint8_t pad_[6];
+} kgv_output; /* 24 bytes */
+typedef struct {
+  uint64_t amount;
+  uint64_t block_daa_score;
+  uint32_t script_off, script_len;  /* script_public_key.script */
+  uint16_t spk_version;
+  uint8_t is_coinbase;
+  uint8_t pad_[5];
+} kgv_utxo_entry; /* 32 bytes */
+typedef struct {
+  const kgv_tx* txs; size_t n_txs;
+  const kgv_input* inputs; size_t n_inputs;
+  const kgv_output* outputs; size_t n_outputs;
+  const kgv_utxo_entry* entries; /* one populated entry per input (PopulatedTransaction), or NULL */
+  const uint8_t* bytes; size_t n_bytes;
+} kgv_tx_batch; /* the arrays are all host pointers or all device pointers */
+
+/* Transaction ids / hashes of every tx of the batch: out32 = n_txs * 32 bytes.
+ * Replaces consensus/core/src/hashing/tx.rs:16-42 (`hash`, `id`; keyed BLAKE2b). */
+int kgv_tx_ids(kgv_ctx* ctx, const kgv_tx_batch* batch, uint8_t* out32);
+int kgv_tx_hashes(kgv_ctx* ctx, const kgv_tx_batch* batch, uint8_t* out32);
+
+/* Signature hashes.  One item per signature check: `input` is the ABSOLUTE index into
+ * batch->inputs / batch->entries, hash_type one of 01 02 04 81 82 84 (anything else yields an
+ * all-0xFF digest, sighash_type.rs:50-56 InvalidSigHashType), ecdsa != 0 adds the
+ * SHA-256 wrap.  Replaces calc_schnorr_signature_hash / calc_ecdsa_signature_hash
+ * (consensus/core/src/hashing/sighash.rs:238-277); the five per-tx sub-hashes are computed once
+ * per transaction (SigHashReusedValues, sighash.rs:14-138). */
+typedef struct {
+  uint32_t tx;
+  uint32_t input;
+  uint8_t hash_type;
+  uint8_t ecdsa;
+  uint8_t pad_[2];
+} kgv_sighash_item; /* 12 bytes */
+int kgv_sighash(kgv_ctx* ctx, const kgv_tx_batch* batch, const kgv_sighash_item* items, size_t n_items, uint8_t* out32);
+
 /* Test / audit hook: affine coordinates (x||y, 32-byte big-endian each) of entry v (1..65535) of
  * generator table `which` (0: v*G, 1: v*2^128*G) as built on the device. */
 int kgv_gtable_entry(kgv_ctx* ctx, int which, uint32_t v, uint8_t out_xy[64]);
@@ -92,6 +159,12 @@ int kgv_gtable_entry(kgv_ctx* ctx, int which, uint32_t v, uint8_t out_xy[64]);
 #define KGV_TRACE_STAGES 32
 int kgv_debug_schnorr_trace(kgv_ctx* ctx, const uint8_t* pk32, const uint8_t* msg32, const uint8_t* sig64, uint32_t* trace_words,
                             uint8_t* status);
+
+/* Test / audit hook: runs one arithmetic primitive (its PTX body) on n operand pairs on the device.
+ * in_words / out_words: n x 16 u32 (a[8] || b[8] little-endian limbs in; result limbs out).
+ * op: 0 mul_wide 1 sqr_wide 2 fe_mul 3 fe_sqr 4 sc_mul 5 sc_sqr 6 sc_inv 7 fe_inv 8 fe_add 9 fe_sub
+ *     10 mul_wide+reduce mod n  11 glv_split. */
+int kgv_debug_selftest(kgv_ctx* ctx, int op, const uint32_t* in_words, uint32_t* out_words, size_t n);
 
 #ifdef __cplusplus
 }

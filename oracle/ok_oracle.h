@@ -63,6 +63,57 @@ int ok_ec_mul_xy(const uint8_t scalar32[32], const uint8_t px32[32], const uint8
 void ok_fe_mul_bytes(const uint8_t a[32], const uint8_t b[32], uint8_t out[32]);
 void ok_sc_mul_bytes(const uint8_t a[32], const uint8_t b[32], uint8_t out[32]);
 
+/* ---- transaction model (ok_tx.c) ----
+ * Flat SoA batch: the same memory layout the product ABI uses (include/kgv.h kgv_tx / kgv_input /
+ * kgv_output / kgv_utxo_entry), restated here so that tests can hand ONE set of numpy arrays to both
+ * sides.  Mirrors consensus/core/src/tx.rs:49-57,72-77,93-101,121-125,165-185. */
+typedef struct {
+  uint32_t first_input, n_inputs, first_output, n_outputs;
+  uint64_t lock_time, gas, mass;
+  uint32_t payload_off, payload_len;
+  uint16_t version;
+  uint8_t subnetwork_id[20];
+  uint8_t flags; /* unused by the oracle: coinbase-ness is derived from subnetwork_id */
+  uint8_t pad_;
+} ok_tx; /* 72 bytes */
+typedef struct {
+  uint8_t prev_txid[32];
+  uint32_t prev_index;
+  uint32_t sigscript_off, sigscript_len;
+  uint8_t sig_op_count;
+  uint8_t pad_[3];
+  uint64_t sequence;
+} ok_input; /* 56 bytes */
+typedef struct {
+  uint64_t value;
+  uint32_t script_off, script_len;
+  uint16_t spk_version;
+  uint8_t pad_[6];
+} ok_output; /* 24 bytes */
+typedef struct {
+  uint64_t amount;
+  uint64_t block_daa_score;
+  uint32_t script_off, script_len;
+  uint16_t spk_version;
+  uint8_t is_coinbase;
+  uint8_t pad_[5];
+} ok_utxo_entry; /* 32 bytes */
+typedef struct {
+  const ok_tx* txs; size_t n_txs;
+  const ok_input* inputs; size_t n_inputs;
+  const ok_output* outputs; size_t n_outputs;
+  const uint8_t* bytes; size_t n_bytes;
+} ok_batch;
+
+/* consensus/core/src/hashing/tx.rs:16-107 */
+void ok_tx_id(const ok_batch* b, size_t tx, uint8_t out[32]);
+void ok_tx_hash(const ok_batch* b, size_t tx, uint8_t out[32]);
+void ok_tx_ids(const ok_batch* b, uint8_t* out32, int nthreads);
+void ok_tx_hashes(const ok_batch* b, uint8_t* out32, int nthreads);
+/* consensus/core/src/hashing/sighash.rs:140-277; entries[] is indexed like b->inputs (one populated
+ * UTXO entry per input, scripts in b->bytes); input_index is relative to the tx. */
+void ok_sighash(const ok_batch* b, const ok_utxo_entry* entries, size_t tx, uint32_t input_index, uint8_t hash_type, int ecdsa, uint8_t out[32]);
+
 #ifdef __cplusplus
 }
 #endif

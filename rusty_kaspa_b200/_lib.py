@@ -27,7 +27,11 @@ SYMBOLS = [
     ("kgv_schnorr_verify", _c.c_int, [_c.c_void_p, _u8p, _u8p, _u8p, _c.c_size_t, _u8p]),
     ("kgv_ecdsa_verify", _c.c_int, [_c.c_void_p, _u8p, _u8p, _u8p, _c.c_size_t, _u8p]),
     ("kgv_status_to_bitmap", _c.c_int, [_c.c_void_p, _u8p, _c.c_size_t, _u8p]),
+    ("kgv_tx_ids", _c.c_int, [_c.c_void_p, _c.c_void_p, _u8p]),
+    ("kgv_tx_hashes", _c.c_int, [_c.c_void_p, _c.c_void_p, _u8p]),
+    ("kgv_sighash", _c.c_int, [_c.c_void_p, _c.c_void_p, _u8p, _c.c_size_t, _u8p]),
     ("kgv_gtable_entry", _c.c_int, [_c.c_void_p, _c.c_int, _c.c_uint32, _u8p]),
+    ("kgv_debug_selftest", _c.c_int, [_c.c_void_p, _c.c_int, _u8p, _u8p, _c.c_size_t]),
     ("kgv_debug_schnorr_trace", _c.c_int, [_c.c_void_p, _u8p, _u8p, _u8p, _u8p, _u8p]),
 ]
 TRACE_STAGES = 32

@@ -425,7 +425,7 @@ KGV_HD void fe_reduce_wide(fe& r, const uint32_t* t) {
 #define KGV_NOINLINE_MUL 1
 #endif
 #if defined(__CUDACC__) && KGV_NOINLINE_MUL
-__device__ __noinline__ fe fe_mul_call(fe a, fe b) {
+static __device__ __noinline__ fe fe_mul_call(fe a, fe b) {
   fe r;
   uint32_t t[16];
   mul_wide(t, a.v, b.v);
@@ -518,7 +518,7 @@ KGV_HD void sqr_wide(uint32_t* t, const uint32_t* a) {
 }
 
 #if defined(__CUDACC__) && KGV_NOINLINE_MUL
-__device__ __noinline__ fe fe_sqr_call(fe a) {
+static __device__ __noinline__ fe fe_sqr_call(fe a) {
   fe r;
   uint32_t t[16];
   sqr_wide(t, a.v);

@@ -21,6 +21,10 @@ struct kgv_ctx {
   size_t d_in_cap = 0;
   uint8_t* d_out = nullptr;
   size_t d_out_cap = 0;
+  uint8_t* d_batch = nullptr;   // staging for host-resident transaction batches
+  size_t d_batch_cap = 0;
+  uint8_t* d_scratch = nullptr; // per-call device scratch (sub-hashes, sig items, ...)
+  size_t d_scratch_cap = 0;
   uint64_t launches = 0;
   std::mutex mu;
   std::string err;
@@ -28,3 +32,16 @@ struct kgv_ctx {
 
 int kgv_ptr_is_device(const void* p);
 int kgv_reserve(kgv_ctx* ctx, uint8_t** buf, size_t* cap, size_t need);
+
+// ---- transaction batches on the device (kgv_hash.cu) ----
+#include "../../include/kgv.h"
+struct kgv_dev_batch {
+  const kgv_tx* txs;
+  const kgv_input* inputs;
+  const kgv_output* outputs;
+  const kgv_utxo_entry* entries;
+  const uint8_t* bytes;
+  size_t n_txs, n_inputs, n_outputs, n_bytes;
+};
+// Makes the batch arrays device-resident (uploads host arrays into ctx staging; wraps device arrays).
+int kgv_batch_to_device(kgv_ctx* ctx, const kgv_tx_batch* b, kgv_dev_batch* out, bool need_entries);

@@ -136,6 +136,38 @@ k_schnorr_trace(const uint8_t* __restrict__ pk, const uint8_t* __restrict__ msg,
   status[0] = schnorr_verify_core(pkw, mw, sw, tab, gtab, GLoadDev(), DevTrace{dbg});
 }
 
+// audit/debug: exercise the arithmetic primitives directly (PTX bodies) on caller-provided operands.
+// in: n items x 16 words (a[8], b[8]); out: n items x 16 words.
+__global__ void k_selftest(int op, const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t a[8], b[8], r[16];
+#pragma unroll
+  for (int k = 0; k < 8; k++) { a[k] = in[i * 16 + k]; b[k] = in[i * 16 + 8 + k]; }
+#pragma unroll
+  for (int k = 0; k < 16; k++) r[k] = 0;
+  fe fa, fb, fr;
+#pragma unroll
+  for (int k = 0; k < 8; k++) { fa.v[k] = a[k]; fb.v[k] = b[k]; }
+  switch (op) {
+    case 0: mul_wide(r, a, b); break;
+    case 1: sqr_wide(r, a); break;
+    case 2: fe_mul(fr, fa, fb); for (int k = 0; k < 8; k++) r[k] = fr.v[k]; break;
+    case 3: fe_sqr(fr, fa); for (int k = 0; k < 8; k++) r[k] = fr.v[k]; break;
+    case 4: sc_mul(r, a, b); break;
+    case 5: sc_sqr(r, a); break;
+    case 6: sc_inv(r, a); break;
+    case 7: fe_inv(fr, fa); for (int k = 0; k < 8; k++) r[k] = fr.v[k]; break;
+    case 8: fe_add(fr, fa, fb); for (int k = 0; k < 8; k++) r[k] = fr.v[k]; break;
+    case 9: fe_sub(fr, fa, fb); for (int k = 0; k < 8; k++) r[k] = fr.v[k]; break;
+    case 10: { uint32_t t[16]; mul_wide(t, a, b); sc_reduce512(r, t); } break;
+    case 11: { uint32_t k1[5], k2[5]; bool n1, n2; glv_split(k1, n1, k2, n2, a); for (int k = 0; k < 5; k++) { r[k] = k1[k]; r[8 + k] = k2[k]; } r[5] = n1; r[13] = n2; } break;
+    default: break;
+  }
+#pragma unroll
+  for (int k = 0; k < 16; k++) out[i * 16 + k] = r[k];
+}
+
 __global__ void k_status_to_bitmap(const uint8_t* __restrict__ status, size_t n, uint8_t* __restrict__ bitmap) {
   size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t nbytes = (n + 7) / 8;
@@ -230,6 +262,8 @@ extern "C" void kgv_destroy(kgv_ctx* ctx) {
   if (ctx->gtab) cudaFree(ctx->gtab);
   if (ctx->d_in) cudaFree(ctx->d_in);
   if (ctx->d_out) cudaFree(ctx->d_out);
+  if (ctx->d_batch) cudaFree(ctx->d_batch);
+  if (ctx->d_scratch) cudaFree(ctx->d_scratch);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
@@ -363,6 +397,24 @@ extern "C" int kgv_debug_schnorr_trace(kgv_ctx* ctx, const uint8_t* pk32, const 
   ctx->launches++;
   CK(cudaMemcpyAsync(trace_words, ctx->d_out, tw, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaMemcpyAsync(status, ctx->d_out + tw, 1, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return KGV_OK;
+}
+
+extern "C" int kgv_debug_selftest(kgv_ctx* ctx, int op, const uint32_t* in_words, uint32_t* out_words, size_t n) {
+  if (!ctx) return KGV_ERR_ARG;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  if (!in_words || !out_words || n == 0 || n > (1u << 20)) return fail_arg(ctx, "bad selftest arguments");
+  CK(cudaSetDevice(ctx->device));
+  int rc = kgv_reserve(ctx, &ctx->d_in, &ctx->d_in_cap, n * 64);
+  if (rc) return rc;
+  rc = kgv_reserve(ctx, &ctx->d_out, &ctx->d_out_cap, n * 64);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(ctx->d_in, in_words, n * 64, cudaMemcpyHostToDevice, ctx->stream));
+  k_selftest<<<(unsigned)((n + 63) / 64), 64, 0, ctx->stream>>>(op, (const uint32_t*)ctx->d_in, (uint32_t*)ctx->d_out, (int)n);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  CK(cudaMemcpyAsync(out_words, ctx->d_out, n * 64, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return KGV_OK;
 }

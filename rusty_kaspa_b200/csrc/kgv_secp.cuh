@@ -121,6 +121,40 @@ KGV_HD void sc_reduce512(uint32_t* r, const uint32_t* t) {
   }
   sc_reduce_once(r);
 }
+// As for fe_mul / fe_sqr, the device versions are real functions (operands by value, in registers).
+struct sc8 { uint32_t v[8]; };
+#if defined(__CUDACC__) && KGV_NOINLINE_MUL
+static __device__ __noinline__ sc8 sc_mul_call(sc8 a, sc8 b) {
+  sc8 r;
+  uint32_t t[16];
+  mul_wide(t, a.v, b.v);
+  sc_reduce512(r.v, t);
+  return r;
+}
+static __device__ __noinline__ sc8 sc_sqr_call(sc8 a) {
+  sc8 r;
+  uint32_t t[16];
+  sqr_wide(t, a.v);
+  sc_reduce512(r.v, t);
+  return r;
+}
+KGV_HD void sc_mul(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+  sc8 x, y;
+#pragma unroll
+  for (int i = 0; i < 8; i++) { x.v[i] = a[i]; y.v[i] = b[i]; }
+  sc8 z = sc_mul_call(x, y);
+#pragma unroll
+  for (int i = 0; i < 8; i++) r[i] = z.v[i];
+}
+KGV_HD void sc_sqr(uint32_t* r, const uint32_t* a) {
+  sc8 x;
+#pragma unroll
+  for (int i = 0; i < 8; i++) x.v[i] = a[i];
+  sc8 z = sc_sqr_call(x);
+#pragma unroll
+  for (int i = 0; i < 8; i++) r[i] = z.v[i];
+}
+#else
 KGV_HD void sc_mul(uint32_t* r, const uint32_t* a, const uint32_t* b) {
   uint32_t t[16];
   mul_wide(t, a, b);
@@ -131,6 +165,7 @@ KGV_HD void sc_sqr(uint32_t* r, const uint32_t* a) {
   sqr_wide(t, a);
   sc_reduce512(r, t);
 }
+#endif
 // r = a^(n-2) mod n (a != 0). The exponent is public and identical in every lane: no divergence.
 KGV_HD void sc_inv(uint32_t* r, const uint32_t* a) {
   // n - 2
@@ -277,7 +312,7 @@ KGV_HD void gej_double_body(gej& r) {
 #define KGV_NOINLINE_POINT 1
 #endif
 #if defined(__CUDACC__) && KGV_NOINLINE_POINT
-__device__ __noinline__ gej gej_double_call(gej r) { gej_double_body(r); return r; }
+static __device__ __noinline__ gej gej_double_call(gej r) { gej_double_body(r); return r; }
 KGV_HD void gej_double(gej& r) { r = gej_double_call(r); }
 #else
 KGV_HD void gej_double(gej& r) { gej_double_body(r); }
@@ -329,7 +364,7 @@ KGV_HD void gej_add_ge_body(gej& r, const fe& bx, const fe& by, fe* hout) {
 }
 
 #if defined(__CUDACC__) && KGV_NOINLINE_POINT
-__device__ __noinline__ gej gej_add_ge_call(gej r, fe bx, fe by) { gej_add_ge_body(r, bx, by, nullptr); return r; }
+static __device__ __noinline__ gej gej_add_ge_call(gej r, fe bx, fe by) { gej_add_ge_body(r, bx, by, nullptr); return r; }
 KGV_HD void gej_add_ge(gej& r, const fe& bx, const fe& by, fe* hout = nullptr) {
   if (hout) gej_add_ge_body(r, bx, by, hout);
   else r = gej_add_ge_call(r, bx, by);

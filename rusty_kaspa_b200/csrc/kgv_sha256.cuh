@@ -7,7 +7,7 @@
 namespace kgv {
 
 #if defined(__CUDACC__)
-__device__ __constant__ uint32_t kSha256K[64] = {
+static __device__ __constant__ uint32_t kSha256K[64] = {
 #else
 static const uint32_t kSha256K[64] = {
 #endif

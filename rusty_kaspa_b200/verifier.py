@@ -37,6 +37,24 @@ def _addr_and_keepalive(buf, nbytes, writable=False):
     return arr.ctypes.data, False, arr
 
 
+class _KgvTxBatch(ctypes.Structure):
+    _fields_ = [("txs", ctypes.c_void_p), ("n_txs", ctypes.c_size_t), ("inputs", ctypes.c_void_p), ("n_inputs", ctypes.c_size_t),
+                ("outputs", ctypes.c_void_p), ("n_outputs", ctypes.c_size_t), ("entries", ctypes.c_void_p),
+                ("bytes", ctypes.c_void_p), ("n_bytes", ctypes.c_size_t)]
+
+
+SIGHASH_ITEM_DTYPE = np.dtype([("tx", "<u4"), ("input", "<u4"), ("hash_type", "u1"), ("ecdsa", "u1"), ("pad_", "u1", (2,))])
+assert SIGHASH_ITEM_DTYPE.itemsize == 12
+
+
+def _c_batch(b, with_entries=True):
+    """ctypes view of a txbatch.TxBatch (host arrays)."""
+    cb = _KgvTxBatch(b.txs.ctypes.data, len(b.txs), b.inputs.ctypes.data, len(b.inputs), b.outputs.ctypes.data, len(b.outputs),
+                     b.entries.ctypes.data if (with_entries and b.entries is not None) else None, b.arena.ctypes.data, len(b.arena))
+    cb._keep = b
+    return cb
+
+
 class GpuContext:
     """One per device; wraps kgv_create/kgv_destroy. Fails loudly without a CUDA device."""
 
@@ -110,6 +128,45 @@ class GpuContext:
         a_bm, _, k1 = _addr_and_keepalive(bitmap, (n + 7) // 8, writable=True)
         self._check(self._lib.kgv_status_to_bitmap(self._h, a_st, n, a_bm))
         return bitmap
+
+    # -- transaction hashing ----------------------------------------------------------------------
+    def tx_ids(self, batch):
+        """(n_txs, 32) uint8: Transaction::id() of every tx (consensus/core/src/hashing/tx.rs:30-42)."""
+        out = np.zeros((batch.n_txs, 32), dtype=np.uint8)
+        cb = _c_batch(batch, with_entries=False)
+        self._check(self._lib.kgv_tx_ids(self._h, ctypes.byref(cb), out.ctypes.data))
+        return out
+
+    def tx_hashes(self, batch):
+        """(n_txs, 32) uint8: hashing::tx::hash of every tx (consensus/core/src/hashing/tx.rs:16-20)."""
+        out = np.zeros((batch.n_txs, 32), dtype=np.uint8)
+        cb = _c_batch(batch, with_entries=False)
+        self._check(self._lib.kgv_tx_hashes(self._h, ctypes.byref(cb), out.ctypes.data))
+        return out
+
+    def sighash(self, batch, items):
+        """items: array of SIGHASH_ITEM_DTYPE or list of (tx, abs_input, hash_type, ecdsa). Returns (n, 32) uint8."""
+        if not isinstance(items, np.ndarray):
+            arr = np.zeros(len(items), dtype=SIGHASH_ITEM_DTYPE)
+            for i, (t, a, h, e) in enumerate(items):
+                arr[i] = (t, a, h, 1 if e else 0, (0, 0))
+            items = arr
+        out = np.zeros((len(items), 32), dtype=np.uint8)
+        cb = _c_batch(batch)
+        self._check(self._lib.kgv_sighash(self._h, ctypes.byref(cb), items.ctypes.data, len(items), out.ctypes.data))
+        return out
+
+    def debug_selftest(self, op, a_vals, b_vals):
+        """Runs arithmetic primitive `op` (include/kgv.h) on the device for lists of 256-bit ints; returns 512-bit ints."""
+        n = len(a_vals)
+        inp = np.zeros((n, 16), dtype=np.uint32)
+        for i, (a, b) in enumerate(zip(a_vals, b_vals)):
+            for k in range(8):
+                inp[i, k] = (a >> (32 * k)) & 0xFFFFFFFF
+                inp[i, 8 + k] = (b >> (32 * k)) & 0xFFFFFFFF
+        out = np.zeros((n, 16), dtype=np.uint32)
+        self._check(self._lib.kgv_debug_selftest(self._h, int(op), inp.ctypes.data, out.ctypes.data, n))
+        return [sum(int(out[i, k]) << (32 * k) for k in range(16)) for i in range(n)]
 
     def debug_schnorr_trace(self, pk32, msg32, sig64):
         """(status, trace[32][16] uint32) of one triple verified on the device (audit hook)."""

@@ -235,3 +235,29 @@ def ecdsa_triples(n, seed=0x6B61737061, n_keys=65536, n_nonces=65536, frac_bitfl
         else:
             sig[i, byte - 65] ^= 1 << bit
     return pk, msgs, sig, kind
+
+
+# ------------------------------------------------------------------------------------------------
+# random transactions for the hashing kernels (shape-only: arbitrary scripts / payloads)
+# ------------------------------------------------------------------------------------------------
+def random_transactions(n, seed=1, max_inputs=4, max_outputs=4, max_script=80, max_payload=300):
+    """n arbitrary transactions + a populated entry per input (ragged sizes, empty scripts/payloads,
+    coinbase / native / other subnetworks, non-zero mass) for tx-id / tx-hash / sighash parity tests."""
+    rng = np.random.default_rng(seed)
+    rb = lambda k: rng.integers(0, 256, size=int(k), dtype=np.uint8).tobytes()
+    txs, entries = [], []
+    for t in range(n):
+        kind = int(rng.integers(0, 10))
+        subnet = bytes(20) if kind < 7 else (bytes([1]) + bytes(19) if kind == 7 else rb(20))
+        n_in = 0 if (kind == 7 and rng.random() < 0.5) else int(rng.integers(0 if kind >= 7 else 1, max_inputs + 1))
+        n_out = int(rng.integers(0, max_outputs + 1))
+        ins = [{"txid": rb(32), "index": int(rng.integers(0, 2**32)), "sigscript": rb(rng.integers(0, max_script)),
+                "sequence": int(rng.integers(0, 2**63)) * 2 + int(rng.integers(0, 2)), "sig_op_count": int(rng.integers(0, 256))} for _ in range(n_in)]
+        outs = [{"value": int(rng.integers(0, 2**62)), "spk_version": int(rng.integers(0, 3)), "script": rb(rng.integers(0, max_script))} for _ in range(n_out)]
+        payload = b"" if rng.random() < 0.5 else rb(rng.integers(1, max_payload))
+        txs.append({"version": int(rng.integers(0, 3)), "inputs": ins, "outputs": outs, "lock_time": int(rng.integers(0, 2**62)),
+                    "subnetwork_id": subnet, "gas": int(rng.integers(0, 2**40)), "payload": payload,
+                    "mass": 0 if rng.random() < 0.5 else int(rng.integers(1, 2**40))})
+        entries.append([{"amount": int(rng.integers(0, 2**62)), "spk_version": int(rng.integers(0, 2)), "script": rb(rng.integers(0, max_script)),
+                         "block_daa_score": int(rng.integers(0, 2**40)), "is_coinbase": bool(rng.integers(0, 2))} for _ in range(n_in)])
+    return txs, entries

@@ -1,0 +1,84 @@
+"""The C oracle against the reference's own vectors (tests/golden, produced by make_golden.py)."""
+import copy
+import ctypes
+
+import numpy as np
+
+import oracle_tx
+import pyref
+from golden_util import apply_sighash_action, entry_from_json, load, tx_from_json
+from rusty_kaspa_b200.txbatch import build_batch
+
+
+def test_hashers_incremental(oracle):
+    g = load("hashers.json")
+    inputs = [bytes.fromhex(h) for h in g["inputs_hex"]]
+    blake = {"TransactionHash", "TransactionID", "TransactionSigningHash", "BlockHash", "MerkleBranchHash"}
+    o = ctypes.create_string_buffer(32)
+    seen = 0
+    for v in g["vectors"]:
+        acc = b""
+        for data, exp in zip(inputs, v["expected"]):
+            acc += data
+            if v["hasher"] in blake:
+                oracle.ok_blake2b_keyed(v["hasher"].encode(), acc, len(acc), o)
+            elif v["hasher"] == "TransactionSigningHashECDSA":
+                oracle.ok_sha256_domain(b"TransactionSigningHashECDSA", acc, len(acc), o)
+            else:
+                continue
+            assert o.raw.hex() == exp, (v["hasher"], len(acc))
+            seen += 1
+    assert seen == 30
+
+
+def test_tx_id_and_hash(oracle):
+    vec = load("tx_hashing.json")["vectors"]
+    b = build_batch([tx_from_json(v["tx"]) for v in vec])
+    ids, hashes = oracle_tx.tx_ids(oracle, b), oracle_tx.tx_hashes(oracle, b, threads=3)
+    for i, v in enumerate(vec):
+        assert ids[i].tobytes().hex() == v["expected_id"], i
+        assert hashes[i].tobytes().hex() == v["expected_hash"], i
+
+
+def test_sighash_vectors(oracle):
+    g = load("sighash.json")
+    for v in g["vectors"]:
+        tx = tx_from_json(g[v["tx"]])
+        entries = [entry_from_json(e) for e in g["entries"]]
+        apply_sighash_action(tx, entries, v["action"], v["action_arg"])
+        b = build_batch([tx], [entries])
+        assert oracle_tx.sighash(oracle, b, 0, v["input_index"], v["hash_type"]).hex() == v["expected"], v["name"]
+        # the ECDSA wrap is pinned by the hasher vectors; cross-check the composition against the twin
+        assert oracle_tx.sighash(oracle, b, 0, v["input_index"], v["hash_type"], ecdsa=True) == pyref.sighash_ecdsa(tx, entries, v["input_index"], v["hash_type"])
+
+
+def test_simpa_dag_every_signed_input_verifies(oracle):
+    """224 signed inputs of the reference's simpa-generated DAG fixture: tx ids recomputed, prevouts resolved
+    inside the DAG, sighash + BIP-340 verify must accept every one (the reference's json_test asserts the
+    whole DAG is UTXO-valid)."""
+    g = load("simpa_goref_1060.json.gz")
+    txs = [tx_from_json(t) for blk in g["blocks"] for t in blk["transactions"]]
+    b0 = build_batch(txs)
+    ids = oracle_tx.tx_ids(oracle, b0, threads=4)
+    by_id = {ids[i].tobytes(): t for i, t in enumerate(txs)}
+    spend, entries = [], []
+    for t in txs:
+        if not t["inputs"]:
+            continue
+        ents = []
+        for i in t["inputs"]:
+            prev = by_id[i["txid"]]
+            o = prev["outputs"][i["index"]]
+            ents.append({"amount": o["value"], "spk_version": o["spk_version"], "script": o["script"]})
+        spend.append(t)
+        entries.append(ents)
+    b = build_batch(spend, entries)
+    n = 0
+    for ti, t in enumerate(spend):
+        for k, i in enumerate(t["inputs"]):
+            ss, spk = i["sigscript"], entries[ti][k]["script"]
+            assert len(ss) == 66 and ss[0] == 0x41 and len(spk) == 34 and spk[0] == 0x20 and spk[33] == 0xAC
+            msg = oracle_tx.sighash(oracle, b, ti, k, ss[65])
+            assert oracle.ok_schnorr_verify(spk[1:33], msg, ss[1:65]) == 1
+            n += 1
+    assert n == 224
