@@ -114,6 +114,46 @@ void ok_tx_hashes(const ok_batch* b, uint8_t* out32, int nthreads);
  * UTXO entry per input, scripts in b->bytes); input_index is relative to the tx. */
 void ok_sighash(const ok_batch* b, const ok_utxo_entry* entries, size_t tx, uint32_t input_index, uint8_t hash_type, int ecdsa, uint8_t out[32]);
 
+/* ---- UTXO state, transaction validation in UTXO context (ok_validate.c) ----
+ * Status / error numbering is shared with include/kgv.h (KGV_TX_*, KGV_SCRIPT_*). */
+enum { OK_TX_OK = 0, OK_TX_MISSING_OUTPOINTS = 1, OK_TX_IMMATURE_COINBASE = 2, OK_TX_INPUT_AMOUNT_OVERFLOW = 3,
+       OK_TX_INPUT_AMOUNT_TOO_HIGH = 4, OK_TX_SPEND_TOO_HIGH = 5, OK_TX_MASS_INCOMPUTABLE = 6, OK_TX_WRONG_MASS = 7,
+       OK_TX_SEQUENCE_LOCK = 8, OK_TX_SIGNATURE_INVALID = 9, OK_TX_SIGNATURE_EMPTY = 10, OK_TX_NEEDS_HOST_VM = 11, OK_TX_SKIPPED_COINBASE = 12 };
+enum { OK_SCRIPT_OK = 0, OK_SCRIPT_EVAL_FALSE = 1, OK_SCRIPT_NULL_FAIL = 2, OK_SCRIPT_INVALID_SIGNATURE = 3, OK_SCRIPT_SIG_LENGTH = 4,
+       OK_SCRIPT_PUBKEY_FORMAT = 5, OK_SCRIPT_INVALID_SIGHASH_TYPE = 6, OK_SCRIPT_EXCEEDED_SIGOP_LIMIT = 7, OK_SCRIPT_NONSTANDARD = 255 };
+enum { OK_FLAGS_FULL = 0, OK_FLAGS_SKIP_SCRIPT_CHECKS = 1, OK_FLAGS_SKIP_MASS_CHECK = 2 };
+typedef struct { uint64_t coinbase_maturity, storage_mass_parameter, max_sompi; } ok_params;
+typedef struct { uint64_t fee; uint32_t fail_input; uint8_t status, script_err, pad_[2]; } ok_tx_result; /* 16 bytes */
+
+/* Script check of ONE input for the standard script classes (P2PK Schnorr, P2PK ECDSA, P2SH m-of-n
+ * multisig), following TxScriptEngine::execute for exactly these shapes (crypto/txscript/src/lib.rs:399-643,
+ * opcodes/mod.rs:746-808, script_class.rs:58-82).  Anything else returns OK_SCRIPT_NONSTANDARD. */
+int ok_check_script_std(const ok_batch* b, const ok_utxo_entry* entries, size_t tx, uint32_t input_index);
+
+/* storage mass, consensus/core/src/mass/mod.rs:338-410. returns 0 and *mass on success, -1 if incomputable */
+int ok_storage_mass(const ok_batch* b, const ok_utxo_entry* entries, size_t tx, uint64_t storm_param, uint64_t* mass);
+
+/* validate_populated_transaction_and_get_fee (tx_validation_in_utxo_context.rs:34-61) with entries given. */
+void ok_validate_populated(const ok_batch* b, const ok_utxo_entry* entries, size_t tx, uint64_t pov_daa_score, int flags, const ok_params* p, ok_tx_result* out);
+
+/* UTXO state = base set composed with one diff layer (utxo_view.rs:22-35, utxo_diff.rs:15-19,233-269,
+ * model/stores/utxo_set.rs:107-112). */
+typedef struct ok_state ok_state;
+ok_state* ok_state_new(void);
+void ok_state_free(ok_state* s);
+/* validate_transactions_in_parallel (utxo_validation.rs:262-338): every non-coinbase tx of the batch against
+ * the composed view; results[i] for tx i (coinbase: OK_TX_SKIPPED_COINBASE). */
+void ok_state_validate(ok_state* s, const ok_batch* b, uint64_t pov_daa_score, int flags, const ok_params* p, ok_tx_result* results, int nthreads);
+/* mergeset_diff.add_transaction for every tx with accept[i] != 0 (utxo_diff.rs:233-247). returns 0, or -1 on a UtxoAlgebraError */
+int ok_state_accept(ok_state* s, const ok_batch* b, const uint8_t* accept, uint64_t pov_daa_score);
+/* write_diff_batch: fold the diff into the base (utxo_set.rs:107-112) */
+void ok_state_commit(ok_state* s);
+/* composed get: returns 1 if found (entry header + script bytes copied, script_cap bytes max) */
+int ok_state_get(const ok_state* s, const uint8_t key36[36], ok_utxo_entry* e, uint8_t* script, size_t script_cap);
+uint64_t ok_state_count(const ok_state* s);
+/* order-independent digest of the composed set: sum mod 2^256 of the MuHashElement hashes (consensus/core/src/muhash.rs:47-59) */
+void ok_state_digest(const ok_state* s, uint8_t out[32]);
+
 #ifdef __cplusplus
 }
 #endif
