@@ -148,6 +148,91 @@ typedef struct {
 } kgv_sighash_item; /* 12 bytes */
 int kgv_sighash(kgv_ctx* ctx, const kgv_tx_batch* batch, const kgv_sighash_item* items, size_t n_items, uint8_t* out32);
 
+/* ------------------------------------------------------------------------------------------------
+ * UTXO-context validation (the rayon fan-out of utxo_validation.rs:262-338 as a batch call)
+ * ------------------------------------------------------------------------------------------------ */
+/* per-transaction verdicts = TxRuleError classes (consensus/core/src/errors/tx.rs:8-103) reachable from
+ * validate_transaction_in_utxo_context (utxo_validation.rs:312-338) */
+#define KGV_TX_OK 0
+#define KGV_TX_MISSING_OUTPOINTS 1      /* MissingTxOutpoints                */
+#define KGV_TX_IMMATURE_COINBASE 2      /* ImmatureCoinbaseSpend             */
+#define KGV_TX_INPUT_AMOUNT_OVERFLOW 3  /* InputAmountOverflow               */
+#define KGV_TX_INPUT_AMOUNT_TOO_HIGH 4  /* InputAmountTooHigh                */
+#define KGV_TX_SPEND_TOO_HIGH 5         /* SpendTooHigh                      */
+#define KGV_TX_MASS_INCOMPUTABLE 6      /* MassIncomputable                  */
+#define KGV_TX_WRONG_MASS 7             /* WrongMass                         */
+#define KGV_TX_SEQUENCE_LOCK 8          /* SequenceLockConditionsAreNotMet   */
+#define KGV_TX_SIGNATURE_INVALID 9      /* SignatureInvalid(script_err)      */
+#define KGV_TX_SIGNATURE_EMPTY 10       /* SignatureEmpty(script_err)        */
+#define KGV_TX_NEEDS_HOST_VM 11         /* an input is not one of the GPU fast-path script classes: the host
+                                           script engine must decide this transaction (all context checks passed) */
+#define KGV_TX_SKIPPED_COINBASE 12      /* coinbase transactions are skipped (utxo_validation.rs:273) */
+/* script errors = TxScriptError variants the standard classes can produce (crypto/txscript/errors) */
+#define KGV_SCRIPT_OK 0
+#define KGV_SCRIPT_EVAL_FALSE 1
+#define KGV_SCRIPT_NULL_FAIL 2
+#define KGV_SCRIPT_INVALID_SIGNATURE 3
+#define KGV_SCRIPT_SIG_LENGTH 4
+#define KGV_SCRIPT_PUBKEY_FORMAT 5
+#define KGV_SCRIPT_INVALID_SIGHASH_TYPE 6
+#define KGV_SCRIPT_EXCEEDED_SIGOP_LIMIT 7
+#define KGV_SCRIPT_NONSTANDARD 255
+/* TxValidationFlags (tx_validation_in_utxo_context.rs:20-31) */
+#define KGV_FLAGS_FULL 0
+#define KGV_FLAGS_SKIP_SCRIPT_CHECKS 1
+#define KGV_FLAGS_SKIP_MASS_CHECK 2
+
+typedef struct {
+  uint64_t coinbase_maturity;       /* Params::coinbase_maturity      */
+  uint64_t storage_mass_parameter;  /* Params::storage_mass_parameter */
+  uint64_t max_sompi;               /* constants::MAX_SOMPI           */
+} kgv_params;
+typedef struct {
+  uint64_t fee;        /* calculated_fee (valid when status == KGV_TX_OK) */
+  uint32_t fail_input; /* first failing input (index within the tx) for status 2, 9, 10, 11 */
+  uint8_t status;      /* KGV_TX_*     */
+  uint8_t script_err;  /* KGV_SCRIPT_* */
+  uint8_t pad_[2];
+} kgv_tx_result; /* 16 bytes */
+
+/* validate_populated_transaction_and_get_fee for every tx of a batch whose entries are already
+ * populated (batch->entries != NULL) — tx_validation_in_utxo_context.rs:34-61 incl. check_scripts
+ * (:157-196) for the standard script classes.  results: n_txs records. */
+int kgv_validate_populated(kgv_ctx* ctx, const kgv_tx_batch* batch, uint64_t pov_daa_score, uint32_t flags, const kgv_params* params,
+                           kgv_tx_result* results);
+
+/* GPU-resident UTXO set: open-addressed hash table keyed by the 36-byte outpoint (txid || index LE),
+ * 128-byte slots (entry + up to 68 script bytes inline, longer scripts in an overflow arena).
+ * It plays the role of the base layer of every composed view: DbUtxoSetStore
+ * (consensus/src/model/stores/utxo_set.rs:31-44,107-112,143-152) and UtxoCollection
+ * (consensus/core/src/utxo/utxo_collection.rs:5,28-32). */
+typedef struct kgv_utxo_table kgv_utxo_table;
+int kgv_utxo_create(kgv_ctx* ctx, uint64_t capacity_slots /* rounded up to a power of two */, kgv_utxo_table** out);
+void kgv_utxo_destroy(kgv_ctx* ctx, kgv_utxo_table* t);
+/* UtxoView::get for n outpoints: found[i] in {0,1}; entries[i].script_off = i*script_stride into scripts_out
+ * (scripts longer than script_stride are truncated there; script_len is always the true length). */
+int kgv_utxo_lookup(kgv_ctx* ctx, kgv_utxo_table* t, const uint8_t* keys36, size_t n, kgv_utxo_entry* entries, uint8_t* scripts_out,
+                    uint32_t script_stride, uint8_t* found);
+/* write_diff_batch (utxo_set.rs:107-112): delete the removed outpoints, then put the added ones.
+ * add_entries[i].script_off/len point into add_bytes.  Keys of one call must be distinct.
+ * rem_status[i]: 1 = was present, 0 = absent; add_status[i]: 1 = inserted, 2 = replaced an existing entry. */
+int kgv_utxo_apply_diff(kgv_ctx* ctx, kgv_utxo_table* t, const uint8_t* rem_keys36, size_t n_rem, uint8_t* rem_status,
+                        const uint8_t* add_keys36, const kgv_utxo_entry* add_entries, const uint8_t* add_bytes, size_t n_add_bytes, size_t n_add,
+                        uint8_t* add_status);
+/* number of live entries, and an order-independent digest of the set: the sum modulo 2^256 of the keyed
+ * BLAKE2b "MuHashElement" hashes of every (outpoint, entry) (consensus/core/src/muhash.rs:47-59). */
+int kgv_utxo_count(kgv_ctx* ctx, kgv_utxo_table* t, uint64_t* count);
+int kgv_utxo_digest(kgv_ctx* ctx, kgv_utxo_table* t, uint8_t out32[32]);
+
+/* validate_transactions_in_parallel (utxo_validation.rs:262-278) against the table: populate every input
+ * by table lookup (:319-327), then as kgv_validate_populated.  batch->entries is ignored. */
+int kgv_validate_txs(kgv_ctx* ctx, kgv_utxo_table* t, const kgv_tx_batch* batch, uint64_t pov_daa_score, uint32_t flags, const kgv_params* params,
+                     kgv_tx_result* results);
+/* UtxoDiff::add_transaction (utxo_diff.rs:233-247) applied directly to the table for every tx with
+ * accept[i] != 0: spent outpoints are erased, outputs inserted with block_daa_score = pov_daa_score and
+ * is_coinbase of the tx (tx ids are computed on the device). */
+int kgv_utxo_apply_accepted(kgv_ctx* ctx, kgv_utxo_table* t, const kgv_tx_batch* batch, const uint8_t* accept, uint64_t pov_daa_score);
+
 /* Test / audit hook: affine coordinates (x||y, 32-byte big-endian each) of entry v (1..65535) of
  * generator table `which` (0: v*G, 1: v*2^128*G) as built on the device. */
 int kgv_gtable_entry(kgv_ctx* ctx, int which, uint32_t v, uint8_t out_xy[64]);

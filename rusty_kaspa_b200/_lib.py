@@ -30,6 +30,15 @@ SYMBOLS = [
     ("kgv_tx_ids", _c.c_int, [_c.c_void_p, _c.c_void_p, _u8p]),
     ("kgv_tx_hashes", _c.c_int, [_c.c_void_p, _c.c_void_p, _u8p]),
     ("kgv_sighash", _c.c_int, [_c.c_void_p, _c.c_void_p, _u8p, _c.c_size_t, _u8p]),
+    ("kgv_validate_populated", _c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_uint64, _c.c_uint32, _c.c_void_p, _u8p]),
+    ("kgv_utxo_create", _c.c_int, [_c.c_void_p, _c.c_uint64, _c.POINTER(_c.c_void_p)]),
+    ("kgv_utxo_destroy", None, [_c.c_void_p, _c.c_void_p]),
+    ("kgv_utxo_lookup", _c.c_int, [_c.c_void_p, _c.c_void_p, _u8p, _c.c_size_t, _u8p, _u8p, _c.c_uint32, _u8p]),
+    ("kgv_utxo_apply_diff", _c.c_int, [_c.c_void_p, _c.c_void_p, _u8p, _c.c_size_t, _u8p, _u8p, _u8p, _u8p, _c.c_size_t, _c.c_size_t, _u8p]),
+    ("kgv_utxo_count", _c.c_int, [_c.c_void_p, _c.c_void_p, _c.POINTER(_c.c_uint64)]),
+    ("kgv_utxo_digest", _c.c_int, [_c.c_void_p, _c.c_void_p, _u8p]),
+    ("kgv_validate_txs", _c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_uint64, _c.c_uint32, _c.c_void_p, _u8p]),
+    ("kgv_utxo_apply_accepted", _c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _u8p, _c.c_uint64]),
     ("kgv_gtable_entry", _c.c_int, [_c.c_void_p, _c.c_int, _c.c_uint32, _u8p]),
     ("kgv_debug_selftest", _c.c_int, [_c.c_void_p, _c.c_int, _u8p, _u8p, _c.c_size_t]),
     ("kgv_debug_schnorr_trace", _c.c_int, [_c.c_void_p, _u8p, _u8p, _u8p, _u8p, _u8p]),

@@ -75,8 +75,14 @@ __global__ void __launch_bounds__(128) k_sighash_reused(BatchView b, uint32_t n_
   reused[i] = r;
 }
 
-__device__ __forceinline__ bool sighash_type_allowed(uint32_t t) {  // sighash_type.rs:15-22
-  return t == 1 || t == 2 || t == 4 || t == 0x81 || t == 0x82 || t == 0x84;
+__global__ void k_entries_to_dev(const kgv_utxo_entry* __restrict__ in, const uint8_t* __restrict__ bytes, size_t n, DevEntry* __restrict__ out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  kgv_utxo_entry e = in[i];
+  DevEntry d;
+  d.amount = e.amount; d.block_daa_score = e.block_daa_score; d.script = bytes + e.script_off; d.script_len = e.script_len;
+  d.spk_version = e.spk_version; d.is_coinbase = e.is_coinbase; d.found = 1;
+  out[i] = d;
 }
 
 __global__ void __launch_bounds__(128)
@@ -114,7 +120,7 @@ static int digest_common(kgv_ctx* ctx, const kgv_tx_batch* batch, uint8_t* out32
     if (rc) return rc;
     dout = ctx->d_out;
   }
-  BatchView v{d.txs, d.inputs, d.outputs, d.entries, d.bytes};
+  BatchView v{d.txs, d.inputs, d.outputs, nullptr, d.bytes};
   unsigned blocks = (unsigned)((d.n_txs + 127) / 128);
   if (hash) k_tx_digest<true><<<blocks, 128, 0, ctx->stream>>>(v, (uint32_t)d.n_txs, (uint64_t*)dout);
   else k_tx_digest<false><<<blocks, 128, 0, ctx->stream>>>(v, (uint32_t)d.n_txs, (uint64_t*)dout);
@@ -140,7 +146,7 @@ extern "C" int kgv_sighash(kgv_ctx* ctx, const kgv_tx_batch* batch, const kgv_si
   if (rc) return rc;
   bool io_dev = kgv_ptr_is_device(items);
   if ((bool)kgv_ptr_is_device(out32) != io_dev) { ctx->err = "items and out32 must both be host or both be device pointers"; return KGV_ERR_ARG; }
-  size_t o_reused = 0, o_items = al256(d.n_txs * sizeof(SigHashReused));
+  size_t o_reused = 0, o_ent = al256(d.n_txs * sizeof(SigHashReused)), o_items = al256(o_ent + d.n_inputs * sizeof(DevEntry));
   rc = kgv_reserve(ctx, &ctx->d_scratch, &ctx->d_scratch_cap, o_items + (io_dev ? 0 : n_items * sizeof(kgv_sighash_item)) + 256);
   if (rc) return rc;
   SigHashReused* dre = (SigHashReused*)(ctx->d_scratch + o_reused);
@@ -153,7 +159,13 @@ extern "C" int kgv_sighash(kgv_ctx* ctx, const kgv_tx_batch* batch, const kgv_si
     if (rc) return rc;
     dout = ctx->d_out;
   }
-  BatchView v{d.txs, d.inputs, d.outputs, d.entries, d.bytes};
+  DevEntry* dent = (DevEntry*)(ctx->d_scratch + o_ent);
+  if (d.n_inputs) {
+    k_entries_to_dev<<<(unsigned)((d.n_inputs + 127) / 128), 128, 0, ctx->stream>>>(d.entries, d.bytes, d.n_inputs, dent);
+    CK(cudaGetLastError());
+    ctx->launches++;
+  }
+  BatchView v{d.txs, d.inputs, d.outputs, dent, d.bytes};
   k_sighash_reused<<<(unsigned)((d.n_txs + 127) / 128), 128, 0, ctx->stream>>>(v, (uint32_t)d.n_txs, dre);
   CK(cudaGetLastError());
   k_sighash_items<<<(unsigned)((n_items + 127) / 128), 128, 0, ctx->stream>>>(v, dre, ditems, n_items, (uint32_t)d.n_txs, (uint32_t)d.n_inputs, (uint32_t*)dout);

@@ -45,3 +45,7 @@ struct kgv_dev_batch {
 };
 // Makes the batch arrays device-resident (uploads host arrays into ctx staging; wraps device arrays).
 int kgv_batch_to_device(kgv_ctx* ctx, const kgv_tx_batch* b, kgv_dev_batch* out, bool need_entries);
+
+// Enqueue a verification kernel on device-resident SoA item arrays (no locking, no copies): used by the
+// fused validation path.  ecdsa: pk stride 33, else 32.
+int kgv_launch_verify(kgv_ctx* ctx, const uint8_t* dpk, const uint8_t* dmsg, const uint8_t* dsig, size_t n, uint8_t* dstatus, bool ecdsa);

@@ -296,6 +296,15 @@ extern "C" uint64_t kgv_launch_count(const kgv_ctx* ctx) { return ctx ? ctx->lau
 // ---------------------------------------------------------------------------------------------
 // signature verification entry points
 // ---------------------------------------------------------------------------------------------
+int kgv_launch_verify(kgv_ctx* ctx, const uint8_t* dpk, const uint8_t* dmsg, const uint8_t* dsig, size_t n, uint8_t* dst, bool ecdsa) {
+  if (n == 0) return KGV_OK;
+  {
+    int rc = kgv_launch_verify(ctx, dpk, dmsg, dsig, n, dst, ecdsa);
+    if (rc) return rc;
+  }
+  return KGV_OK;
+}
+
 static int verify_common(kgv_ctx* ctx, const uint8_t* pk, size_t pk_stride, const uint8_t* msg, const uint8_t* sig, size_t n,
                          uint8_t* status, bool ecdsa) {
   if (!ctx) return KGV_ERR_ARG;
@@ -320,18 +329,10 @@ static int verify_common(kgv_ctx* ctx, const uint8_t* pk, size_t pk_stride, cons
     CK(cudaMemcpyAsync(ctx->d_in + off_sig, sig, 64 * n, cudaMemcpyHostToDevice, ctx->stream));
     dpk = ctx->d_in; dmsg = ctx->d_in + off_msg; dsig = ctx->d_in + off_sig; dst = ctx->d_out;
   }
-  const int smem = KGV_BLOCK * 128 * (int)sizeof(uint32_t);
-  unsigned blocks = (unsigned)((n + KGV_BLOCK - 1) / KGV_BLOCK);
-  bool aligned = (((uintptr_t)dmsg | (uintptr_t)dsig | (ecdsa ? 0 : (uintptr_t)dpk)) & 31) == 0;
-  if (ecdsa) {
-    if (aligned) k_ecdsa_verify<true><<<blocks, KGV_BLOCK, smem, ctx->stream>>>(dpk, dmsg, dsig, n, dst, ctx->gtab);
-    else k_ecdsa_verify<false><<<blocks, KGV_BLOCK, smem, ctx->stream>>>(dpk, dmsg, dsig, n, dst, ctx->gtab);
-  } else {
-    if (aligned) k_schnorr_verify<true><<<blocks, KGV_BLOCK, smem, ctx->stream>>>(dpk, dmsg, dsig, n, dst, ctx->gtab);
-    else k_schnorr_verify<false><<<blocks, KGV_BLOCK, smem, ctx->stream>>>(dpk, dmsg, dsig, n, dst, ctx->gtab);
+  {
+    int rc = kgv_launch_verify(ctx, dpk, dmsg, dsig, n, dst, ecdsa);
+    if (rc) return rc;
   }
-  CK(cudaGetLastError());
-  ctx->launches++;
   if (!dev) {
     CK(cudaMemcpyAsync(status, dst, n, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));

@@ -11,6 +11,7 @@
 #include "../../include/kgv.h"
 #include "kgv_blake2b.cuh"
 #include "kgv_sha256.cuh"
+#include "kgv_script_std.cuh"
 
 namespace kgv {
 
@@ -18,7 +19,7 @@ struct BatchView {
   const kgv_tx* txs;
   const kgv_input* inputs;
   const kgv_output* outputs;
-  const kgv_utxo_entry* entries;  // per input (may be null when not needed)
+  const DevEntry* entries;  // populated entry per input (null when not needed)
   const uint8_t* bytes;
 };
 
@@ -121,7 +122,7 @@ KGV_HD void sighash_final(uint32_t* out_be_words, const BatchView& b, uint32_t t
                           const SigHashReused& r) {
   const kgv_tx& t = b.txs[tx];
   const kgv_input& in = b.inputs[in_abs];
-  const kgv_utxo_entry& e = b.entries[in_abs];
+  const DevEntry& e = b.entries[in_abs];
   const bool acp = (hash_type & 0x80u) != 0;
   const uint32_t base = hash_type & 7u;
   const uint64_t zero[4] = {0, 0, 0, 0};
@@ -148,7 +149,7 @@ KGV_HD void sighash_final(uint32_t* out_be_words, const BatchView& b, uint32_t t
   b2b_bytes(s, in.prev_txid, 32);
   b2b_u32(s, in.prev_index);
   b2b_u16(s, e.spk_version);
-  b2b_var_bytes(s, b.bytes + e.script_off, e.script_len);
+  b2b_var_bytes(s, e.script, e.script_len);
   b2b_u64(s, e.amount);
   b2b_u64(s, in.sequence);
   b2b_u8(s, in.sig_op_count);

@@ -1,0 +1,797 @@
+// kgv_validate.cu — GPU-resident UTXO table, per-transaction context rules and the fused
+// validate_transactions path (include/kgv.h).
+//
+// Data flow of kgv_validate_txs (one call = one block's worth or more of transactions):
+//   k_populate        per input : outpoint -> table slot -> DevEntry            (HBM latency bound)
+//   k_tx_context      per tx    : maturity, amounts, storage mass, seq-lock      (tx_validation_in_utxo_context.rs:75-155)
+//   k_plan            per input : recognise P2PK / P2PK-ECDSA / P2SH multisig, count signature checks
+//   (scan)                        exclusive prefix sums -> item offsets (two lists: Schnorr, ECDSA)
+//   k_emit_items      per input : gather (pk, sig) of every candidate pair into SoA arrays
+//   k_sighash_reused  per tx    : the five reusable sub-hashes                   (sighash.rs:14-221)
+//   k_item_msgs       per item  : final signature hash                           (sighash.rs:238-277)
+//   k_schnorr_verify / k_ecdsa_verify per item                                   (lib.rs:593, :628)
+//   k_resolve         per input : replay of the script engine over the verdicts  (lib.rs:488-571)
+//   k_tx_finalize     per tx    : first failing input -> TxRuleError class       (:162-200)
+#include "kgv_internal.h"
+#include "kgv_txhash.cuh"
+
+#include <cstdio>
+#include <vector>
+
+using namespace kgv;
+
+#define CK(call)                                                                                  \
+  do {                                                                                            \
+    cudaError_t e_ = (call);                                                                      \
+    if (e_ != cudaSuccess) {                                                                      \
+      char b_[256];                                                                               \
+      snprintf(b_, sizeof b_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+      ctx->err = b_;                                                                              \
+      return KGV_ERR_CUDA;                                                                        \
+    }                                                                                             \
+  } while (0)
+
+static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+// ---------------------------------------------------------------------------------------------
+// UTXO table
+// ---------------------------------------------------------------------------------------------
+#define SLOT_EMPTY 0u
+#define SLOT_FULL 1u
+#define SLOT_TOMB 2u
+#define SLOT_BUSY 3u
+#define INLINE_SCRIPT 68u
+
+struct __align__(128) UtxoSlot {
+  uint32_t state;
+  uint32_t key[9];       // txid (8 words) + index
+  uint64_t amount;       // word 10,11
+  uint64_t daa;          // word 12,13
+  uint32_t meta;         // spk_version | is_coinbase << 16 | script_len << 17
+  uint8_t script[INLINE_SCRIPT];  // inline bytes, or (len > 68) a u64 offset into the overflow arena
+};
+static_assert(sizeof(UtxoSlot) == 128, "slot must be one 128-byte line");
+
+struct kgv_utxo_table {
+  UtxoSlot* slots = nullptr;
+  uint64_t mask = 0;             // capacity - 1
+  uint8_t* overflow = nullptr;   // long scripts
+  uint64_t overflow_cap = 0;
+  unsigned long long* counters = nullptr;  // [0] live entries, [1] tombstones, [2] overflow bytes used, [3] insert failures
+};
+
+struct TableView {
+  UtxoSlot* slots;
+  uint64_t mask;
+  uint8_t* overflow;
+  uint64_t overflow_cap;
+  unsigned long long* counters;
+};
+
+__device__ __forceinline__ void load_key(uint32_t* k, const uint8_t* p) {
+#pragma unroll
+  for (int i = 0; i < 9; i++) k[i] = (uint32_t)p[4 * i] | ((uint32_t)p[4 * i + 1] << 8) | ((uint32_t)p[4 * i + 2] << 16) | ((uint32_t)p[4 * i + 3] << 24);
+}
+__device__ __forceinline__ uint64_t key_hash(const uint32_t* k) {
+  uint64_t h = ((uint64_t)k[1] << 32 | k[0]) ^ ((uint64_t)k[3] << 32 | k[2]) * 0x9E3779B97F4A7C15ull;
+  h ^= (uint64_t)k[8] * 0xD6E8FEB86659FD93ull;
+  h ^= h >> 29;
+  h *= 0xBF58476D1CE4E5B9ull;
+  h ^= h >> 32;
+  return h;
+}
+__device__ __forceinline__ bool key_eq(const UtxoSlot* s, const uint32_t* k) {
+  bool eq = true;
+#pragma unroll
+  for (int i = 0; i < 9; i++) eq = eq && (s->key[i] == k[i]);
+  return eq;
+}
+// returns the slot holding key k, or nullptr (table is not being modified concurrently)
+__device__ __forceinline__ UtxoSlot* table_find(const TableView& t, const uint32_t* k) {
+  uint64_t i = key_hash(k) & t.mask;
+  for (uint64_t probes = 0; probes <= t.mask; probes++) {
+    UtxoSlot* s = &t.slots[i];
+    uint32_t st = s->state;
+    if (st == SLOT_EMPTY) return nullptr;
+    if (st == SLOT_FULL && key_eq(s, k)) return s;
+    i = (i + 1) & t.mask;
+  }
+  return nullptr;
+}
+__device__ __forceinline__ const uint8_t* slot_script(const TableView& t, const UtxoSlot* s, uint32_t len) {
+  if (len <= INLINE_SCRIPT) return s->script;
+  uint64_t off;
+  memcpy(&off, s->script, 8);
+  return t.overflow + off;
+}
+__device__ __forceinline__ void slot_to_entry(DevEntry& e, const TableView& t, const UtxoSlot* s) {
+  e.amount = s->amount;
+  e.block_daa_score = s->daa;
+  e.spk_version = (uint16_t)(s->meta & 0xFFFFu);
+  e.is_coinbase = (uint8_t)((s->meta >> 16) & 1u);
+  e.script_len = s->meta >> 17;
+  e.script = slot_script(t, s, e.script_len);
+  e.found = 1;
+}
+
+// upsert; returns 1 inserted, 2 replaced, 0 failed (table or overflow arena full)
+__device__ uint32_t table_put(const TableView& t, const uint32_t* k, uint64_t amount, uint64_t daa, uint32_t spk_version, uint32_t is_coinbase,
+                              const uint8_t* script, uint32_t script_len) {
+  uint64_t i = key_hash(k) & t.mask;
+  UtxoSlot* target = nullptr;
+  bool replace = false;
+  for (uint64_t probes = 0; probes <= t.mask; probes++) {
+    UtxoSlot* s = &t.slots[i];
+    uint32_t st = *(volatile uint32_t*)&s->state;
+    if (st == SLOT_BUSY) { probes--; continue; }  // another thread is filling this slot: wait for its key
+    if (st == SLOT_FULL) {
+      if (key_eq(s, k)) { target = s; replace = true; break; }
+    } else {  // empty or tombstone: try to claim it
+      uint32_t old = atomicCAS(&s->state, st, SLOT_BUSY);
+      if (old == st) {
+        target = s;
+        if (st == SLOT_TOMB) atomicAdd(&t.counters[1], (unsigned long long)-1);
+        break;
+      }
+      probes--;  // lost the race: look at the same slot again
+      continue;
+    }
+    i = (i + 1) & t.mask;
+  }
+  if (!target) { atomicAdd(&t.counters[3], 1ull); return 0; }
+#pragma unroll
+  for (int w = 0; w < 9; w++) target->key[w] = k[w];
+  target->amount = amount;
+  target->daa = daa;
+  target->meta = (spk_version & 0xFFFFu) | ((is_coinbase & 1u) << 16) | (script_len << 17);
+  if (script_len <= INLINE_SCRIPT) {
+    for (uint32_t b = 0; b < script_len; b++) target->script[b] = script[b];
+  } else {
+    uint64_t need = (script_len + 7u) & ~7ull;
+    uint64_t off = atomicAdd(&t.counters[2], (unsigned long long)need);
+    if (off + need > t.overflow_cap) { atomicAdd(&t.counters[3], 1ull); if (!replace) { __threadfence(); target->state = SLOT_TOMB; atomicAdd(&t.counters[1], 1ull); } return 0; }
+    for (uint32_t b = 0; b < script_len; b++) t.overflow[off + b] = script[b];
+    memcpy(target->script, &off, 8);
+  }
+  if (!replace) {
+    __threadfence();
+    target->state = SLOT_FULL;
+    atomicAdd(&t.counters[0], 1ull);
+  }
+  return replace ? 2u : 1u;
+}
+__device__ uint32_t table_erase(const TableView& t, const uint32_t* k) {
+  UtxoSlot* s = table_find(t, k);
+  if (!s) return 0;
+  s->state = SLOT_TOMB;
+  atomicAdd(&t.counters[0], (unsigned long long)-1);
+  atomicAdd(&t.counters[1], 1ull);
+  return 1;
+}
+
+__global__ void k_utxo_lookup(TableView t, const uint8_t* __restrict__ keys, size_t n, kgv_utxo_entry* __restrict__ entries,
+                              uint8_t* __restrict__ scripts, uint32_t stride, uint8_t* __restrict__ found) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t k[9];
+  load_key(k, keys + 36 * i);
+  UtxoSlot* s = table_find(t, k);
+  kgv_utxo_entry e;
+  memset(&e, 0, sizeof e);
+  e.script_off = (uint32_t)(i * stride);
+  if (s) {
+    DevEntry d;
+    slot_to_entry(d, t, s);
+    e.amount = d.amount; e.block_daa_score = d.block_daa_score; e.script_len = d.script_len; e.spk_version = d.spk_version; e.is_coinbase = d.is_coinbase;
+    for (uint32_t b = 0; b < d.script_len && b < stride; b++) scripts[i * stride + b] = d.script[b];
+  }
+  entries[i] = e;
+  found[i] = s ? 1 : 0;
+}
+__global__ void k_utxo_erase(TableView t, const uint8_t* __restrict__ keys, size_t n, uint8_t* __restrict__ status) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t k[9];
+  load_key(k, keys + 36 * i);
+  uint32_t r = table_erase(t, k);
+  if (status) status[i] = (uint8_t)r;
+}
+__global__ void k_utxo_insert(TableView t, const uint8_t* __restrict__ keys, const kgv_utxo_entry* __restrict__ entries, const uint8_t* __restrict__ bytes,
+                              size_t n, uint8_t* __restrict__ status) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t k[9];
+  load_key(k, keys + 36 * i);
+  kgv_utxo_entry e = entries[i];
+  uint32_t r = table_put(t, k, e.amount, e.block_daa_score, e.spk_version, e.is_coinbase, bytes + e.script_off, e.script_len);
+  if (status) status[i] = (uint8_t)r;
+}
+
+// digest: sum of MuHashElement hashes, accumulated as 8 x 32-bit limbs in 64-bit counters (carries folded on the host)
+__global__ void k_utxo_digest(TableView t, unsigned long long* __restrict__ acc) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > t.mask) return;
+  const UtxoSlot* s = &t.slots[i];
+  if (s->state != SLOT_FULL) return;
+  DevEntry e;
+  slot_to_entry(e, t, s);
+  // keyed BLAKE2b "MuHashElement": midstate is not tabulated, so hash the key block explicitly
+  Blake2b h;
+  b2b_init(h, B2B_UNKEYED);
+  h.h[0] = kB2bIV[0] ^ (0x01010000ull ^ (13ull << 8) ^ 32ull);
+  const char dom[13] = {'M', 'u', 'H', 'a', 's', 'h', 'E', 'l', 'e', 'm', 'e', 'n', 't'};
+  for (int b = 0; b < 128; b++) b2b_byte(h, b < 13 ? (uint32_t)dom[b] : 0u);
+  for (int w = 0; w < 9; w++) b2b_u32(h, s->key[w]);
+  b2b_u64(h, e.block_daa_score);
+  b2b_u64(h, e.amount);
+  b2b_u8(h, e.is_coinbase ? 1 : 0);
+  b2b_u16(h, e.spk_version);
+  b2b_u64(h, e.script_len);
+  b2b_bytes(h, e.script, e.script_len);
+  uint64_t d[4];
+  b2b_final(h, d);
+#pragma unroll
+  for (int w = 0; w < 4; w++) {
+    atomicAdd(&acc[2 * w], (unsigned long long)(uint32_t)d[w]);
+    atomicAdd(&acc[2 * w + 1], (unsigned long long)(uint32_t)(d[w] >> 32));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// validation kernels
+// ---------------------------------------------------------------------------------------------
+__global__ void k_entries_from_batch(const kgv_utxo_entry* __restrict__ in, const uint8_t* __restrict__ bytes, size_t n, DevEntry* __restrict__ out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  kgv_utxo_entry e = in[i];
+  DevEntry d;
+  d.amount = e.amount; d.block_daa_score = e.block_daa_score; d.script = bytes + e.script_off; d.script_len = e.script_len;
+  d.spk_version = e.spk_version; d.is_coinbase = e.is_coinbase; d.found = 1;
+  out[i] = d;
+}
+
+__global__ void k_populate(TableView t, const kgv_input* __restrict__ inputs, size_t n, DevEntry* __restrict__ out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t k[9];
+  const kgv_input& in = inputs[i];
+#pragma unroll
+  for (int w = 0; w < 8; w++) k[w] = (uint32_t)in.prev_txid[4 * w] | ((uint32_t)in.prev_txid[4 * w + 1] << 8) | ((uint32_t)in.prev_txid[4 * w + 2] << 16) | ((uint32_t)in.prev_txid[4 * w + 3] << 24);
+  k[8] = in.prev_index;
+  UtxoSlot* s = table_find(t, k);
+  DevEntry d;
+  if (s) slot_to_entry(d, t, s);
+  else { d.amount = 0; d.block_daa_score = 0; d.script = nullptr; d.script_len = 0; d.spk_version = 0; d.is_coinbase = 0; d.found = 0; }
+  out[i] = d;
+}
+
+__global__ void k_tx_context(BatchView b, uint32_t n_txs, uint64_t pov, uint32_t flags, kgv_params prm, kgv_tx_result* __restrict__ res) {
+  uint32_t ti = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ti >= n_txs) return;
+  const kgv_tx& t = b.txs[ti];
+  kgv_tx_result r;
+  r.fee = 0; r.fail_input = 0; r.status = KGV_TX_OK; r.script_err = 0; r.pad_[0] = r.pad_[1] = 0;
+  const DevEntry* ent = b.entries + t.first_input;
+  bool cb = tx_is_coinbase(t);
+  if (cb) { r.status = KGV_TX_SKIPPED_COINBASE; res[ti] = r; return; }
+  for (uint32_t i = 0; i < t.n_inputs; i++)
+    if (!ent[i].found) { r.status = KGV_TX_MISSING_OUTPOINTS; res[ti] = r; return; }  // utxo_validation.rs:319-327
+  for (uint32_t i = 0; i < t.n_inputs; i++)
+    if (ent[i].is_coinbase && ent[i].block_daa_score + prm.coinbase_maturity > pov) { r.status = KGV_TX_IMMATURE_COINBASE; r.fail_input = i; res[ti] = r; return; }
+  uint64_t total_in = 0;
+  for (uint32_t i = 0; i < t.n_inputs; i++) {
+    if (ck_add(total_in, ent[i].amount, total_in)) { r.status = KGV_TX_INPUT_AMOUNT_OVERFLOW; res[ti] = r; return; }
+    if (total_in > prm.max_sompi) { r.status = KGV_TX_INPUT_AMOUNT_TOO_HIGH; res[ti] = r; return; }
+  }
+  uint64_t total_out = 0;
+  for (uint32_t i = 0; i < t.n_outputs; i++) total_out += b.outputs[t.first_output + i].value;
+  if (total_in < total_out) { r.status = KGV_TX_SPEND_TOO_HIGH; res[ti] = r; return; }
+  r.fee = total_in - total_out;
+  if (flags != KGV_FLAGS_SKIP_MASS_CHECK) {
+    uint64_t mass;
+    const kgv_output* outs = b.outputs + t.first_output;
+    bool ok = storage_mass(mass, false, t.n_inputs, t.n_outputs, [&](uint32_t i) -> const DevEntry& { return ent[i]; },
+                           [&](uint32_t i, uint64_t& v, uint32_t& l) { v = outs[i].value; l = outs[i].script_len; }, prm.storage_mass_parameter);
+    if (!ok) { r.status = KGV_TX_MASS_INCOMPUTABLE; res[ti] = r; return; }
+    if (mass != t.mass) { r.status = KGV_TX_WRONG_MASS; res[ti] = r; return; }
+  }
+  for (uint32_t i = 0; i < t.n_inputs; i++) {
+    uint64_t seq = b.inputs[t.first_input + i].sequence;
+    if (seq & (1ull << 63)) continue;
+    long long lock = (long long)ent[i].block_daa_score + (long long)(seq & 0xFFFFFFFFull) - 1;
+    if (lock >= (long long)pov) { r.status = KGV_TX_SEQUENCE_LOCK; res[ti] = r; return; }
+  }
+  res[ti] = r;
+}
+
+// plan: one thread per input. counts[0][i] = Schnorr items, counts[1][i] = ECDSA items (0 when the tx already failed).
+__global__ void k_plan(BatchView b, size_t n_inputs, const uint32_t* __restrict__ input_tx, const kgv_tx_result* __restrict__ res,
+                       InputPlan* __restrict__ plans, uint32_t* __restrict__ cnt_s, uint32_t* __restrict__ cnt_e) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_inputs) return;
+  InputPlan pl;
+  pl.item_base = 0; pl.redeem_off = 0; pl.redeem_len = 0; pl.cls = CLS_NONSTANDARD; pl.m = pl.n = pl.n_items = 0; pl.pad_[0] = pl.pad_[1] = 0;
+  uint32_t cs = 0, ce = 0;
+  if (res[input_tx[i]].status == KGV_TX_OK) {
+    const kgv_input& in = b.inputs[i];
+    plan_input(pl, b.bytes + in.sigscript_off, in.sigscript_len, b.entries[i]);
+    if (pl.cls == CLS_P2PK || pl.cls == CLS_MULTISIG) cs = pl.n_items;
+    if (pl.cls == CLS_P2PK_ECDSA || pl.cls == CLS_MULTISIG_ECDSA) ce = pl.n_items;
+  }
+  plans[i] = pl;
+  cnt_s[i] = cs;
+  cnt_e[i] = ce;
+}
+
+// single-block exclusive scan (inputs per call are at most a few hundred thousand: plumbing, not a hot kernel)
+__global__ void k_exclusive_scan(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, size_t n, uint32_t* __restrict__ total) {
+  __shared__ uint32_t sums[1024];
+  __shared__ uint32_t carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (size_t base = 0; base < n; base += 1024) {
+    size_t i = base + threadIdx.x;
+    uint32_t v = i < n ? in[i] : 0;
+    sums[threadIdx.x] = v;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {
+      uint32_t t = threadIdx.x >= off ? sums[threadIdx.x - off] : 0;
+      __syncthreads();
+      sums[threadIdx.x] += t;
+      __syncthreads();
+    }
+    if (i < n) out[i] = carry + sums[threadIdx.x] - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry += sums[1023];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total = carry;
+}
+
+struct ItemRef { uint32_t input; uint32_t k; };  // which input / which candidate pair
+
+__global__ void k_emit_items(BatchView b, size_t n_inputs, InputPlan* __restrict__ plans, const uint32_t* __restrict__ off_s, const uint32_t* __restrict__ off_e,
+                             uint8_t* __restrict__ pk_s, uint8_t* __restrict__ sig_s, ItemRef* __restrict__ ref_s,
+                             uint8_t* __restrict__ pk_e, uint8_t* __restrict__ sig_e, ItemRef* __restrict__ ref_e) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_inputs) return;
+  InputPlan pl = plans[i];
+  if (pl.n_items == 0) return;
+  bool ecdsa = pl.cls == CLS_P2PK_ECDSA || pl.cls == CLS_MULTISIG_ECDSA;
+  uint32_t base = ecdsa ? off_e[i] : off_s[i];
+  plans[i].item_base = base;
+  const kgv_input& in = b.inputs[i];
+  const uint8_t* ss = b.bytes + in.sigscript_off;
+  for (uint32_t k = 0; k < pl.n_items; k++) {
+    const uint8_t *sig, *key;
+    item_location(pl, k, ss, b.entries[i], sig, key);
+    size_t it = base + k;
+    if (ecdsa) {
+      for (int x = 0; x < 33; x++) pk_e[33 * it + x] = key[x];
+      for (int x = 0; x < 64; x++) sig_e[64 * it + x] = sig[x];
+      ref_e[it] = ItemRef{(uint32_t)i, k};
+    } else {
+      for (int x = 0; x < 32; x++) pk_s[32 * it + x] = key[x];
+      for (int x = 0; x < 64; x++) sig_s[64 * it + x] = sig[x];
+      ref_s[it] = ItemRef{(uint32_t)i, k};
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128) k_sighash_reused_v(BatchView b, uint32_t n_txs, const kgv_tx_result* __restrict__ res, SigHashReused* __restrict__ reused) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_txs) return;
+  if (res[i].status != KGV_TX_OK) return;
+  SigHashReused r;
+  sighash_reused(r, b, i);
+  reused[i] = r;
+}
+
+__global__ void __launch_bounds__(128)
+k_item_msgs(BatchView b, const SigHashReused* __restrict__ reused, const uint32_t* __restrict__ input_tx, const InputPlan* __restrict__ plans,
+            const ItemRef* __restrict__ refs, size_t n_items, bool ecdsa, uint32_t* __restrict__ msgs) {
+  size_t it = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (it >= n_items) return;
+  ItemRef rf = refs[it];
+  InputPlan pl = plans[rf.input];
+  const kgv_input& in = b.inputs[rf.input];
+  const uint8_t* ss = b.bytes + in.sigscript_off;
+  const uint8_t *sig, *key;
+  item_location(pl, rf.k, ss, b.entries[rf.input], sig, key);
+  uint32_t ht = sig[64];
+  uint32_t w[8];
+  if (!sighash_type_allowed(ht)) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) w[k] = 0;  // never consulted: resolve reports InvalidSigHashType first
+  } else {
+    uint32_t tx = input_tx[rf.input];
+    SigHashReused r = reused[tx];
+    sighash_final(w, b, tx, rf.input, ht, ecdsa, r);
+  }
+#pragma unroll
+  for (int k = 0; k < 8; k++) msgs[8 * it + k] = bswap32(w[k]);
+}
+
+__global__ void k_resolve(BatchView b, size_t n_inputs, const uint32_t* __restrict__ input_tx, const kgv_tx_result* __restrict__ res,
+                          const InputPlan* __restrict__ plans, const uint8_t* __restrict__ st_s, const uint8_t* __restrict__ st_e,
+                          uint8_t* __restrict__ input_err) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_inputs) return;
+  if (res[input_tx[i]].status != KGV_TX_OK) { input_err[i] = KGV_SCRIPT_OK; return; }
+  InputPlan pl = plans[i];
+  const kgv_input& in = b.inputs[i];
+  bool ecdsa = pl.cls == CLS_P2PK_ECDSA || pl.cls == CLS_MULTISIG_ECDSA;
+  const uint8_t* st = (ecdsa ? st_e : st_s) + pl.item_base;
+  input_err[i] = (uint8_t)resolve_input(pl, b.bytes + in.sigscript_off, b.entries[i], in.sig_op_count, st);
+}
+
+__global__ void k_tx_finalize(BatchView b, uint32_t n_txs, const uint8_t* __restrict__ input_err, kgv_tx_result* __restrict__ res) {
+  uint32_t ti = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ti >= n_txs) return;
+  kgv_tx_result r = res[ti];
+  if (r.status != KGV_TX_OK) return;
+  const kgv_tx& t = b.txs[ti];
+  for (uint32_t i = 0; i < t.n_inputs; i++) {  // check_scripts_sequential order (:170-178)
+    uint32_t err = input_err[t.first_input + i];
+    if (err == KGV_SCRIPT_OK) continue;
+    r.fail_input = i;
+    r.script_err = (uint8_t)err;
+    if (err == KGV_SCRIPT_NONSTANDARD) r.status = KGV_TX_NEEDS_HOST_VM;
+    else r.status = b.inputs[t.first_input + i].sigscript_len == 0 ? KGV_TX_SIGNATURE_EMPTY : KGV_TX_SIGNATURE_INVALID;  // map_script_err :198-200
+    break;
+  }
+  res[ti] = r;
+}
+
+__global__ void k_input_tx_index(const kgv_tx* __restrict__ txs, uint32_t n_txs, uint32_t* __restrict__ input_tx) {
+  uint32_t ti = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ti >= n_txs) return;
+  kgv_tx t = txs[ti];
+  for (uint32_t i = 0; i < t.n_inputs; i++) input_tx[t.first_input + i] = ti;
+}
+
+// apply accepted transactions to the table (UtxoDiff::add_transaction, utxo_diff.rs:233-247)
+__global__ void k_apply_erase(TableView t, const kgv_tx* __restrict__ txs, const kgv_input* __restrict__ inputs, size_t n_inputs,
+                              const uint32_t* __restrict__ input_tx, const uint8_t* __restrict__ accept) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_inputs) return;
+  if (!accept[input_tx[i]]) return;
+  uint32_t k[9];
+  const kgv_input& in = inputs[i];
+#pragma unroll
+  for (int w = 0; w < 8; w++) k[w] = (uint32_t)in.prev_txid[4 * w] | ((uint32_t)in.prev_txid[4 * w + 1] << 8) | ((uint32_t)in.prev_txid[4 * w + 2] << 16) | ((uint32_t)in.prev_txid[4 * w + 3] << 24);
+  k[8] = in.prev_index;
+  table_erase(t, k);
+}
+__global__ void k_output_tx_index(const kgv_tx* __restrict__ txs, uint32_t n_txs, uint32_t* __restrict__ output_tx) {
+  uint32_t ti = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ti >= n_txs) return;
+  kgv_tx t = txs[ti];
+  for (uint32_t i = 0; i < t.n_outputs; i++) output_tx[t.first_output + i] = ti;
+}
+__global__ void k_apply_insert(TableView t, BatchView b, size_t n_outputs, const uint32_t* __restrict__ output_tx, const uint8_t* __restrict__ accept,
+                               const uint64_t* __restrict__ txids, uint64_t pov) {
+  size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= n_outputs) return;
+  uint32_t ti = output_tx[o];
+  if (!accept[ti]) return;
+  const kgv_tx& tx = b.txs[ti];
+  const kgv_output& out = b.outputs[o];
+  uint32_t k[9];
+#pragma unroll
+  for (int w = 0; w < 4; w++) { k[2 * w] = (uint32_t)txids[4 * (size_t)ti + w]; k[2 * w + 1] = (uint32_t)(txids[4 * (size_t)ti + w] >> 32); }
+  k[8] = (uint32_t)(o - tx.first_output);
+  table_put(t, k, out.value, pov, out.spk_version, tx_is_coinbase(tx) ? 1u : 0u, b.bytes + out.script_off, out.script_len);
+}
+__global__ void __launch_bounds__(128) k_tx_ids_dev(BatchView b, uint32_t n_txs, uint64_t* __restrict__ out) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_txs) return;
+  uint64_t d[4];
+  tx_id(d, b, i);
+#pragma unroll
+  for (int k = 0; k < 4; k++) out[4 * (size_t)i + k] = d[k];
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static TableView view_of(const kgv_utxo_table* t) { return TableView{t->slots, t->mask, t->overflow, t->overflow_cap, t->counters}; }
+static inline unsigned nblk(size_t n, unsigned b) { return (unsigned)((n + b - 1) / b); }
+
+extern "C" int kgv_utxo_create(kgv_ctx* ctx, uint64_t capacity_slots, kgv_utxo_table** out) {
+  if (!ctx || !out) return KGV_ERR_ARG;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  *out = nullptr;
+  CK(cudaSetDevice(ctx->device));
+  uint64_t cap = 1024;
+  while (cap < capacity_slots) cap <<= 1;
+  kgv_utxo_table* t = new kgv_utxo_table();
+  t->mask = cap - 1;
+  t->overflow_cap = cap * 8 < (64ull << 20) ? (64ull << 20) : cap * 8;
+  cudaError_t e = cudaMalloc((void**)&t->slots, cap * sizeof(UtxoSlot));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&t->overflow, t->overflow_cap);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&t->counters, 16 * sizeof(unsigned long long));
+  if (e != cudaSuccess) {
+    ctx->err = std::string("cudaMalloc failed for the UTXO table: ") + cudaGetErrorString(e);
+    (void)cudaGetLastError();
+    if (t->slots) cudaFree(t->slots);
+    if (t->overflow) cudaFree(t->overflow);
+    delete t;
+    return KGV_ERR_NOMEM;
+  }
+  CK(cudaMemsetAsync(t->slots, 0, cap * sizeof(UtxoSlot), ctx->stream));
+  CK(cudaMemsetAsync(t->counters, 0, 16 * sizeof(unsigned long long), ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  *out = t;
+  return KGV_OK;
+}
+extern "C" void kgv_utxo_destroy(kgv_ctx* ctx, kgv_utxo_table* t) {
+  if (!t) return;
+  if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
+  cudaFree(t->slots); cudaFree(t->overflow); cudaFree(t->counters);
+  delete t;
+}
+
+// stage a host array on the device inside ctx->d_in at a running offset
+struct Stager {
+  kgv_ctx* ctx;
+  size_t off = 0;
+  explicit Stager(kgv_ctx* c) : ctx(c) {}
+};
+
+extern "C" int kgv_utxo_lookup(kgv_ctx* ctx, kgv_utxo_table* t, const uint8_t* keys36, size_t n, kgv_utxo_entry* entries, uint8_t* scripts_out,
+                               uint32_t script_stride, uint8_t* found) {
+  if (!ctx || !t) return KGV_ERR_ARG;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  if (n == 0) return KGV_OK;
+  if (!keys36 || !entries || !found || (script_stride && !scripts_out)) { ctx->err = "null buffer"; return KGV_ERR_ARG; }
+  CK(cudaSetDevice(ctx->device));
+  bool dev = kgv_ptr_is_device(keys36);
+  const uint8_t* dk = keys36;
+  kgv_utxo_entry* de = entries;
+  uint8_t *ds = scripts_out, *df = found;
+  size_t o_e = 0, o_s = al256(n * sizeof(kgv_utxo_entry)), o_f = al256(o_s + n * (size_t)script_stride);
+  if (!dev) {
+    int rc = kgv_reserve(ctx, &ctx->d_in, &ctx->d_in_cap, n * 36);
+    if (rc) return rc;
+    rc = kgv_reserve(ctx, &ctx->d_out, &ctx->d_out_cap, o_f + n);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(ctx->d_in, keys36, n * 36, cudaMemcpyHostToDevice, ctx->stream));
+    dk = ctx->d_in; de = (kgv_utxo_entry*)(ctx->d_out + o_e); ds = ctx->d_out + o_s; df = ctx->d_out + o_f;
+  }
+  k_utxo_lookup<<<nblk(n, 128), 128, 0, ctx->stream>>>(view_of(t), dk, n, de, ds, script_stride, df);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  if (!dev) {
+    CK(cudaMemcpyAsync(entries, de, n * sizeof(kgv_utxo_entry), cudaMemcpyDeviceToHost, ctx->stream));
+    if (script_stride) CK(cudaMemcpyAsync(scripts_out, ds, n * (size_t)script_stride, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(found, df, n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  return KGV_OK;
+}
+
+extern "C" int kgv_utxo_apply_diff(kgv_ctx* ctx, kgv_utxo_table* t, const uint8_t* rem_keys36, size_t n_rem, uint8_t* rem_status,
+                                   const uint8_t* add_keys36, const kgv_utxo_entry* add_entries, const uint8_t* add_bytes, size_t n_add_bytes, size_t n_add,
+                                   uint8_t* add_status) {
+  if (!ctx || !t) return KGV_ERR_ARG;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  if ((n_rem && !rem_keys36) || (n_add && (!add_keys36 || !add_entries || (n_add_bytes && !add_bytes)))) { ctx->err = "null buffer"; return KGV_ERR_ARG; }
+  CK(cudaSetDevice(ctx->device));
+  const void* probe = n_rem ? (const void*)rem_keys36 : (const void*)add_keys36;
+  if (!probe) return KGV_OK;
+  bool dev = kgv_ptr_is_device(probe);
+  size_t o_rk = 0, o_ak = al256(n_rem * 36), o_ae = al256(o_ak + n_add * 36), o_ab = al256(o_ae + n_add * sizeof(kgv_utxo_entry));
+  size_t o_rs = 0, o_as = al256(n_rem);
+  const uint8_t *drk = rem_keys36, *dak = add_keys36, *dab = add_bytes;
+  const kgv_utxo_entry* dae = add_entries;
+  uint8_t *drs = rem_status, *das = add_status;
+  if (!dev) {
+    int rc = kgv_reserve(ctx, &ctx->d_in, &ctx->d_in_cap, o_ab + n_add_bytes + 16);
+    if (rc) return rc;
+    rc = kgv_reserve(ctx, &ctx->d_out, &ctx->d_out_cap, o_as + n_add + 16);
+    if (rc) return rc;
+    if (n_rem) CK(cudaMemcpyAsync(ctx->d_in + o_rk, rem_keys36, n_rem * 36, cudaMemcpyHostToDevice, ctx->stream));
+    if (n_add) {
+      CK(cudaMemcpyAsync(ctx->d_in + o_ak, add_keys36, n_add * 36, cudaMemcpyHostToDevice, ctx->stream));
+      CK(cudaMemcpyAsync(ctx->d_in + o_ae, add_entries, n_add * sizeof(kgv_utxo_entry), cudaMemcpyHostToDevice, ctx->stream));
+      if (n_add_bytes) CK(cudaMemcpyAsync(ctx->d_in + o_ab, add_bytes, n_add_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    drk = ctx->d_in + o_rk; dak = ctx->d_in + o_ak; dae = (const kgv_utxo_entry*)(ctx->d_in + o_ae); dab = ctx->d_in + o_ab;
+    drs = ctx->d_out + o_rs; das = ctx->d_out + o_as;
+  }
+  if (n_rem) { k_utxo_erase<<<nblk(n_rem, 128), 128, 0, ctx->stream>>>(view_of(t), drk, n_rem, drs); CK(cudaGetLastError()); ctx->launches++; }
+  if (n_add) { k_utxo_insert<<<nblk(n_add, 128), 128, 0, ctx->stream>>>(view_of(t), dak, dae, dab, n_add, das); CK(cudaGetLastError()); ctx->launches++; }
+  if (!dev) {
+    if (n_rem && rem_status) CK(cudaMemcpyAsync(rem_status, drs, n_rem, cudaMemcpyDeviceToHost, ctx->stream));
+    if (n_add && add_status) CK(cudaMemcpyAsync(add_status, das, n_add, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  return KGV_OK;
+}
+
+extern "C" int kgv_utxo_count(kgv_ctx* ctx, kgv_utxo_table* t, uint64_t* count) {
+  if (!ctx || !t || !count) return KGV_ERR_ARG;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  CK(cudaSetDevice(ctx->device));
+  unsigned long long c[4];
+  CK(cudaMemcpyAsync(c, t->counters, sizeof c, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (c[3]) { ctx->err = "UTXO table insert failures (table or overflow arena full)"; return KGV_ERR_NOMEM; }
+  *count = c[0];
+  return KGV_OK;
+}
+
+extern "C" int kgv_utxo_digest(kgv_ctx* ctx, kgv_utxo_table* t, uint8_t out32[32]) {
+  if (!ctx || !t || !out32) return KGV_ERR_ARG;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  CK(cudaSetDevice(ctx->device));
+  unsigned long long* acc = t->counters + 8;
+  CK(cudaMemsetAsync(acc, 0, 8 * sizeof(unsigned long long), ctx->stream));
+  k_utxo_digest<<<nblk(t->mask + 1, 128), 128, 0, ctx->stream>>>(view_of(t), acc);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  unsigned long long h[8];
+  CK(cudaMemcpyAsync(h, acc, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  unsigned __int128 c = 0;
+  for (int i = 0; i < 8; i++) {  // fold the 32-bit limb sums into a 256-bit little-endian integer (mod 2^256)
+    c += h[i];
+    uint32_t limb = (uint32_t)c;
+    c >>= 32;
+    for (int b = 0; b < 4; b++) out32[4 * i + b] = (uint8_t)(limb >> (8 * b));
+  }
+  return KGV_OK;
+}
+
+// shared core of kgv_validate_populated / kgv_validate_txs
+static int validate_core(kgv_ctx* ctx, kgv_utxo_table* table, const kgv_tx_batch* batch, uint64_t pov, uint32_t flags, const kgv_params* prm,
+                         kgv_tx_result* results) {
+  if (!batch || !prm || (batch->n_txs && !results)) { ctx->err = "null argument"; return KGV_ERR_ARG; }
+  if (flags > KGV_FLAGS_SKIP_MASS_CHECK) { ctx->err = "unknown validation flags"; return KGV_ERR_ARG; }
+  if (batch->n_txs == 0) return KGV_OK;
+  CK(cudaSetDevice(ctx->device));
+  kgv_dev_batch d;
+  int rc = kgv_batch_to_device(ctx, batch, &d, table == nullptr);
+  if (rc) return rc;
+  const size_t nt = d.n_txs, ni = d.n_inputs;
+  const size_t max_items = ni * 110 < ((size_t)1 << 26) ? 0 : 0;  // (sized after the scan)
+  (void)max_items;
+  // scratch layout (phase 1)
+  size_t o_ent = 0;
+  size_t o_itx = al256(o_ent + ni * sizeof(DevEntry));
+  size_t o_res = al256(o_itx + ni * 4);
+  size_t o_plan = al256(o_res + nt * sizeof(kgv_tx_result));
+  size_t o_cs = al256(o_plan + ni * sizeof(InputPlan));
+  size_t o_ce = al256(o_cs + ni * 4);
+  size_t o_os = al256(o_ce + ni * 4);
+  size_t o_oe = al256(o_os + ni * 4);
+  size_t o_tot = al256(o_oe + ni * 4);
+  size_t o_err = al256(o_tot + 64);
+  size_t o_reu = al256(o_err + ni);
+  size_t phase1 = al256(o_reu + nt * sizeof(SigHashReused));
+  rc = kgv_reserve(ctx, &ctx->d_scratch, &ctx->d_scratch_cap, phase1);
+  if (rc) return rc;
+  uint8_t* S = ctx->d_scratch;
+  DevEntry* dent = (DevEntry*)(S + o_ent);
+  uint32_t* itx = (uint32_t*)(S + o_itx);
+  kgv_tx_result* dres = (kgv_tx_result*)(S + o_res);
+  InputPlan* plans = (InputPlan*)(S + o_plan);
+  uint32_t *cs = (uint32_t*)(S + o_cs), *ce = (uint32_t*)(S + o_ce), *os = (uint32_t*)(S + o_os), *oe = (uint32_t*)(S + o_oe), *tot = (uint32_t*)(S + o_tot);
+  uint8_t* ierr = S + o_err;
+  SigHashReused* reu = (SigHashReused*)(S + o_reu);
+  cudaStream_t st = ctx->stream;
+
+  if (ni) {
+    if (table) k_populate<<<nblk(ni, 128), 128, 0, st>>>(view_of(table), d.inputs, ni, dent);
+    else k_entries_from_batch<<<nblk(ni, 128), 128, 0, st>>>(d.entries, d.bytes, ni, dent);
+    CK(cudaGetLastError());
+    k_input_tx_index<<<nblk(nt, 128), 128, 0, st>>>(d.txs, (uint32_t)nt, itx);
+    CK(cudaGetLastError());
+    ctx->launches += 2;
+  }
+  BatchView v{d.txs, d.inputs, d.outputs, dent, d.bytes};
+  k_tx_context<<<nblk(nt, 128), 128, 0, st>>>(v, (uint32_t)nt, pov, flags, *prm, dres);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  if (flags != KGV_FLAGS_SKIP_SCRIPT_CHECKS && ni) {
+    k_plan<<<nblk(ni, 128), 128, 0, st>>>(v, ni, itx, dres, plans, cs, ce);
+    CK(cudaGetLastError());
+    k_exclusive_scan<<<1, 1024, 0, st>>>(cs, os, ni, tot);
+    CK(cudaGetLastError());
+    k_exclusive_scan<<<1, 1024, 0, st>>>(ce, oe, ni, tot + 1);
+    CK(cudaGetLastError());
+    ctx->launches += 3;
+    uint32_t totals[2];
+    CK(cudaMemcpyAsync(totals, tot, sizeof totals, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    size_t ns = totals[0], ne = totals[1];
+    // item arrays (phase 2) live in d_in (pk/sig/msg) and d_out (status/refs): both unused by this call so far unless the batch was host-resident
+    size_t i_pks = 0, i_sigs = al256(i_pks + ns * 32), i_msgs = al256(i_sigs + ns * 64), i_refs = al256(i_msgs + ns * 32), i_sts = al256(i_refs + ns * sizeof(ItemRef));
+    size_t i_pke = al256(i_sts + ns), i_sige = al256(i_pke + ne * 33), i_msge = al256(i_sige + ne * 64), i_refe = al256(i_msge + ne * 32), i_ste = al256(i_refe + ne * sizeof(ItemRef));
+    size_t total2 = al256(i_ste + ne + 64);
+    rc = kgv_reserve(ctx, &ctx->d_in, &ctx->d_in_cap, total2);
+    if (rc) return rc;
+    uint8_t* I = ctx->d_in;
+    if (ns + ne) {
+      k_emit_items<<<nblk(ni, 128), 128, 0, st>>>(v, ni, plans, os, oe, I + i_pks, I + i_sigs, (ItemRef*)(I + i_refs), I + i_pke, I + i_sige, (ItemRef*)(I + i_refe));
+      CK(cudaGetLastError());
+      k_sighash_reused_v<<<nblk(nt, 128), 128, 0, st>>>(v, (uint32_t)nt, dres, reu);
+      CK(cudaGetLastError());
+      ctx->launches += 2;
+    }
+    if (ns) {
+      k_item_msgs<<<nblk(ns, 128), 128, 0, st>>>(v, reu, itx, plans, (const ItemRef*)(I + i_refs), ns, false, (uint32_t*)(I + i_msgs));
+      CK(cudaGetLastError());
+      ctx->launches++;
+      rc = kgv_launch_verify(ctx, I + i_pks, I + i_msgs, I + i_sigs, ns, I + i_sts, false);
+      if (rc) return rc;
+    }
+    if (ne) {
+      k_item_msgs<<<nblk(ne, 128), 128, 0, st>>>(v, reu, itx, plans, (const ItemRef*)(I + i_refe), ne, true, (uint32_t*)(I + i_msge));
+      CK(cudaGetLastError());
+      ctx->launches++;
+      rc = kgv_launch_verify(ctx, I + i_pke, I + i_msge, I + i_sige, ne, I + i_ste, true);
+      if (rc) return rc;
+    }
+    k_resolve<<<nblk(ni, 128), 128, 0, st>>>(v, ni, itx, dres, plans, I + i_sts, I + i_ste, ierr);
+    CK(cudaGetLastError());
+    k_tx_finalize<<<nblk(nt, 128), 128, 0, st>>>(v, (uint32_t)nt, ierr, dres);
+    CK(cudaGetLastError());
+    ctx->launches += 2;
+  }
+  if (kgv_ptr_is_device(results)) {
+    CK(cudaMemcpyAsync(results, dres, nt * sizeof(kgv_tx_result), cudaMemcpyDeviceToDevice, st));
+  } else {
+    CK(cudaMemcpyAsync(results, dres, nt * sizeof(kgv_tx_result), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+  }
+  return KGV_OK;
+}
+
+extern "C" int kgv_validate_populated(kgv_ctx* ctx, const kgv_tx_batch* batch, uint64_t pov_daa_score, uint32_t flags, const kgv_params* params,
+                                      kgv_tx_result* results) {
+  if (!ctx) return KGV_ERR_ARG;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  return validate_core(ctx, nullptr, batch, pov_daa_score, flags, params, results);
+}
+extern "C" int kgv_validate_txs(kgv_ctx* ctx, kgv_utxo_table* t, const kgv_tx_batch* batch, uint64_t pov_daa_score, uint32_t flags, const kgv_params* params,
+                                kgv_tx_result* results) {
+  if (!ctx || !t) return KGV_ERR_ARG;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  return validate_core(ctx, t, batch, pov_daa_score, flags, params, results);
+}
+
+extern "C" int kgv_utxo_apply_accepted(kgv_ctx* ctx, kgv_utxo_table* t, const kgv_tx_batch* batch, const uint8_t* accept, uint64_t pov_daa_score) {
+  if (!ctx || !t) return KGV_ERR_ARG;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  if (!batch || (batch->n_txs && !accept)) { ctx->err = "null argument"; return KGV_ERR_ARG; }
+  if (batch->n_txs == 0) return KGV_OK;
+  CK(cudaSetDevice(ctx->device));
+  kgv_dev_batch d;
+  int rc = kgv_batch_to_device(ctx, batch, &d, false);
+  if (rc) return rc;
+  size_t nt = d.n_txs, ni = d.n_inputs, no = d.n_outputs;
+  size_t o_itx = 0, o_otx = al256(ni * 4), o_ids = al256(o_otx + no * 4), o_acc = al256(o_ids + nt * 32);
+  rc = kgv_reserve(ctx, &ctx->d_scratch, &ctx->d_scratch_cap, al256(o_acc + nt));
+  if (rc) return rc;
+  uint8_t* S = ctx->d_scratch;
+  const uint8_t* dacc = accept;
+  if (!kgv_ptr_is_device(accept)) {
+    CK(cudaMemcpyAsync(S + o_acc, accept, nt, cudaMemcpyHostToDevice, ctx->stream));
+    dacc = S + o_acc;
+  }
+  BatchView v{d.txs, d.inputs, d.outputs, nullptr, d.bytes};
+  cudaStream_t st = ctx->stream;
+  k_tx_ids_dev<<<nblk(nt, 128), 128, 0, st>>>(v, (uint32_t)nt, (uint64_t*)(S + o_ids));
+  CK(cudaGetLastError());
+  k_input_tx_index<<<nblk(nt, 128), 128, 0, st>>>(d.txs, (uint32_t)nt, (uint32_t*)(S + o_itx));
+  CK(cudaGetLastError());
+  k_output_tx_index<<<nblk(nt, 128), 128, 0, st>>>(d.txs, (uint32_t)nt, (uint32_t*)(S + o_otx));
+  CK(cudaGetLastError());
+  ctx->launches += 3;
+  if (ni) { k_apply_erase<<<nblk(ni, 128), 128, 0, st>>>(view_of(t), d.txs, d.inputs, ni, (const uint32_t*)(S + o_itx), dacc); CK(cudaGetLastError()); ctx->launches++; }
+  if (no) { k_apply_insert<<<nblk(no, 128), 128, 0, st>>>(view_of(t), v, no, (const uint32_t*)(S + o_otx), dacc, (const uint64_t*)(S + o_ids), pov_daa_score); CK(cudaGetLastError()); ctx->launches++; }
+  if (!kgv_ptr_is_device(accept)) CK(cudaStreamSynchronize(st));
+  return KGV_OK;
+}

@@ -1,0 +1,257 @@
+"""simpa-shaped DAG workload generator (BASELINE configs 1, 3, 4, 5), seeded and self-contained.
+
+Restates the *shape* of what simpa's miner emits (simpa/src/simulator/miner.rs:138-207: native-subnetwork
+version-0 transactions spending the miner's own earlier outputs, P2PK Schnorr `20 <xonly> ac` outputs,
+`41 <sig64> 01` signature scripts, sig_op_count = 1, storage mass committed with C from
+simpa/src/main.rs:205, <= --tpb transactions per block) and extends it as BASELINE.json asks:
+2-in/2-out transactions (config 3), P2PK-ECDSA and P2SH 2-of-3 multisig (config 4), and a small
+fraction of deliberately invalid transactions.  simpa itself uses thread_rng, so its exact DAGs are
+not reproducible; this generator is.
+
+Blocks are produced as a linearised schedule (one merged block per "chain block", pov_daa_score =
+block index): GHOSTDAG ordering is out of scope, the consumer replays the schedule.
+
+No elliptic-curve library and nothing from oracle/ is used: keys and nonces come from
+workload.ScalarPointPool, signatures are scalar arithmetic over those pools.
+"""
+import hashlib
+import struct
+
+import numpy as np
+
+from . import workload as W
+
+N = W.N
+SUBNET_NATIVE = bytes(20)
+SUBNET_COINBASE = bytes([1]) + bytes(19)
+SIGHASH_ALL = 1
+DEFAULT_STORAGE_MASS_PARAMETER = 10_000  # simpa/src/main.rs:205
+DEFAULT_COINBASE_MATURITY = 200          # simpa/src/main.rs:204
+
+KIND_P2PK, KIND_P2PK_ECDSA, KIND_MS, KIND_MS_ECDSA = 0, 1, 2, 3
+
+
+def _h(domain, data):
+    return hashlib.blake2b(data, digest_size=32, key=domain).digest()
+
+
+def _varbytes(b):
+    return struct.pack("<Q", len(b)) + b
+
+
+def _enc_output(o):
+    return struct.pack("<QH", o["value"], o["spk_version"]) + _varbytes(o["script"])
+
+
+def tx_id(tx):
+    """hashing/tx.rs:30-42"""
+    cb = tx["subnetwork_id"] == SUBNET_COINBASE
+    b = struct.pack("<HQ", tx["version"], len(tx["inputs"]))
+    for i in tx["inputs"]:
+        b += i["txid"] + struct.pack("<I", i["index"])
+        b += (_varbytes(i["sigscript"]) + bytes([i["sig_op_count"]])) if cb else _varbytes(b"")
+        b += struct.pack("<Q", i["sequence"])
+    b += struct.pack("<Q", len(tx["outputs"])) + b"".join(_enc_output(o) for o in tx["outputs"])
+    b += struct.pack("<Q", tx["lock_time"]) + tx["subnetwork_id"] + struct.pack("<Q", tx["gas"]) + _varbytes(tx["payload"])
+    if cb and tx.get("mass", 0) > 0:
+        b += struct.pack("<Q", tx["mass"])
+    return _h(b"TransactionID", b)
+
+
+def sighash_all(tx, entries, idx, ecdsa):
+    """hashing/sighash.rs:238-277 for SIG_HASH_ALL"""
+    H = lambda d: _h(b"TransactionSigningHash", d)
+    prev = H(b"".join(i["txid"] + struct.pack("<I", i["index"]) for i in tx["inputs"]))
+    seqs = H(b"".join(struct.pack("<Q", i["sequence"]) for i in tx["inputs"]))
+    sops = H(bytes(i["sig_op_count"] for i in tx["inputs"]))
+    outs = H(b"".join(_enc_output(o) for o in tx["outputs"]))
+    pay = bytes(32) if (tx["subnetwork_id"] == SUBNET_NATIVE and not tx["payload"]) else H(_varbytes(tx["payload"]))
+    i, e = tx["inputs"][idx], entries[idx]
+    pre = (struct.pack("<H", tx["version"]) + prev + seqs + sops + i["txid"] + struct.pack("<I", i["index"])
+           + struct.pack("<H", e["spk_version"]) + _varbytes(e["script"]) + struct.pack("<QQ", e["amount"], i["sequence"])
+           + bytes([i["sig_op_count"]]) + outs + struct.pack("<Q", tx["lock_time"]) + tx["subnetwork_id"]
+           + struct.pack("<Q", tx["gas"]) + pay + bytes([SIGHASH_ALL]))
+    d = H(pre)
+    if ecdsa:
+        d = hashlib.sha256(hashlib.sha256(b"TransactionSigningHashECDSA").digest() + d).digest()
+    return d
+
+
+def storage_mass(in_amounts_scriptlens, out_values_scriptlens, C):
+    """consensus/core/src/mass/mod.rs:338-410 (non-coinbase, no overflow expected for generator values)"""
+    plur = lambda l: (63 + l + 99) // 100
+    outs_plur = sum(plur(l) for _, l in out_values_scriptlens)
+    harm_outs = sum(C * plur(l) * plur(l) // v for v, l in out_values_scriptlens)
+    ins_plur = sum(plur(l) for _, l in in_amounts_scriptlens)
+    n_in = len(in_amounts_scriptlens)
+    if outs_plur == 1 or (n_in <= 2 and (ins_plur == 1 or (outs_plur == 2 and ins_plur == 2))):
+        harm_ins = sum(C * plur(l) * plur(l) // a for a, l in in_amounts_scriptlens)
+        return max(0, harm_outs - harm_ins)
+    mean = sum(a for a, _ in in_amounts_scriptlens) // ins_plur
+    return max(0, harm_outs - ins_plur * (C // mean))
+
+
+def _push(data):
+    n = len(data)
+    if n <= 75:
+        return bytes([n]) + data
+    if n <= 255:
+        return bytes([0x4C, n]) + data
+    return bytes([0x4D, n & 0xFF, n >> 8]) + data
+
+
+class SimDag:
+    """Seeded generator of blocks of signed transactions with a private view of the spendable outputs."""
+
+    def __init__(self, seed=0x6B61737061, n_keys=1024, n_nonces=4096, storage_mass_parameter=DEFAULT_STORAGE_MASS_PARAMETER,
+                 coinbase_maturity=DEFAULT_COINBASE_MATURITY, mix=(1.0, 0.0, 0.0, 0.0), frac_two_inputs=0.5, frac_invalid=0.0,
+                 coinbase_outputs=8, subsidy=50_000_000_000):
+        self.rng = np.random.default_rng(seed)
+        self.keys = W.ScalarPointPool(n_keys, seed, b"sim-keys")
+        self.nonces = W.ScalarPointPool(n_nonces, seed, b"sim-nonces")
+        self.kinv = [pow(k, -1, N) for k in self.nonces.scalars]
+        self.C = storage_mass_parameter
+        self.maturity = coinbase_maturity
+        self.mix = np.array(mix, dtype=float) / sum(mix)
+        self.frac_two_inputs = frac_two_inputs
+        self.frac_invalid = frac_invalid
+        self.coinbase_outputs = coinbase_outputs
+        self.subsidy = subsidy
+        self.utxos = []  # dicts: txid, index, amount, script, kind, keys(list of key idx), redeem, daa, coinbase
+        self.daa = 0
+        self.n_signatures = 0
+
+    # ---- scripts -------------------------------------------------------------------------------
+    def _new_output_script(self):
+        kind = int(self.rng.choice(4, p=self.mix))
+        if kind == KIND_P2PK:
+            k = int(self.rng.integers(0, self.keys.count))
+            return kind, [k], None, bytes([0x20]) + self.keys.xs[k] + bytes([0xAC])
+        if kind == KIND_P2PK_ECDSA:
+            k = int(self.rng.integers(0, self.keys.count))
+            return kind, [k], None, bytes([0x21, 0x02]) + self.keys.xs[k] + bytes([0xAB])
+        ks = [int(x) for x in self.rng.choice(self.keys.count, size=3, replace=False)]
+        if kind == KIND_MS:
+            redeem = bytes([0x52]) + b"".join(bytes([0x20]) + self.keys.xs[k] for k in ks) + bytes([0x53, 0xAE])
+        else:
+            redeem = bytes([0x52]) + b"".join(bytes([0x21, 0x02]) + self.keys.xs[k] for k in ks) + bytes([0x53, 0xA9])
+        spk = bytes([0xAA, 0x20]) + hashlib.blake2b(redeem, digest_size=32).digest() + bytes([0x87])
+        return kind, ks, redeem, spk
+
+    def _sign(self, key_idx, msg, ecdsa):
+        j = int(self.rng.integers(0, self.nonces.count))
+        d, k = self.keys.scalars[key_idx], self.nonces.scalars[j]
+        self.n_signatures += 1
+        if not ecdsa:
+            e = W._challenge(self.nonces.xs[j], self.keys.xs[key_idx], msg)
+            return self.nonces.xs[j] + ((k + e * d) % N).to_bytes(32, "big")
+        r = int.from_bytes(self.nonces.xs[j], "big") % N
+        s = self.kinv[j] * (int.from_bytes(msg, "big") + r * d) % N
+        if s > N // 2:
+            s = N - s
+        return r.to_bytes(32, "big") + s.to_bytes(32, "big")
+
+    # ---- blocks --------------------------------------------------------------------------------
+    def make_block(self, n_txs):
+        """Returns (txs, pov_daa_score): txs[0] is the coinbase; the rest spend earlier outputs."""
+        self.daa += 1
+        pov = self.daa
+        txs = []
+        cb_outs = []
+        created = []
+        for _ in range(self.coinbase_outputs):
+            kind, ks, redeem, spk = self._new_output_script()
+            cb_outs.append({"value": self.subsidy // self.coinbase_outputs, "spk_version": 0, "script": spk})
+            created.append((kind, ks, redeem))
+        cb = {"version": 0, "inputs": [], "outputs": cb_outs, "lock_time": 0, "subnetwork_id": SUBNET_COINBASE, "gas": 0,
+              "payload": struct.pack("<Q", pov) + b"kgv-sim", "mass": 0}
+        txs.append(cb)
+        new_utxos = [self._utxo(cb, i, created[i], pov, True) for i in range(len(cb_outs))]
+        spent_in_block = set()
+        for _ in range(n_txs):
+            tx = self._make_tx(pov, spent_in_block, new_utxos)
+            if tx is not None:
+                txs.append(tx)
+        self.utxos.extend(new_utxos)
+        return txs, pov
+
+    def _utxo(self, tx, index, created, daa, coinbase, txid=None):
+        kind, ks, redeem = created
+        o = tx["outputs"][index]
+        return {"txid": txid if txid is not None else tx_id(tx), "index": index, "amount": o["value"], "script": o["script"], "kind": kind,
+                "keys": ks, "redeem": redeem, "daa": daa, "coinbase": coinbase}
+
+    def _pick(self, pov, spent_in_block):
+        for _ in range(50):
+            if not self.utxos:
+                return None
+            i = int(self.rng.integers(0, len(self.utxos)))
+            u = self.utxos[i]
+            if u["coinbase"] and u["daa"] + self.maturity > pov:
+                continue
+            if u["amount"] < 4 or (u["txid"], u["index"]) in spent_in_block:
+                continue
+            self.utxos[i] = self.utxos[-1]
+            self.utxos.pop()
+            spent_in_block.add((u["txid"], u["index"]))
+            return u
+        return None
+
+    def _make_tx(self, pov, spent_in_block, new_utxos):
+        n_in = 2 if self.rng.random() < self.frac_two_inputs else 1
+        ins = [u for u in (self._pick(pov, spent_in_block) for _ in range(n_in)) if u is not None]
+        if not ins:
+            return None
+        total = sum(u["amount"] for u in ins)
+        fee = 1
+        created, outs = [], []
+        v0 = (total - fee) // 2
+        for v in (v0, total - fee - v0):
+            kind, ks, redeem, spk = self._new_output_script()
+            outs.append({"value": v, "spk_version": 0, "script": spk})
+            created.append((kind, ks, redeem))
+        tx = {"version": 0, "inputs": [{"txid": u["txid"], "index": u["index"], "sigscript": b"", "sequence": 0,
+                                          "sig_op_count": 1 if u["kind"] in (KIND_P2PK, KIND_P2PK_ECDSA) else 3} for u in ins],
+              "outputs": outs, "lock_time": 0, "subnetwork_id": SUBNET_NATIVE, "gas": 0, "payload": b"", "mass": 0}
+        tx["mass"] = storage_mass([(u["amount"], len(u["script"])) for u in ins], [(o["value"], len(o["script"])) for o in outs], self.C)
+        invalid = self.rng.random() < self.frac_invalid
+        mode = int(self.rng.integers(0, 8)) if invalid else -1
+        k0 = ins[0]["kind"]
+        if (mode == 5 and k0 not in (KIND_P2PK_ECDSA,)) or (mode == 7 and k0 not in (KIND_MS, KIND_MS_ECDSA)) or (mode == 6 and k0 in (KIND_MS, KIND_MS_ECDSA)):
+            mode = 4
+        if mode == 0:
+            tx["mass"] += 1                                   # WrongMass
+        elif mode == 1:
+            tx["outputs"][0]["value"] += total                 # SpendTooHigh
+        elif mode == 2:
+            tx["inputs"][0]["txid"] = bytes(self.rng.integers(0, 256, 32, dtype=np.uint8))  # MissingTxOutpoints
+        elif mode == 3:
+            tx["inputs"][0]["sig_op_count"] = 0                # ExceededSigOpLimit
+        entries = [{"amount": u["amount"], "spk_version": 0, "script": u["script"]} for u in ins]
+        for idx, u in enumerate(ins):
+            ecdsa = u["kind"] in (KIND_P2PK_ECDSA, KIND_MS_ECDSA)
+            msg = sighash_all(tx, entries, idx, ecdsa)
+            if u["kind"] in (KIND_P2PK, KIND_P2PK_ECDSA):
+                sig = self._sign(u["keys"][0], msg, ecdsa)
+                if mode == 4 and idx == 0:
+                    sig = sig[:40] + bytes([sig[40] ^ 1]) + sig[41:]   # EvalFalse
+                if mode == 5 and idx == 0 and ecdsa:
+                    sig = sig[:32] + (N - int.from_bytes(sig[32:], "big")).to_bytes(32, "big")  # high S
+                ht = 0x03 if (mode == 6 and idx == 0) else SIGHASH_ALL  # InvalidSigHashType
+                tx["inputs"][idx]["sigscript"] = bytes([0x41]) + sig + bytes([ht])
+            else:
+                pair = sorted(int(x) for x in self.rng.choice(3, size=2, replace=False))
+                if mode == 7 and idx == 0:
+                    pair = pair[::-1]                                   # wrong order => NullFail
+                sigs = [self._sign(u["keys"][p], msg, ecdsa) for p in pair]
+                if mode == 4 and idx == 0:
+                    sigs[1] = sigs[1][:40] + bytes([sigs[1][40] ^ 1]) + sigs[1][41:]
+                tx["inputs"][idx]["sigscript"] = b"".join(bytes([0x41]) + s + bytes([SIGHASH_ALL]) for s in sigs) + _push(u["redeem"])
+        if mode == -1:  # outputs only become spendable for the generator if the tx is valid
+            tid = tx_id(tx)
+            for i in range(len(outs)):
+                new_utxos.append(self._utxo(tx, i, created[i], pov, False, txid=tid))
+        else:
+            for u in ins:  # an invalid tx is not accepted: its inputs stay unspent
+                self.utxos.append(u)
+        return tx

@@ -1,0 +1,110 @@
+"""Host-side Python mirror of the validation surface of the reference, on top of the C ABI.
+
+    TransactionValidator.validate_populated_transactions  <->  validate_populated_transaction_and_get_fee
+        (consensus/src/processes/transaction_validator/tx_validation_in_utxo_context.rs:34-61)
+    GpuUtxoSet (get / apply_diff / count / digest)          <->  UtxoView::get, DbUtxoSetStore::write_diff_batch
+        (consensus/core/src/utxo/utxo_view.rs:5-7, consensus/src/model/stores/utxo_set.rs:107-112,143-152)
+    TransactionValidator.validate_transactions_in_parallel  <->  VirtualStateProcessor::validate_transactions_in_parallel
+        (consensus/src/pipeline/virtual_processor/utxo_validation.rs:262-278)
+    GpuUtxoSet.add_transactions                              <->  UtxoDiff::add_transaction (utxo_diff.rs:233-247)
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from .txbatch import ENTRY_DTYPE
+from .verifier import _c_batch
+
+RESULT_DTYPE = np.dtype([("fee", "<u8"), ("fail_input", "<u4"), ("status", "u1"), ("script_err", "u1"), ("pad_", "u1", (2,))])
+assert RESULT_DTYPE.itemsize == 16
+
+FLAGS_FULL, FLAGS_SKIP_SCRIPT_CHECKS, FLAGS_SKIP_MASS_CHECK = 0, 1, 2
+MAX_SOMPI = 29_000_000_000 * 100_000_000
+TX_OK, TX_NEEDS_HOST_VM, TX_SKIPPED_COINBASE = 0, 11, 12
+
+
+class Params(ctypes.Structure):
+    """kgv_params: the consensus parameters the path reads (consensus/core/src/config/params.rs)."""
+    _fields_ = [("coinbase_maturity", ctypes.c_uint64), ("storage_mass_parameter", ctypes.c_uint64), ("max_sompi", ctypes.c_uint64)]
+
+    def __init__(self, coinbase_maturity=100, storage_mass_parameter=10**12, max_sompi=MAX_SOMPI):
+        super().__init__(coinbase_maturity, storage_mass_parameter, max_sompi)
+
+
+class GpuUtxoSet:
+    """GPU-resident UTXO set (kgv_utxo_table)."""
+
+    def __init__(self, ctx, capacity_slots=1 << 20):
+        self.ctx = ctx
+        self._lib = ctx._lib
+        h = ctypes.c_void_p()
+        ctx._check(self._lib.kgv_utxo_create(ctx._h, int(capacity_slots), ctypes.byref(h)))
+        self._h = h
+
+    def close(self):
+        if self._h:
+            self._lib.kgv_utxo_destroy(self.ctx._h, self._h)
+            self._h = None
+
+    def get(self, keys36, script_stride=128):
+        """keys36: (n, 36) uint8. Returns (found (n,), entries (n,) ENTRY_DTYPE, scripts (n, stride))."""
+        keys36 = np.ascontiguousarray(keys36, dtype=np.uint8).reshape(-1, 36)
+        n = len(keys36)
+        ent = np.zeros(n, dtype=ENTRY_DTYPE)
+        scr = np.zeros((n, script_stride), dtype=np.uint8)
+        found = np.zeros(n, dtype=np.uint8)
+        if n:
+            self.ctx._check(self._lib.kgv_utxo_lookup(self.ctx._h, self._h, keys36.ctypes.data, n, ent.ctypes.data, scr.ctypes.data, script_stride, found.ctypes.data))
+        return found, ent, scr
+
+    def apply_diff(self, rem_keys36=None, add_keys36=None, add_entries=None, add_bytes=None):
+        """write_diff_batch: delete `rem_keys36`, then put (add_keys36, add_entries[script_off/len into add_bytes])."""
+        rk = np.zeros((0, 36), np.uint8) if rem_keys36 is None else np.ascontiguousarray(rem_keys36, dtype=np.uint8).reshape(-1, 36)
+        ak = np.zeros((0, 36), np.uint8) if add_keys36 is None else np.ascontiguousarray(add_keys36, dtype=np.uint8).reshape(-1, 36)
+        ae = np.zeros(0, ENTRY_DTYPE) if add_entries is None else np.ascontiguousarray(add_entries)
+        ab = np.zeros(8, np.uint8) if add_bytes is None else np.ascontiguousarray(add_bytes, dtype=np.uint8)
+        rs, as_ = np.zeros(max(len(rk), 1), np.uint8), np.zeros(max(len(ak), 1), np.uint8)
+        self.ctx._check(self._lib.kgv_utxo_apply_diff(self.ctx._h, self._h, rk.ctypes.data if len(rk) else None, len(rk), rs.ctypes.data,
+                                                      ak.ctypes.data if len(ak) else None, ae.ctypes.data if len(ak) else None, ab.ctypes.data, len(ab), len(ak),
+                                                      as_.ctypes.data))
+        return rs[:len(rk)], as_[:len(ak)]
+
+    def add_transactions(self, batch, accept, pov_daa_score):
+        """UtxoDiff::add_transaction for every tx with accept[i] != 0, applied to the table."""
+        acc = np.ascontiguousarray(accept, dtype=np.uint8)
+        cb = _c_batch(batch, with_entries=False)
+        self.ctx._check(self._lib.kgv_utxo_apply_accepted(self.ctx._h, self._h, ctypes.byref(cb), acc.ctypes.data, int(pov_daa_score)))
+
+    def count(self):
+        c = ctypes.c_uint64()
+        self.ctx._check(self._lib.kgv_utxo_count(self.ctx._h, self._h, ctypes.byref(c)))
+        return int(c.value)
+
+    def digest(self):
+        out = (ctypes.c_uint8 * 32)()
+        self.ctx._check(self._lib.kgv_utxo_digest(self.ctx._h, self._h, ctypes.addressof(out)))
+        return bytes(out)
+
+
+class TransactionValidator:
+    """Batch counterpart of the reference's TransactionValidator for the UTXO-context rules."""
+
+    def __init__(self, ctx, params=None):
+        self.ctx = ctx
+        self._lib = ctx._lib
+        self.params = params or Params()
+
+    def validate_populated_transactions(self, batch, pov_daa_score, flags=FLAGS_FULL):
+        """batch.entries must hold the populated UtxoEntry of every input. Returns RESULT_DTYPE[n_txs]."""
+        res = np.zeros(batch.n_txs, dtype=RESULT_DTYPE)
+        cb = _c_batch(batch, with_entries=True)
+        self.ctx._check(self._lib.kgv_validate_populated(self.ctx._h, ctypes.byref(cb), int(pov_daa_score), int(flags), ctypes.byref(self.params), res.ctypes.data))
+        return res
+
+    def validate_transactions_in_parallel(self, utxo_set, batch, pov_daa_score, flags=FLAGS_FULL):
+        """Populate from the GPU UTXO set, then validate. Returns RESULT_DTYPE[n_txs] (coinbase: status 12)."""
+        res = np.zeros(batch.n_txs, dtype=RESULT_DTYPE)
+        cb = _c_batch(batch, with_entries=False)
+        self.ctx._check(self._lib.kgv_validate_txs(self.ctx._h, utxo_set._h, ctypes.byref(cb), int(pov_daa_score), int(flags), ctypes.byref(self.params), res.ctypes.data))
+        return res

@@ -1,0 +1,113 @@
+"""GPU parity: UTXO table + fused transaction validation (C ABI) vs the CPU oracle state on simulated DAGs."""
+import copy
+
+import numpy as np
+import pytest
+
+import oracle_tx
+from golden_util import entry_from_json, load, tx_from_json
+from rusty_kaspa_b200 import GpuUtxoSet, Params, TransactionValidator
+from rusty_kaspa_b200.simgen import SimDag
+from rusty_kaspa_b200.txbatch import ENTRY_DTYPE, build_batch
+
+pytestmark = pytest.mark.gpu
+
+
+def _same_results(got, exp):
+    """status / script error / failing input / fee must agree (fee only meaningful when the tx is accepted)."""
+    assert (got["status"] == exp["status"]).all(), np.nonzero(got["status"] != exp["status"])[0][:5]
+    assert (got["script_err"] == exp["script_err"]).all()
+    ok = got["status"] == 0
+    assert (got["fee"][ok] == exp["fee"][ok]).all()
+    bad = (got["status"] != 0) & (got["status"] != 12)
+    assert (got["fail_input"][bad] == exp["fail_input"][bad]).all()
+
+
+def test_reference_kats_through_the_gpu(gpu_ctx, oracle):
+    """real mainnet spends (tx_validation_in_utxo_context.rs:228-709) validated by kgv_validate_populated"""
+    tv = TransactionValidator(gpu_ctx, Params(coinbase_maturity=100, storage_mass_parameter=0))
+    for c in load("check_scripts_kat.json")["cases"]:
+        tx, entries = tx_from_json(c["tx"]), [entry_from_json(e) for e in c["entries"]]
+        tx2 = copy.deepcopy(tx)
+        tx2["inputs"].append(copy.deepcopy(tx2["inputs"][-1]))
+        b = build_batch([tx, tx2], [entries, entries + [copy.deepcopy(entries[-1])]])
+        res = tv.validate_populated_transactions(b, entries[0]["block_daa_score"] + 1000, flags=2)
+        for r, exp in zip(res, (c["expected"], c["expected_duplicated_input"])):
+            name = "Ok" if r["status"] == 0 else oracle_tx.SCRIPT_ERR[int(r["script_err"])]
+            if r["status"] == 11:
+                assert c["name"] in ("check_empty_incorrect_multi_signature_test", "check_non_push_only_script_sig_test")
+            elif exp == "AnyError":
+                assert r["status"] == 9
+            else:
+                assert name == exp, (c["name"], name, exp)
+
+
+def test_utxo_table_basic_semantics(gpu_ctx):
+    us = GpuUtxoSet(gpu_ctx, 1 << 12)
+    rng = np.random.default_rng(4)
+    n = 1500
+    keys = rng.integers(0, 256, size=(n, 36), dtype=np.uint8)
+    ent = np.zeros(n, dtype=ENTRY_DTYPE)
+    lens = rng.integers(0, 200, size=n)
+    lens[:10] = [0, 1, 34, 35, 67, 68, 69, 70, 150, 199]
+    arena = bytearray()
+    for i in range(n):
+        ent[i]["amount"], ent[i]["block_daa_score"], ent[i]["spk_version"], ent[i]["is_coinbase"] = int(rng.integers(1, 2**62)), int(rng.integers(0, 2**40)), int(rng.integers(0, 3)), int(rng.integers(0, 2))
+        ent[i]["script_off"], ent[i]["script_len"] = len(arena), int(lens[i])
+        arena.extend(rng.integers(0, 256, size=int(lens[i]), dtype=np.uint8).tobytes())
+    arena = np.frombuffer(bytes(arena) + bytes(8), dtype=np.uint8)
+    _, st = us.apply_diff(add_keys36=keys, add_entries=ent, add_bytes=arena)
+    assert (st == 1).all() and us.count() == n
+    found, got, scr = us.get(keys, script_stride=256)
+    assert found.all()
+    for f in ("amount", "block_daa_score", "spk_version", "is_coinbase", "script_len"):
+        assert (got[f] == ent[f]).all(), f
+    for i in range(n):
+        assert scr[i, :lens[i]].tobytes() == arena[ent[i]["script_off"]:ent[i]["script_off"] + lens[i]].tobytes()
+    # absent keys, erase, re-insert (tombstone reuse), replace
+    other = rng.integers(0, 256, size=(100, 36), dtype=np.uint8)
+    assert not us.get(other)[0].any()
+    rs, _ = us.apply_diff(rem_keys36=np.concatenate([keys[:700], other[:5]]))
+    assert (rs[:700] == 1).all() and (rs[700:] == 0).all() and us.count() == n - 700
+    f2 = us.get(keys)[0]
+    assert not f2[:700].any() and f2[700:].all()
+    _, st = us.apply_diff(add_keys36=keys[:800], add_entries=ent[:800], add_bytes=arena)
+    assert (st[:700] == 1).all() and (st[700:] == 2).all() and us.count() == n
+    assert us.get(keys)[0].all()
+    d1 = us.digest()
+    us2 = GpuUtxoSet(gpu_ctx, 1 << 13)
+    perm = rng.permutation(n)
+    us2.apply_diff(add_keys36=keys[perm], add_entries=ent[perm], add_bytes=arena)
+    assert us2.digest() == d1  # digest is order / layout independent
+    us.close(); us2.close()
+
+
+@pytest.mark.parametrize("mix,frac_invalid,blocks,tpb", [((1, 0, 0, 0), 0.1, 30, 40), ((0.4, 0.2, 0.2, 0.2), 0.15, 40, 24)])
+def test_dag_replay_matches_oracle(gpu_ctx, oracle, mix, frac_invalid, blocks, tpb):
+    """validate_transactions_in_parallel + add_transaction, block after block, against the oracle's composed view"""
+    dag = SimDag(seed=11, n_keys=96, n_nonces=128, mix=mix, frac_invalid=frac_invalid, coinbase_maturity=3, coinbase_outputs=6)
+    op = oracle_tx.params(coinbase_maturity=3, storage_mass_parameter=dag.C)
+    tv = TransactionValidator(gpu_ctx, Params(coinbase_maturity=3, storage_mass_parameter=dag.C))
+    us = GpuUtxoSet(gpu_ctx, 1 << 14)
+    ost = oracle_tx.State(oracle)
+    statuses = set()
+    for _ in range(blocks):
+        txs, pov = dag.make_block(tpb)
+        b = build_batch(txs)
+        exp = ost.validate(b, pov, 0, op, threads=2)
+        got = tv.validate_transactions_in_parallel(us, b, pov)
+        _same_results(got, exp)
+        statuses |= set((int(s), int(e)) for s, e in zip(got["status"], got["script_err"]))
+        acc = np.array([1 if (i == 0 or got[i]["status"] == 0) else 0 for i in range(len(txs))], dtype=np.uint8)
+        assert ost.accept(b, acc, pov) == 0
+        ost.commit()
+        us.add_transactions(b, acc, pov)
+        assert us.count() == ost.count()
+    assert us.digest() == ost.digest()
+    assert (0, 0) in statuses and len(statuses) >= 5
+    # SkipScriptChecks / SkipMassCheck flags
+    txs, pov = dag.make_block(tpb)
+    b = build_batch(txs)
+    for flags in (1, 2):
+        _same_results(tv.validate_transactions_in_parallel(us, b, pov, flags=flags), ost.validate(b, pov, flags, op, threads=2))
+    us.close(); ost.close()
