@@ -298,10 +298,18 @@ extern "C" uint64_t kgv_launch_count(const kgv_ctx* ctx) { return ctx ? ctx->lau
 // ---------------------------------------------------------------------------------------------
 int kgv_launch_verify(kgv_ctx* ctx, const uint8_t* dpk, const uint8_t* dmsg, const uint8_t* dsig, size_t n, uint8_t* dst, bool ecdsa) {
   if (n == 0) return KGV_OK;
-  {
-    int rc = kgv_launch_verify(ctx, dpk, dmsg, dsig, n, dst, ecdsa);
-    if (rc) return rc;
+  const int smem = KGV_BLOCK * 128 * (int)sizeof(uint32_t);
+  unsigned blocks = (unsigned)((n + KGV_BLOCK - 1) / KGV_BLOCK);
+  bool aligned = (((uintptr_t)dmsg | (uintptr_t)dsig | (ecdsa ? 0 : (uintptr_t)dpk)) & 31) == 0;
+  if (ecdsa) {
+    if (aligned) k_ecdsa_verify<true><<<blocks, KGV_BLOCK, smem, ctx->stream>>>(dpk, dmsg, dsig, n, dst, ctx->gtab);
+    else k_ecdsa_verify<false><<<blocks, KGV_BLOCK, smem, ctx->stream>>>(dpk, dmsg, dsig, n, dst, ctx->gtab);
+  } else {
+    if (aligned) k_schnorr_verify<true><<<blocks, KGV_BLOCK, smem, ctx->stream>>>(dpk, dmsg, dsig, n, dst, ctx->gtab);
+    else k_schnorr_verify<false><<<blocks, KGV_BLOCK, smem, ctx->stream>>>(dpk, dmsg, dsig, n, dst, ctx->gtab);
   }
+  CK(cudaGetLastError());
+  ctx->launches++;
   return KGV_OK;
 }
 

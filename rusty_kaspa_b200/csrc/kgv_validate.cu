@@ -33,6 +33,18 @@ using namespace kgv;
 
 static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 
+// KGV_DEBUG=1: synchronise and report after every stage of the fused path (locates a faulting kernel)
+#include <cstdlib>
+static bool kgv_debug_on() { static int v = -1; if (v < 0) v = getenv("KGV_DEBUG") ? 1 : 0; return v == 1; }
+#define STAGE(name)                                                                               \
+  do {                                                                                            \
+    if (kgv_debug_on()) {                                                                         \
+      cudaError_t e_ = cudaStreamSynchronize(ctx->stream);                                        \
+      fprintf(stderr, "[kgv] stage %s: %s\n", name, cudaGetErrorString(e_));                      \
+      fflush(stderr);                                                                             \
+    }                                                                                             \
+  } while (0)
+
 // ---------------------------------------------------------------------------------------------
 // UTXO table
 // ---------------------------------------------------------------------------------------------
@@ -114,30 +126,33 @@ __device__ __forceinline__ void slot_to_entry(DevEntry& e, const TableView& t, c
   e.found = 1;
 }
 
-// upsert; returns 1 inserted, 2 replaced, 0 failed (table or overflow arena full)
+// upsert; returns 1 inserted, 2 replaced, 0 failed (table or overflow arena full).
+// Keys inserted concurrently by one kernel must be distinct (API contract), so a slot another thread is
+// filling (BUSY) always belongs to a different key and is simply skipped: no thread ever waits on another.
 __device__ uint32_t table_put(const TableView& t, const uint32_t* k, uint64_t amount, uint64_t daa, uint32_t spk_version, uint32_t is_coinbase,
                               const uint8_t* script, uint32_t script_len) {
   uint64_t i = key_hash(k) & t.mask;
   UtxoSlot* target = nullptr;
+  UtxoSlot* tomb = nullptr;
   bool replace = false;
-  for (uint64_t probes = 0; probes <= t.mask; probes++) {
+  for (uint64_t probes = 0; probes <= t.mask; probes++, i = (i + 1) & t.mask) {
     UtxoSlot* s = &t.slots[i];
     uint32_t st = *(volatile uint32_t*)&s->state;
-    if (st == SLOT_BUSY) { probes--; continue; }  // another thread is filling this slot: wait for its key
     if (st == SLOT_FULL) {
       if (key_eq(s, k)) { target = s; replace = true; break; }
-    } else {  // empty or tombstone: try to claim it
-      uint32_t old = atomicCAS(&s->state, st, SLOT_BUSY);
-      if (old == st) {
-        target = s;
-        if (st == SLOT_TOMB) atomicAdd(&t.counters[1], (unsigned long long)-1);
-        break;
-      }
-      probes--;  // lost the race: look at the same slot again
       continue;
     }
-    i = (i + 1) & t.mask;
+    if (st == SLOT_TOMB) { if (!tomb) tomb = s; continue; }
+    if (st == SLOT_BUSY) continue;
+    // EMPTY: the key is not in the table. Prefer the first tombstone seen, else this slot.
+    if (tomb) {
+      if (atomicCAS(&tomb->state, SLOT_TOMB, SLOT_BUSY) == SLOT_TOMB) { target = tomb; atomicAdd(&t.counters[1], (unsigned long long)-1); break; }
+      tomb = nullptr;
+    }
+    if (atomicCAS(&s->state, SLOT_EMPTY, SLOT_BUSY) == SLOT_EMPTY) { target = s; break; }
+    // lost the race for this slot (it now holds another key): keep probing
   }
+  if (!target && tomb && atomicCAS(&tomb->state, SLOT_TOMB, SLOT_BUSY) == SLOT_TOMB) { target = tomb; atomicAdd(&t.counters[1], (unsigned long long)-1); }
   if (!target) { atomicAdd(&t.counters[3], 1ull); return 0; }
 #pragma unroll
   for (int w = 0; w < 9; w++) target->key[w] = k[w];
@@ -690,13 +705,16 @@ static int validate_core(kgv_ctx* ctx, kgv_utxo_table* table, const kgv_tx_batch
     CK(cudaGetLastError());
     ctx->launches += 2;
   }
+  STAGE("populate");
   BatchView v{d.txs, d.inputs, d.outputs, dent, d.bytes};
   k_tx_context<<<nblk(nt, 128), 128, 0, st>>>(v, (uint32_t)nt, pov, flags, *prm, dres);
   CK(cudaGetLastError());
   ctx->launches++;
+  STAGE("tx_context");
   if (flags != KGV_FLAGS_SKIP_SCRIPT_CHECKS && ni) {
     k_plan<<<nblk(ni, 128), 128, 0, st>>>(v, ni, itx, dres, plans, cs, ce);
     CK(cudaGetLastError());
+    STAGE("plan");
     k_exclusive_scan<<<1, 1024, 0, st>>>(cs, os, ni, tot);
     CK(cudaGetLastError());
     k_exclusive_scan<<<1, 1024, 0, st>>>(ce, oe, ni, tot + 1);
@@ -706,6 +724,7 @@ static int validate_core(kgv_ctx* ctx, kgv_utxo_table* table, const kgv_tx_batch
     CK(cudaMemcpyAsync(totals, tot, sizeof totals, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     size_t ns = totals[0], ne = totals[1];
+    if (kgv_debug_on()) fprintf(stderr, "[kgv] items: schnorr %zu ecdsa %zu\n", ns, ne);
     // item arrays (phase 2) live in d_in (pk/sig/msg) and d_out (status/refs): both unused by this call so far unless the batch was host-resident
     size_t i_pks = 0, i_sigs = al256(i_pks + ns * 32), i_msgs = al256(i_sigs + ns * 64), i_refs = al256(i_msgs + ns * 32), i_sts = al256(i_refs + ns * sizeof(ItemRef));
     size_t i_pke = al256(i_sts + ns), i_sige = al256(i_pke + ne * 33), i_msge = al256(i_sige + ne * 64), i_refe = al256(i_msge + ne * 32), i_ste = al256(i_refe + ne * sizeof(ItemRef));
@@ -719,23 +738,29 @@ static int validate_core(kgv_ctx* ctx, kgv_utxo_table* table, const kgv_tx_batch
       k_sighash_reused_v<<<nblk(nt, 128), 128, 0, st>>>(v, (uint32_t)nt, dres, reu);
       CK(cudaGetLastError());
       ctx->launches += 2;
+      STAGE("emit+reused");
     }
     if (ns) {
       k_item_msgs<<<nblk(ns, 128), 128, 0, st>>>(v, reu, itx, plans, (const ItemRef*)(I + i_refs), ns, false, (uint32_t*)(I + i_msgs));
       CK(cudaGetLastError());
       ctx->launches++;
+      STAGE("msgs schnorr");
       rc = kgv_launch_verify(ctx, I + i_pks, I + i_msgs, I + i_sigs, ns, I + i_sts, false);
       if (rc) return rc;
+      STAGE("verify schnorr");
     }
     if (ne) {
       k_item_msgs<<<nblk(ne, 128), 128, 0, st>>>(v, reu, itx, plans, (const ItemRef*)(I + i_refe), ne, true, (uint32_t*)(I + i_msge));
       CK(cudaGetLastError());
       ctx->launches++;
+      STAGE("msgs ecdsa");
       rc = kgv_launch_verify(ctx, I + i_pke, I + i_msge, I + i_sige, ne, I + i_ste, true);
       if (rc) return rc;
+      STAGE("verify ecdsa");
     }
     k_resolve<<<nblk(ni, 128), 128, 0, st>>>(v, ni, itx, dres, plans, I + i_sts, I + i_ste, ierr);
     CK(cudaGetLastError());
+    STAGE("resolve");
     k_tx_finalize<<<nblk(nt, 128), 128, 0, st>>>(v, (uint32_t)nt, ierr, dres);
     CK(cudaGetLastError());
     ctx->launches += 2;
