@@ -150,6 +150,61 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def measure_tx_validation(ctx, dev, n_txs, steps):
+    """Secondary metric of BASELINE.json ("txs-validated/sec"): config-3-shaped window of independent
+    1-in/2-out and 2-in/2-out P2PK Schnorr transactions validated against the GPU UTXO table by ONE
+    kgv_validate_txs call (populate + context rules + sighash + verify + resolve), device-resident batch,
+    then end to end with host arrays; followed by kgv_utxo_apply_accepted."""
+    import ctypes as C
+    import torch
+    from rusty_kaspa_b200 import GpuUtxoSet, Params, TransactionValidator, simgen
+    from rusty_kaspa_b200.txbatch import build_batch
+    from rusty_kaspa_b200.validator import RESULT_DTYPE
+    from rusty_kaspa_b200.verifier import _KgvTxBatch
+    t0 = time.perf_counter()
+    fkeys, fentries, txs = simgen.funded_window(n_txs)
+    b = build_batch(txs)
+    earr, earena = simgen.entries_to_arrays(fentries)
+    gen_s = time.perf_counter() - t0
+    n_sigs = int(b.n_inputs)
+    us = GpuUtxoSet(ctx, 4 * len(fkeys))
+    us.apply_diff(add_keys36=fkeys, add_entries=earr, add_bytes=earena)
+    tv = TransactionValidator(ctx, Params(coinbase_maturity=100, storage_mass_parameter=simgen.DEFAULT_STORAGE_MASS_PARAMETER))
+    res = tv.validate_transactions_in_parallel(us, b, 10)  # warm-up + correctness guard
+    assert (res["status"] == 0).all(), "funded window must validate completely"
+    # device-resident batch
+    dt = [torch.from_numpy(a.view(np.uint8).reshape(-1)).to(dev) for a in (b.txs, b.inputs, b.outputs, b.arena)]
+    dres = torch.empty(len(b.txs) * RESULT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+    cb = _KgvTxBatch(dt[0].data_ptr(), len(b.txs), dt[1].data_ptr(), len(b.inputs), dt[2].data_ptr(), len(b.outputs), None, dt[3].data_ptr(), len(b.arena))
+    lib, h = ctx._lib, ctx._h
+    stream = torch.cuda.current_stream(dev)
+    call = lambda: ctx._check(lib.kgv_validate_txs(h, us._h, C.byref(cb), 10, 0, C.byref(tv.params), dres.data_ptr()))
+    call(); stream.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        call()
+    e1.record(stream)
+    stream.synchronize()
+    dev_s = e0.elapsed_time(e1) * 1e-3 / steps
+    st = np.frombuffer(dres.cpu().numpy().tobytes(), dtype=RESULT_DTYPE)
+    assert (st["status"] == 0).all()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        tv.validate_transactions_in_parallel(us, b, 10)
+    e2e_s = (time.perf_counter() - t0) / steps
+    t0 = time.perf_counter()
+    us.add_transactions(b, np.ones(len(txs), dtype=np.uint8), 10)
+    n_after = us.count()
+    apply_s = time.perf_counter() - t0
+    assert n_after == 2 * len(txs)
+    us.close()
+    return {"workload": "window of independent P2PK-Schnorr txs (50% 1-in/2-out, 50% 2-in/2-out) vs GPU UTXO table, one kgv_validate_txs call",
+            "n_txs": len(txs), "n_sig_checks": n_sigs, "txs_per_s": len(txs) / dev_s, "sig_checks_per_s": n_sigs / dev_s,
+            "e2e_txs_per_s": len(txs) / e2e_s, "e2e_h2d_bytes": int(b.txs.nbytes + b.inputs.nbytes + b.outputs.nbytes + b.arena.nbytes),
+            "apply_accepted_ms": apply_s * 1e3, "ms_per_call": dev_s * 1e3, "generation_s": round(gen_s, 1)}
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -272,6 +327,11 @@ def run_ours(args, rank, world, local_rank):
         cpu = {"value": sample / dt, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": f"first {sample} triples of the same batch, C restatement of the reference path (oracle/), {threads} pthreads; verdicts identical to the GPU's"}
 
+    txv = None
+    if world == 1 and args.tx_window > 0:
+        with torch.cuda.stream(stream):
+            txv = measure_tx_validation(ctx, dev, args.tx_window, max(2, min(args.steps, 5)))
+
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32 limbs (256-bit modular integer)", "data": "synthetic",
@@ -286,7 +346,7 @@ def run_ours(args, rank, world, local_rank):
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 128 * n * world, "d2h_bytes_per_step": n * world,
                     "steps": e2e_steps, "how": "kgv_schnorr_verify through the C ABI with pinned host buffers: H2D + kernel + D2H + sync inside the timed region (host clock)"},
-            "gpu_launches": int(launches), "clocks": clocks}
+            "tx_validation": txv, "gpu_launches": int(launches), "clocks": clocks}
     print(json.dumps(line), flush=True)
 
 
@@ -298,6 +358,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=N_DEFAULT, help="triples per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--tx-window", type=int, default=32768, help="transactions in the secondary txs-validated/s measurement (0 = skip)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

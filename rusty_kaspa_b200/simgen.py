@@ -255,3 +255,54 @@ class SimDag:
             for u in ins:  # an invalid tx is not accepted: its inputs stay unspent
                 self.utxos.append(u)
         return tx
+
+
+def funded_window(n_txs, seed=0x6B61737061, n_keys=4096, n_nonces=4096, storage_mass_parameter=DEFAULT_STORAGE_MASS_PARAMETER, two_input_fraction=0.5):
+    """BASELINE config 3 as one pre-verification window: `n_txs` mutually independent P2PK-Schnorr transactions
+    (50 % 1-in/2-out, 50 % 2-in/2-out) spending distinct funding outputs, i.e. what ~n_txs/150 consecutive
+    10-BPS blocks carry.  Returns (funding_keys36 (m,36) u8, funding_entries list of entry dicts, txs list of tx dicts).
+    The funding outputs are to be loaded into the UTXO set first (kgv_utxo_apply_diff)."""
+    rng = np.random.default_rng(seed)
+    keys = W.ScalarPointPool(n_keys, seed, b"win-keys")
+    nonces = W.ScalarPointPool(n_nonces, seed, b"win-nonces")
+    fund_keys, fund_entries, txs = [], [], []
+    for t in range(n_txs):
+        n_in = 2 if rng.random() < two_input_fraction else 1
+        ins, ents, kidx = [], [], []
+        for _ in range(n_in):
+            k = int(rng.integers(0, keys.count))
+            txid = hashlib.blake2b(struct.pack("<QQ", seed & 0xFFFFFFFFFFFF, len(fund_keys)), digest_size=32).digest()
+            amount = int(rng.integers(10**8, 10**11))
+            spk = bytes([0x20]) + keys.xs[k] + bytes([0xAC])
+            fund_keys.append(txid + struct.pack("<I", 0))
+            fund_entries.append({"amount": amount, "spk_version": 0, "script": spk, "block_daa_score": 1, "is_coinbase": False})
+            ins.append({"txid": txid, "index": 0, "sigscript": b"", "sequence": 0, "sig_op_count": 1})
+            ents.append(fund_entries[-1])
+            kidx.append(k)
+        total = sum(e["amount"] for e in ents)
+        outs = []
+        for v in ((total - 1) // 2, total - 1 - (total - 1) // 2):
+            k = int(rng.integers(0, keys.count))
+            outs.append({"value": v, "spk_version": 0, "script": bytes([0x20]) + keys.xs[k] + bytes([0xAC])})
+        tx = {"version": 0, "inputs": ins, "outputs": outs, "lock_time": 0, "subnetwork_id": SUBNET_NATIVE, "gas": 0, "payload": b"", "mass": 0}
+        tx["mass"] = storage_mass([(e["amount"], 34) for e in ents], [(o["value"], 34) for o in outs], storage_mass_parameter)
+        for idx in range(n_in):
+            msg = sighash_all(tx, ents, idx, False)
+            j = int(rng.integers(0, nonces.count))
+            e = W._challenge(nonces.xs[j], keys.xs[kidx[idx]], msg)
+            s = (nonces.scalars[j] + e * keys.scalars[kidx[idx]]) % N
+            tx["inputs"][idx]["sigscript"] = bytes([0x41]) + nonces.xs[j] + s.to_bytes(32, "big") + bytes([SIGHASH_ALL])
+        txs.append(tx)
+    return np.frombuffer(b"".join(fund_keys), dtype=np.uint8).reshape(-1, 36).copy(), fund_entries, txs
+
+
+def entries_to_arrays(entries):
+    """list of entry dicts -> (ENTRY_DTYPE array, byte arena) for kgv_utxo_apply_diff"""
+    from .txbatch import ENTRY_DTYPE
+    arr = np.zeros(len(entries), dtype=ENTRY_DTYPE)
+    arena = bytearray()
+    for i, e in enumerate(entries):
+        arr[i]["amount"], arr[i]["block_daa_score"], arr[i]["spk_version"], arr[i]["is_coinbase"] = e["amount"], e.get("block_daa_score", 0), e["spk_version"], 1 if e.get("is_coinbase") else 0
+        arr[i]["script_off"], arr[i]["script_len"] = len(arena), len(e["script"])
+        arena.extend(e["script"])
+    return arr, np.frombuffer(bytes(arena) + bytes(8), dtype=np.uint8).copy()
