@@ -233,6 +233,67 @@ int kgv_validate_txs(kgv_ctx* ctx, kgv_utxo_table* t, const kgv_tx_batch* batch,
  * is_coinbase of the tx (tx ids are computed on the device). */
 int kgv_utxo_apply_accepted(kgv_ctx* ctx, kgv_utxo_table* t, const kgv_tx_batch* batch, const uint8_t* accept, uint64_t pov_daa_score);
 
+/* ------------------------------------------------------------------------------------------------
+ * Host script engine for non-standard scripts (KGV_TX_NEEDS_HOST_VM)
+ * Complete restatement of TxScriptEngine (crypto/txscript/src/lib.rs:83-98,276-643, opcodes/mod.rs,
+ * data_stack.rs); signature checks are resolved by a verdict provider, never computed on the CPU.
+ * ------------------------------------------------------------------------------------------------ */
+/* further TxScriptError variants only the full engine can produce (crypto/txscript/errors/src/lib.rs) */
+#define KGV_SCRIPT_NOT_PUSH_ONLY 8
+#define KGV_SCRIPT_CLEAN_STACK 9
+#define KGV_SCRIPT_EMPTY_STACK 10
+#define KGV_SCRIPT_ELEMENT_TOO_BIG 11
+#define KGV_SCRIPT_TOO_MANY_OPERATIONS 12
+#define KGV_SCRIPT_STACK_SIZE_EXCEEDED 13
+#define KGV_SCRIPT_OPCODE_DISABLED 14
+#define KGV_SCRIPT_OPCODE_RESERVED 15
+#define KGV_SCRIPT_INVALID_OPCODE 16
+#define KGV_SCRIPT_MALFORMED_PUSH 17
+#define KGV_SCRIPT_MALFORMED_PUSH_SIZE 18
+#define KGV_SCRIPT_NOT_MINIMAL_DATA 19
+#define KGV_SCRIPT_UNBALANCED_CONDITIONAL 20
+#define KGV_SCRIPT_COND_STACK_EMPTY 21    /* InvalidState("condition stack empty")       */
+#define KGV_SCRIPT_EXPECTED_BOOLEAN 22    /* InvalidState("expected boolean")            */
+#define KGV_SCRIPT_PICK_INVALID 23        /* InvalidState("pick at an invalid location") */
+#define KGV_SCRIPT_ROLL_INVALID 24        /* InvalidState("roll at an invalid location") */
+#define KGV_SCRIPT_VERIFY 25
+#define KGV_SCRIPT_EARLY_RETURN 26
+#define KGV_SCRIPT_INVALID_STACK_OPERATION 27
+#define KGV_SCRIPT_NUMBER_TOO_BIG 28
+#define KGV_SCRIPT_INVALID_PUBKEY_COUNT 29
+#define KGV_SCRIPT_INVALID_SIGNATURE_COUNT 30
+#define KGV_SCRIPT_UNSATISFIED_LOCKTIME 31
+#define KGV_SCRIPT_SCRIPT_SIZE 32
+#define KGV_SCRIPT_NO_SCRIPTS 33
+#define KGV_SCRIPT_INVALID_INPUT_INDEX 34
+#define KGV_SCRIPT_INVALID_OUTPUT_INDEX 35
+#define KGV_SCRIPT_SERIALIZATION 36
+#define KGV_SCRIPT_NEEDS_SIG_VERDICTS 254 /* kgv_script_execute only: the provider did not know a verdict */
+
+typedef struct {
+  uint32_t tx, input;      /* absolute input index into batch->inputs */
+  uint8_t hash_type, ecdsa;
+  uint8_t key_len;         /* 32 or 33 */
+  uint8_t pad_;
+  uint8_t key[33];
+  uint8_t sig[64];
+  uint8_t pad2_[3];
+} kgv_sig_request; /* 112 bytes */
+/* returns KGV_SIG_* (0..3), or a negative value if the verdict is not available */
+typedef int (*kgv_verdict_fn)(void* user, const kgv_sig_request* request);
+
+/* TxScriptEngine::from_transaction_input(..).execute() for ONE input of a HOST-resident populated batch
+ * (lib.rs:276-300,399-449); `input_index` is relative to the transaction.  No GPU context is involved:
+ * every check_schnorr/ecdsa_signature (lib.rs:574-643) asks `verdict` (a SigCache, the GPU batch, ...).
+ * *script_err receives a KGV_SCRIPT_* code (0 = the input's scripts succeed). */
+int kgv_script_execute(const kgv_tx_batch* batch, uint32_t tx, uint32_t input_index, kgv_verdict_fn verdict, void* user, uint8_t* script_err);
+
+/* check_scripts (tx_validation_in_utxo_context.rs:162-200) with the full host engine for the listed
+ * transactions of a HOST-resident populated batch; the signature checks the scripts reach are gathered,
+ * hashed and verified on the GPU in batches (as many rounds as the scripts' control flow needs).
+ * results[i] belongs to tx_indices[i]: status KGV_TX_OK / KGV_TX_SIGNATURE_INVALID / KGV_TX_SIGNATURE_EMPTY. */
+int kgv_check_scripts_host(kgv_ctx* ctx, const kgv_tx_batch* batch, const uint32_t* tx_indices, size_t n, kgv_tx_result* results);
+
 /* Test / audit hook: affine coordinates (x||y, 32-byte big-endian each) of entry v (1..65535) of
  * generator table `which` (0: v*G, 1: v*2^128*G) as built on the device. */
 int kgv_gtable_entry(kgv_ctx* ctx, int which, uint32_t v, uint8_t out_xy[64]);

@@ -32,6 +32,38 @@ class Params(ctypes.Structure):
         super().__init__(coinbase_maturity, storage_mass_parameter, max_sompi)
 
 
+class SigRequest(ctypes.Structure):
+    """kgv_sig_request: one signature check the host script engine asks a verdict for."""
+    _fields_ = [("tx", ctypes.c_uint32), ("input", ctypes.c_uint32), ("hash_type", ctypes.c_uint8), ("ecdsa", ctypes.c_uint8), ("key_len", ctypes.c_uint8),
+                ("pad_", ctypes.c_uint8), ("key", ctypes.c_uint8 * 33), ("sig", ctypes.c_uint8 * 64), ("pad2_", ctypes.c_uint8 * 3)]
+
+
+assert ctypes.sizeof(SigRequest) == 112
+VERDICT_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.POINTER(SigRequest))
+
+SCRIPT_ERR_NAMES = {0: "Ok", 1: "EvalFalse", 2: "NullFail", 3: "InvalidSignature", 4: "SigLength", 5: "PubKeyFormat", 6: "InvalidSigHashType",
+                    7: "ExceededSigOpLimit", 8: "SignatureScriptNotPushOnly", 9: "CleanStack", 10: "EmptyStack", 11: "ElementTooBig",
+                    12: "TooManyOperations", 13: "StackSizeExceeded", 14: "OpcodeDisabled", 15: "OpcodeReserved", 16: "InvalidOpcode",
+                    17: "MalformedPush", 18: "MalformedPushSize", 19: "NotMinimalData", 20: "ErrUnbalancedConditional",
+                    21: "InvalidState(condition stack empty)", 22: "InvalidState(expected boolean)", 23: "InvalidState(pick at an invalid location)",
+                    24: "InvalidState(roll at an invalid location)", 25: "VerifyError", 26: "EarlyReturn", 27: "InvalidStackOperation", 28: "NumberTooBig",
+                    29: "InvalidPubKeyCount", 30: "InvalidSignatureCount", 31: "UnsatisfiedLockTime", 32: "ScriptSize", 33: "NoScripts",
+                    34: "InvalidInputIndex", 35: "InvalidOutputIndex", 36: "Serialization", 254: "NeedsSigVerdicts", 255: "NonStandard"}
+
+
+def script_execute(batch, tx, input_index, verdict=None):
+    """TxScriptEngine::from_transaction_input(..).execute() on the HOST engine of libkgv (no GPU involved).
+    verdict(request: SigRequest) -> KGV_SIG_* or -1.  Returns the KGV_SCRIPT_* code."""
+    lib = _lib.load()
+    cb = _c_batch(batch, with_entries=True)
+    fn = VERDICT_FN((lambda user, rq: int(verdict(rq.contents))) if verdict else (lambda user, rq: -1))
+    err = ctypes.c_uint8(0)
+    rc = lib.kgv_script_execute(ctypes.byref(cb), int(tx), int(input_index), ctypes.cast(fn, ctypes.c_void_p), None, ctypes.addressof(err))
+    if rc != 0:
+        raise _lib.KgvError(f"kgv_script_execute failed ({rc})")
+    return int(err.value)
+
+
 class GpuUtxoSet:
     """GPU-resident UTXO set (kgv_utxo_table)."""
 
@@ -95,12 +127,28 @@ class TransactionValidator:
         self._lib = ctx._lib
         self.params = params or Params()
 
-    def validate_populated_transactions(self, batch, pov_daa_score, flags=FLAGS_FULL):
-        """batch.entries must hold the populated UtxoEntry of every input. Returns RESULT_DTYPE[n_txs]."""
+    def validate_populated_transactions(self, batch, pov_daa_score, flags=FLAGS_FULL, host_vm=False):
+        """batch.entries must hold the populated UtxoEntry of every input. Returns RESULT_DTYPE[n_txs].
+        host_vm=True additionally sends every KGV_TX_NEEDS_HOST_VM transaction through the host script engine."""
         res = np.zeros(batch.n_txs, dtype=RESULT_DTYPE)
         cb = _c_batch(batch, with_entries=True)
         self.ctx._check(self._lib.kgv_validate_populated(self.ctx._h, ctypes.byref(cb), int(pov_daa_score), int(flags), ctypes.byref(self.params), res.ctypes.data))
+        if host_vm:
+            self.check_scripts_host(batch, res)
         return res
+
+    def check_scripts_host(self, batch, results):
+        """check_scripts with the full host engine (GPU-verified signatures) for every tx whose status is NEEDS_HOST_VM; updates `results` in place."""
+        idx = np.nonzero(results["status"] == TX_NEEDS_HOST_VM)[0].astype(np.uint32)
+        if len(idx) == 0:
+            return results
+        out = np.zeros(len(idx), dtype=RESULT_DTYPE)
+        cb = _c_batch(batch, with_entries=True)
+        self.ctx._check(self._lib.kgv_check_scripts_host(self.ctx._h, ctypes.byref(cb), idx.ctypes.data, len(idx), out.ctypes.data))
+        fees = results["fee"][idx]
+        results[idx] = out
+        results["fee"][idx] = fees
+        return results
 
     def validate_transactions_in_parallel(self, utxo_set, batch, pov_daa_score, flags=FLAGS_FULL):
         """Populate from the GPU UTXO set, then validate. Returns RESULT_DTYPE[n_txs] (coinbase: status 12)."""

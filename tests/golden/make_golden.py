@@ -183,6 +183,119 @@ def simpa_fixture():
                                    "blocks": out_blocks})
 
 
+# ------------------------------------------------------------------------------------ script engine rows
+def script_tests():
+    """crypto/txscript/test-data/script_tests.json (872 rows of which 850 are tests, 'short form' assembly) -> raw script bytes.
+    The assembler restates opcodes::parse_short_form (crypto/txscript/src/opcodes/macros.rs:138-175) and
+    ScriptBuilder::{add_i64,add_data,add_op} (script_builder.rs:88-243); the opcode-name table is parsed out of
+    crypto/txscript/src/opcodes/mod.rs."""
+    src = read("crypto/txscript/src/opcodes/mod.rs")
+    names = {}
+    for m in re.finditer(r"opcode\s+(?:\|\w+\|\s+)?(\w+)<(0x[0-9a-fA-F]+),", src):
+        names[m.group(1)] = int(m.group(2), 16)
+    assert len(names) == 256, len(names)
+    by_token = {}
+    for name, num in names.items():
+        by_token[name.upper()] = num
+        if name in ("OpFalse", "OpTrue") or (num != 0x00 and (num < 0x51 or num > 0x60)):
+            by_token.setdefault(name[2:].upper(), num)
+
+    def ser_i64(v, maxlen=8):
+        neg, p, out, sat = v < 0, abs(v), bytearray(), False
+        while p:
+            b = p & 0xFF
+            sat = bool(b & 0x80)
+            out.append(b)
+            p >>= 8
+        if sat:
+            out.append(0)
+        if neg:
+            out[-1] |= 0x80
+        assert len(out) <= maxlen
+        return bytes(out)
+
+    class Rejected(Exception):
+        pass
+
+    def add_data(script, data):
+        n = len(data)
+        if n == 0 or (n == 1 and (data[0] <= 16 or data[0] == 0x81)):
+            size = 1
+        else:
+            size = n + (1 if n <= 75 else 2 if n <= 255 else 3 if n <= 65535 else 5)
+        if len(script) + size > 10000:
+            raise Rejected("DataRejected")
+        if n > 520:
+            raise Rejected("ElementExceedsMaxSize")
+        if n == 0:
+            script.append(0x00)
+        elif n == 1 and 1 <= data[0] <= 16:
+            script.append(0x50 + data[0])
+        elif n == 1 and data[0] == 0x81:
+            script.append(0x4F)
+        else:
+            if n <= 75:
+                script.append(n)
+            elif n <= 255:
+                script += bytes([0x4C, n])
+            else:
+                script += bytes([0x4D, n & 0xFF, n >> 8])
+            script += data
+
+    def assemble(text):
+        script = bytearray()
+        for line in text.splitlines():
+            line = line.split("#")[0]
+            for tok in line.split():
+                try:
+                    v = int(tok)
+                    if not (-2**63 <= v < 2**63) or not re.fullmatch(r"[+-]?\d+", tok):
+                        raise ValueError
+                    if v == -2**63:
+                        add_data(script, ser_i64(v, 9))
+                    elif v == 0:
+                        script.append(0x00)
+                    elif v == -1 or 1 <= v <= 16:
+                        script.append(0x50 + v)
+                    else:
+                        add_data(script, ser_i64(v))
+                    continue
+                except ValueError:
+                    pass
+                if tok.startswith("0x") and re.fullmatch(r"(?:[0-9a-fA-F]{2})*", tok[2:]):
+                    script += bytes.fromhex(tok[2:])
+                elif len(tok) >= 2 and tok[0] == "'" and tok[-1] == "'":
+                    add_data(script, tok[1:-1].encode())
+                else:
+                    t = tok.replace("_", "").upper()
+                    if t not in by_token:
+                        raise KeyError("cannot parse token %r" % tok)
+                    if len(script) >= 10000:
+                        raise Rejected("OpCodeRejected")
+                    script.append(by_token[t])
+        return bytes(script)
+
+    rows = json.load(open(os.path.join(REF, "crypto/txscript/test-data/script_tests.json")))
+    out = []
+    for r in rows:
+        if len(r) < 4:
+            continue
+        sig_txt, spk_txt, _flags, expected = r[0], r[1], r[2], r[3]
+        row = {"sig_text": sig_txt, "spk_text": spk_txt, "expected": expected}
+        try:
+            row["sigscript"] = assemble(sig_txt).hex()
+            row["spk"] = assemble(spk_txt).hex()
+        except Rejected as e:
+            row["builder_error"] = str(e)  # ScriptBuilderError: the reference test maps ElementExceedsMaxSize to PUSH_SIZE
+        out.append(row)
+    assert len(out) == 850, len(out)  # 872 JSON rows, 22 of them comments
+    dump("script_tests.json.gz", {"source": "crypto/txscript/test-data/script_tests.json via opcodes::parse_short_form; harness crypto/txscript/src/lib.rs:1366-1555",
+                                  "spending_tx": "create_spending_transaction (lib.rs:1366-1397): version 1, one input spending output 0 of a version-1 'coinbase' "
+                                                 "(input outpoint (0^32, 0xffffffff), sigscript 0000, sequence u64::MAX, sig_op_count 20, one 0-value output with the spk), "
+                                                 "sequence u64::MAX, sig_op_count 20, one 0-value output with an empty spk; entry: amount 0, daa 0, coinbase",
+                                  "rows": out})
+
+
 if __name__ == "__main__":
     if not os.path.isdir(REF):
         sys.exit("needs /root/reference (run in the build container)")
@@ -191,3 +304,4 @@ if __name__ == "__main__":
     sighash()
     check_scripts_kat()
     simpa_fixture()
+    script_tests()
