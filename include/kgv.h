@@ -118,7 +118,7 @@ typedef struct {
   uint32_t script_off, script_len;  /* script_public_key.script */
   uint16_t spk_version;
   uint8_t is_coinbase;
-  uint8_t pad_[5];
+  uint8_t pad_[5];                  /* pad_[0] != 0 in a populated batch marks the entry ABSENT (-> MissingTxOutpoints) */
 } kgv_utxo_entry; /* 32 bytes */
 typedef struct {
   const kgv_tx* txs; size_t n_txs;
@@ -181,6 +181,11 @@ int kgv_sighash(kgv_ctx* ctx, const kgv_tx_batch* batch, const kgv_sighash_item*
 #define KGV_FLAGS_FULL 0
 #define KGV_FLAGS_SKIP_SCRIPT_CHECKS 1
 #define KGV_FLAGS_SKIP_MASS_CHECK 2
+/* extension: run ONLY check_scripts on populated entries (no maturity / amount / mass / sequence-lock rules).
+ * Signatures are context free given the spent output (the sighash reads only the entry's
+ * script_public_key and amount, sighash.rs:252-255), so a window of future blocks can be script-checked in one
+ * large batch before the in-order pass, which then runs with KGV_FLAGS_SKIP_SCRIPT_CHECKS. */
+#define KGV_FLAGS_SCRIPTS_ONLY 3
 
 typedef struct {
   uint64_t coinbase_maturity;       /* Params::coinbase_maturity      */

@@ -312,15 +312,73 @@ KGV_HD void fe_set_u32(fe& r, uint32_t x) { fe_set_zero(r); r.v[0] = x; }
 // r += k * (2^32 + 977) for k in {0,1}; returns carry out
 KGV_HD uint32_t fe_add_kC(fe& r, uint32_t k) { return add8_small3(r.v, 977u * k, k, 0u); }
 
+// r += (a1:a0) where the carry almost never leaves limb 2: three-limb chain, the (probability 2^-32)
+// propagation through the upper limbs sits on a separate, normally untaken path.  Returns the carry out.
+KGV_HD uint32_t add_low2_rare(uint32_t* r, uint32_t a0, uint32_t a1) {
+  uint32_t c;
+#if defined(__CUDACC__)
+  asm("add.cc.u32 %0, %0, %4;\n\t"
+      "addc.cc.u32 %1, %1, %5;\n\t"
+      "addc.cc.u32 %2, %2, 0;\n\t"
+      "addc.u32 %3, 0, 0;"
+      : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "=r"(c)
+      : "r"(a0), "r"(a1));
+#else
+  uint64_t t = (uint64_t)r[0] + a0; r[0] = (uint32_t)t; t >>= 32;
+  t += (uint64_t)r[1] + a1; r[1] = (uint32_t)t; t >>= 32;
+  t += (uint64_t)r[2]; r[2] = (uint32_t)t; t >>= 32;
+  c = (uint32_t)t;
+#endif
+  if (c) {
+    c = 0;
+#pragma unroll
+    for (int i = 3; i < 8; i++) {
+      r[i] += 1u;
+      if (r[i] != 0) break;
+      if (i == 7) c = 1;
+    }
+  }
+  return c;
+}
+// r -= (a1:a0), same structure; returns the borrow out
+KGV_HD uint32_t sub_low2_rare(uint32_t* r, uint32_t a0, uint32_t a1) {
+  uint32_t bo;
+#if defined(__CUDACC__)
+  asm("sub.cc.u32 %0, %0, %4;\n\t"
+      "subc.cc.u32 %1, %1, %5;\n\t"
+      "subc.cc.u32 %2, %2, 0;\n\t"
+      "subc.u32 %3, 0, 0;"
+      : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "=r"(bo)
+      : "r"(a0), "r"(a1));
+  bo &= 1u;
+#else
+  uint64_t t = (uint64_t)r[0] - a0; r[0] = (uint32_t)t; uint64_t br = (t >> 32) & 1;
+  t = (uint64_t)r[1] - a1 - br; r[1] = (uint32_t)t; br = (t >> 32) & 1;
+  t = (uint64_t)r[2] - br; r[2] = (uint32_t)t; br = (t >> 32) & 1;
+  bo = (uint32_t)br;
+#endif
+  if (bo) {
+    bo = 0;
+#pragma unroll
+    for (int i = 3; i < 8; i++) {
+      uint32_t old = r[i];
+      r[i] = old - 1u;
+      if (old != 0) break;
+      if (i == 7) bo = 1;
+    }
+  }
+  return bo;
+}
+
 KGV_HD void fe_add(fe& r, const fe& a, const fe& b) {
   uint32_t c = add8(r.v, a.v, b.v);
-  c = fe_add_kC(r, c);           // 2^256 == C (mod p)
-  if (c) (void)fe_add_kC(r, 1);  // only when the folded sum wrapped again (cannot wrap twice)
+  c = add_low2_rare(r.v, 977u * c, c);   // 2^256 == C (mod p)
+  if (c) (void)fe_add_kC(r, 1);          // only when the folded sum wrapped again (cannot wrap twice)
 }
 
 KGV_HD void fe_sub(fe& r, const fe& a, const fe& b) {
   uint32_t bo = sub8(r.v, a.v, b.v);
-  bo = sub8_small2(r.v, 977u * bo, bo);  // -2^256 == -C (mod p)
+  bo = sub_low2_rare(r.v, 977u * bo, bo);  // -2^256 == -C (mod p)
   if (bo) (void)sub8_small2(r.v, 977u, 1u);
 }
 
@@ -534,6 +592,50 @@ KGV_HD void fe_sqr(fe& r, const fe& a) {
 }
 #endif
 
+// Paired products: two INDEPENDENT field multiplications / squarings in one call.  The two carry-chain
+// streams have no data dependence, so ptxas interleaves them and the fixed-latency stalls of one stream are
+// filled by the other (the kernel runs only 3 warps per scheduler; ILP has to come from inside the warp).
+struct fe2 { fe a, b; };
+#if defined(__CUDACC__) && KGV_NOINLINE_MUL
+static __device__ __noinline__ fe2 fe_mul2_call(fe a1, fe b1, fe a2, fe b2) {
+  fe2 r;
+  uint32_t t1[16], t2[16];
+  mul_wide(t1, a1.v, b1.v);
+  mul_wide(t2, a2.v, b2.v);
+  fe_reduce_wide(r.a, t1);
+  fe_reduce_wide(r.b, t2);
+  return r;
+}
+static __device__ __noinline__ fe2 fe_sqr2_call(fe a1, fe a2) {
+  fe2 r;
+  uint32_t t1[16], t2[16];
+  sqr_wide(t1, a1.v);
+  sqr_wide(t2, a2.v);
+  fe_reduce_wide(r.a, t1);
+  fe_reduce_wide(r.b, t2);
+  return r;
+}
+static __device__ __noinline__ fe2 fe_mulsqr_call(fe a1, fe b1, fe a2) {
+  fe2 r;
+  uint32_t t1[16], t2[16];
+  mul_wide(t1, a1.v, b1.v);
+  sqr_wide(t2, a2.v);
+  fe_reduce_wide(r.a, t1);
+  fe_reduce_wide(r.b, t2);
+  return r;
+}
+// r1 = a1*b1, r2 = a2*b2
+KGV_HD void fe_mul2(fe& r1, const fe& a1, const fe& b1, fe& r2, const fe& a2, const fe& b2) { fe2 r = fe_mul2_call(a1, b1, a2, b2); r1 = r.a; r2 = r.b; }
+// r1 = a1^2, r2 = a2^2
+KGV_HD void fe_sqr2(fe& r1, const fe& a1, fe& r2, const fe& a2) { fe2 r = fe_sqr2_call(a1, a2); r1 = r.a; r2 = r.b; }
+// r1 = a1*b1, r2 = a2^2
+KGV_HD void fe_mulsqr(fe& r1, const fe& a1, const fe& b1, fe& r2, const fe& a2) { fe2 r = fe_mulsqr_call(a1, b1, a2); r1 = r.a; r2 = r.b; }
+#else
+KGV_HD void fe_mul2(fe& r1, const fe& a1, const fe& b1, fe& r2, const fe& a2, const fe& b2) { fe x, y; fe_mul(x, a1, b1); fe_mul(y, a2, b2); r1 = x; r2 = y; }
+KGV_HD void fe_sqr2(fe& r1, const fe& a1, fe& r2, const fe& a2) { fe x, y; fe_sqr(x, a1); fe_sqr(y, a2); r1 = x; r2 = y; }
+KGV_HD void fe_mulsqr(fe& r1, const fe& a1, const fe& b1, fe& r2, const fe& a2) { fe x, y; fe_mul(x, a1, b1); fe_sqr(y, a2); r1 = x; r2 = y; }
+#endif
+
 KGV_HD void fe_sqr_n(fe& r, const fe& a, int n) {
   r = a;
   for (int i = 0; i < n; i++) fe_sqr(r, r);
@@ -541,7 +643,17 @@ KGV_HD void fe_sqr_n(fe& r, const fe& a, int n) {
 
 // small multiples
 KGV_HD void fe_mul3(fe& r, const fe& a) { fe t; fe_add(t, a, a); fe_add(r, t, a); }
-KGV_HD void fe_mul8(fe& r, const fe& a) { fe t; fe_add(t, a, a); fe_add(t, t, t); fe_add(r, t, t); }
+// r = 8a: shift left by 3 and fold the three bits that leave the top limb (2^256 == C)
+KGV_HD void fe_mul8(fe& r, const fe& a) {
+  uint32_t top = a.v[7] >> 29;
+  fe t;
+#pragma unroll
+  for (int i = 7; i > 0; i--) t.v[i] = (a.v[i] << 3) | (a.v[i - 1] >> 29);
+  t.v[0] = a.v[0] << 3;
+  uint32_t c = add_low2_rare(t.v, 977u * top, top);
+  if (c) (void)fe_add_kC(t, 1);
+  r = t;
+}
 
 // shared prefix of the exponent chains for p-2 and (p+1)/4 (exponent bits from the top: 223 ones, 0, 22 ones, tail)
 KGV_HD void fe_pow_x223(fe& x223, fe& x22, fe& x2, const fe& a) {

@@ -12,6 +12,10 @@
 #define KGV_BLOCKS_PER_SM 3   // 3 x 64 KiB of per-thread tables in shared memory
 #endif
 
+#ifndef KGV_ITEMS
+#define KGV_ITEMS 4           // signatures per thread sharing one modular inversion (see k_schnorr_verify)
+#endif
+
 struct kgv_ctx {
   int device = 0;
   cudaStream_t own_stream = nullptr;
@@ -26,6 +30,7 @@ struct kgv_ctx {
   uint8_t* d_scratch = nullptr; // per-call device scratch (sub-hashes, sig items, ...)
   size_t d_scratch_cap = 0;
   uint64_t launches = 0;
+  int resident_blocks = 148 * KGV_BLOCKS_PER_SM;  // verification kernels: blocks that fit the device at once (persistent grid)
   std::mutex mu;
   std::string err;
 };

@@ -81,38 +81,126 @@ __global__ void __launch_bounds__(128) k_build_gtab(uint32_t* __restrict__ gtab)
   for (int i = 0; i < 8; i++) { out[i] = x.v[i]; out[8 + i] = y.v[i]; }
 }
 
+// Each thread verifies KGV_ITEMS consecutive-stride items (i = tid + j * total_threads: coalesced) and shares
+// ONE modular inversion among them (Montgomery's trick): the field inversion of BIP-340's final affine
+// conversion, resp. the scalar inversion s^-1 of ECDSA, drops from 1 to 1/KGV_ITEMS per signature with no
+// cross-thread synchronisation.  Pending state sits in (L1-resident) local memory between the phases.
 template <bool ALIGNED>
 __global__ void __launch_bounds__(KGV_BLOCK, KGV_BLOCKS_PER_SM)
 k_schnorr_verify(const uint8_t* __restrict__ pk, const uint8_t* __restrict__ msg, const uint8_t* __restrict__ sig, size_t n,
                  uint8_t* __restrict__ status, const uint32_t* __restrict__ gtab) {
   extern __shared__ uint32_t smem[];
-  size_t i = (size_t)blockIdx.x * KGV_BLOCK + threadIdx.x;
-  if (i >= n) return;
-  uint32_t pkw[8], mw[8], sw[16];
-  load_be32<ALIGNED>(pkw, pk + 32 * i);
-  load_be32<ALIGNED>(mw, msg + 32 * i);
-  load_be32<ALIGNED>(sw, sig + 64 * i);
-  load_be32<ALIGNED>(sw + 8, sig + 64 * i + 32);
+  const size_t total = (size_t)gridDim.x * KGV_BLOCK;
+  const size_t tid = (size_t)blockIdx.x * KGV_BLOCK + threadIdx.x;
   SmemTab tab{smem + threadIdx.x};
-  status[i] = schnorr_verify_core(pkw, mw, sw, tab, gtab, GLoadDev());
+  fe X[KGV_ITEMS], Y[KGV_ITEMS], ZT[KGV_ITEMS], RX[KGV_ITEMS], pre[KGV_ITEMS];
+  uint8_t st[KGV_ITEMS];
+  // persistent grid (one resident wave): every thread walks the batch with stride total*KGV_ITEMS, so all
+  // SM slots finish within one item of each other whatever n is (no wave quantisation)
+#pragma unroll 1
+  for (size_t base = 0; base < n; base += total * KGV_ITEMS) {
+  fe acc;
+  fe_set_u32(acc, 1);
+  bool any = false;
+#pragma unroll 1
+  for (int j = 0; j < KGV_ITEMS; j++) {
+    size_t i = base + tid + (size_t)j * total;
+    st[j] = KGV_ST_INVALID;
+    if (i >= n) continue;
+    uint32_t pkw[8], mw[8], sw[16];
+    load_be32<ALIGNED>(pkw, pk + 32 * i);
+    load_be32<ALIGNED>(mw, msg + 32 * i);
+    load_be32<ALIGNED>(sw, sig + 64 * i);
+    load_be32<ALIGNED>(sw + 8, sig + 64 * i + 32);
+    fe x, y, zt, rx;
+    uint8_t s1 = schnorr_phase1(x, y, zt, rx, pkw, mw, sw, tab, gtab, GLoadDev());
+    st[j] = s1;
+    if (s1 == KGV_ST_PENDING) {
+      X[j] = x; Y[j] = y; ZT[j] = zt; RX[j] = rx;
+      pre[j] = acc;
+      fe_mul(acc, acc, zt);
+      any = true;
+    }
+  }
+  if (any) {
+    fe inv;
+    fe_inv(inv, acc);
+#pragma unroll 1
+    for (int j = KGV_ITEMS - 1; j >= 0; j--) {
+      if (st[j] != KGV_ST_PENDING) continue;
+      fe zi;
+      fe_mul(zi, inv, pre[j]);
+      fe_mul(inv, inv, ZT[j]);
+      st[j] = schnorr_phase2(X[j], Y[j], zi, RX[j]);
+    }
+  }
+#pragma unroll 1
+  for (int j = 0; j < KGV_ITEMS; j++) {
+    size_t i = base + tid + (size_t)j * total;
+    if (i < n) status[i] = st[j];
+  }
+  }
 }
+
+struct sc_words { uint32_t v[8]; };
 
 template <bool ALIGNED>
 __global__ void __launch_bounds__(KGV_BLOCK, KGV_BLOCKS_PER_SM)
 k_ecdsa_verify(const uint8_t* __restrict__ pk, const uint8_t* __restrict__ msg, const uint8_t* __restrict__ sig, size_t n,
                uint8_t* __restrict__ status, const uint32_t* __restrict__ gtab) {
   extern __shared__ uint32_t smem[];
-  size_t i = (size_t)blockIdx.x * KGV_BLOCK + threadIdx.x;
-  if (i >= n) return;
-  uint32_t pkw[8], mw[8], sw[16];
-  const uint8_t* kp = pk + 33 * i;  // 33-byte stride: never word aligned
-  uint32_t tag = kp[0];
-  load_be32<false>(pkw, kp + 1);
-  load_be32<ALIGNED>(mw, msg + 32 * i);
-  load_be32<ALIGNED>(sw, sig + 64 * i);
-  load_be32<ALIGNED>(sw + 8, sig + 64 * i + 32);
+  const size_t total = (size_t)gridDim.x * KGV_BLOCK;
+  const size_t tid = (size_t)blockIdx.x * KGV_BLOCK + threadIdx.x;
   SmemTab tab{smem + threadIdx.x};
-  status[i] = ecdsa_verify_core(tag, pkw, mw, sw, tab, gtab, GLoadDev());
+  fe QX[KGV_ITEMS], QY[KGV_ITEMS];
+  sc_words R_[KGV_ITEMS], S_[KGV_ITEMS], M_[KGV_ITEMS], pre[KGV_ITEMS];
+  uint8_t st[KGV_ITEMS];
+#pragma unroll 1
+  for (size_t base = 0; base < n; base += total * KGV_ITEMS) {
+  uint32_t acc[8] = {1, 0, 0, 0, 0, 0, 0, 0};
+  bool any = false;
+#pragma unroll 1
+  for (int j = 0; j < KGV_ITEMS; j++) {
+    size_t i = base + tid + (size_t)j * total;
+    st[j] = KGV_ST_INVALID;
+    if (i >= n) continue;
+    uint32_t pkw[8], mw[8], sw[16];
+    const uint8_t* kp = pk + 33 * i;  // 33-byte stride: never word aligned
+    uint32_t tag = kp[0];
+    load_be32<false>(pkw, kp + 1);
+    load_be32<ALIGNED>(mw, msg + 32 * i);
+    load_be32<ALIGNED>(sw, sig + 64 * i);
+    load_be32<ALIGNED>(sw + 8, sig + 64 * i + 32);
+    fe qx, qy;
+    uint32_t r[8], s[8], m[8];
+    uint8_t s1 = ecdsa_phase1(qx, qy, r, s, m, tag, pkw, mw, sw);
+    st[j] = s1;
+    if (s1 == KGV_ST_PENDING) {
+      QX[j] = qx; QY[j] = qy;
+#pragma unroll
+      for (int w = 0; w < 8; w++) { R_[j].v[w] = r[w]; S_[j].v[w] = s[w]; M_[j].v[w] = m[w]; pre[j].v[w] = acc[w]; }
+      sc_mul(acc, acc, s);
+      any = true;
+    }
+  }
+  if (any) {
+    uint32_t inv[8];
+    sc_inv(inv, acc);
+#pragma unroll 1
+    for (int j = KGV_ITEMS - 1; j >= 0; j--) {
+      if (st[j] != KGV_ST_PENDING) continue;
+      uint32_t sn[8];
+      sc_mul(sn, inv, pre[j].v);
+      sc_mul(inv, inv, S_[j].v);
+      st[j] = ecdsa_phase2(QX[j], QY[j], R_[j].v, sn, M_[j].v, tab, gtab, GLoadDev());
+    }
+  }
+#pragma unroll 1
+  for (int j = 0; j < KGV_ITEMS; j++) {
+    size_t i = base + tid + (size_t)j * total;
+    if (i < n) status[i] = st[j];
+  }
+  }
 }
 
 // audit/debug: one signature, every traced intermediate written to dbg[stage*16 ..]
@@ -242,6 +330,10 @@ extern "C" int kgv_create(int device, uint32_t flags, kgv_ctx** out) {
     CK(cudaFuncSetAttribute(k_schnorr_verify<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     CK(cudaFuncSetAttribute(k_ecdsa_verify<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     CK(cudaFuncSetAttribute(k_ecdsa_verify<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    int per_sm = 0, sms = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_schnorr_verify<true>, KGV_BLOCK, smem));
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    ctx->resident_blocks = per_sm * sms > 0 ? per_sm * sms : 148 * KGV_BLOCKS_PER_SM;
     CK(cudaStreamSynchronize(ctx->stream));
     return KGV_OK;
   };
@@ -299,7 +391,9 @@ extern "C" uint64_t kgv_launch_count(const kgv_ctx* ctx) { return ctx ? ctx->lau
 int kgv_launch_verify(kgv_ctx* ctx, const uint8_t* dpk, const uint8_t* dmsg, const uint8_t* dsig, size_t n, uint8_t* dst, bool ecdsa) {
   if (n == 0) return KGV_OK;
   const int smem = KGV_BLOCK * 128 * (int)sizeof(uint32_t);
-  unsigned blocks = (unsigned)((n + KGV_BLOCK - 1) / KGV_BLOCK);
+  const size_t per_block = (size_t)KGV_BLOCK * KGV_ITEMS;
+  size_t want = (n + per_block - 1) / per_block;
+  unsigned blocks = (unsigned)(want < (size_t)ctx->resident_blocks ? want : (size_t)ctx->resident_blocks);  // one resident wave, persistent
   bool aligned = (((uintptr_t)dmsg | (uintptr_t)dsig | (ecdsa ? 0 : (uintptr_t)dpk)) & 31) == 0;
   if (ecdsa) {
     if (aligned) k_ecdsa_verify<true><<<blocks, KGV_BLOCK, smem, ctx->stream>>>(dpk, dmsg, dsig, n, dst, ctx->gtab);

@@ -261,7 +261,7 @@ __global__ void k_entries_from_batch(const kgv_utxo_entry* __restrict__ in, cons
   kgv_utxo_entry e = in[i];
   DevEntry d;
   d.amount = e.amount; d.block_daa_score = e.block_daa_score; d.script = bytes + e.script_off; d.script_len = e.script_len;
-  d.spk_version = e.spk_version; d.is_coinbase = e.is_coinbase; d.found = 1;
+  d.spk_version = e.spk_version; d.is_coinbase = e.is_coinbase; d.found = e.pad_[0] ? 0 : 1;  // pad_[0] != 0: caller marks the entry absent
   out[i] = d;
 }
 
@@ -291,6 +291,7 @@ __global__ void k_tx_context(BatchView b, uint32_t n_txs, uint64_t pov, uint32_t
   if (cb) { r.status = KGV_TX_SKIPPED_COINBASE; res[ti] = r; return; }
   for (uint32_t i = 0; i < t.n_inputs; i++)
     if (!ent[i].found) { r.status = KGV_TX_MISSING_OUTPOINTS; res[ti] = r; return; }  // utxo_validation.rs:319-327
+  if (flags == KGV_FLAGS_SCRIPTS_ONLY) { res[ti] = r; return; }
   for (uint32_t i = 0; i < t.n_inputs; i++)
     if (ent[i].is_coinbase && ent[i].block_daa_score + prm.coinbase_maturity > pov) { r.status = KGV_TX_IMMATURE_COINBASE; r.fail_input = i; res[ti] = r; return; }
   uint64_t total_in = 0;
@@ -663,7 +664,7 @@ extern "C" int kgv_utxo_digest(kgv_ctx* ctx, kgv_utxo_table* t, uint8_t out32[32
 static int validate_core(kgv_ctx* ctx, kgv_utxo_table* table, const kgv_tx_batch* batch, uint64_t pov, uint32_t flags, const kgv_params* prm,
                          kgv_tx_result* results) {
   if (!batch || !prm || (batch->n_txs && !results)) { ctx->err = "null argument"; return KGV_ERR_ARG; }
-  if (flags > KGV_FLAGS_SKIP_MASS_CHECK) { ctx->err = "unknown validation flags"; return KGV_ERR_ARG; }
+  if (flags > KGV_FLAGS_SCRIPTS_ONLY) { ctx->err = "unknown validation flags"; return KGV_ERR_ARG; }
   if (batch->n_txs == 0) return KGV_OK;
   CK(cudaSetDevice(ctx->device));
   kgv_dev_batch d;

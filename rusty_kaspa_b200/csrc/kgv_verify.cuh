@@ -19,11 +19,15 @@ KGV_HD bool fe_words_lt_p(const uint32_t* v) {
   return lt8(v, p);
 }
 
-// BIP-340 verification. pkw/mw: 8 big-endian words, sigw: 16 big-endian words (r || s).
+#define KGV_ST_PENDING 0xFFu  // phase 1 passed: the verdict needs the (batched) inversion of zt
+
+// BIP-340 verification, phase 1: everything up to the projective result R = s*G - e*P.
+// pkw/mw: 8 big-endian words, sigw: 16 big-endian words (r || s).
+// Returns a final verdict, or KGV_ST_PENDING with (X, Y, zt = true Z, rx) filled in.
 template <class Tab, class GLoad, class Trace = NoTrace>
-KGV_HD uint8_t schnorr_verify_core(const uint32_t* pkw, const uint32_t* mw, const uint32_t* sigw, Tab& tab, const uint32_t* gtab,
-                                   GLoad gload, Trace trace = Trace()) {
-  fe px, py, rx;
+KGV_HD uint8_t schnorr_phase1(fe& X, fe& Y, fe& zt, fe& rx, const uint32_t* pkw, const uint32_t* mw, const uint32_t* sigw, Tab& tab,
+                              const uint32_t* gtab, GLoad gload, Trace trace = Trace()) {
+  fe px, py;
   limbs_from_be_words(px.v, pkw);
   if (!fe_words_lt_p(px.v)) return KGV_ST_PK_PARSE;      // x >= p
   trace(1, px.v, 8);
@@ -46,12 +50,18 @@ KGV_HD uint8_t schnorr_verify_core(const uint32_t* pkw, const uint32_t* mw, cons
   { uint32_t f[1] = {R.inf}; trace(18, f, 1); }
   if (R.inf) return KGV_ST_INVALID;
   trace(19, R.x.v, 8); trace(20, R.y.v, 8); trace(21, R.z.v, 8);
-  fe zt, zi, zi2, ax, ay;
+  X = R.x;
+  Y = R.y;
   fe_mul(zt, R.z, zs);
-  fe_inv(zi, zt);
+  return KGV_ST_PENDING;
+}
+// phase 2: zi = 1/zt. Valid iff y(R) is even and x(R) == r.
+template <class Trace = NoTrace>
+KGV_HD uint8_t schnorr_phase2(const fe& X, const fe& Y, const fe& zi, const fe& rx, Trace trace = Trace()) {
+  fe zi2, ax, ay;
   fe_sqr(zi2, zi);
-  fe_mul(ax, R.x, zi2);
-  fe_mul(ay, R.y, zi2);
+  fe_mul(ax, X, zi2);
+  fe_mul(ay, Y, zi2);
   fe_mul(ay, ay, zi);
   fe_normalize(ay);
   fe_normalize(ax);
@@ -62,17 +72,26 @@ KGV_HD uint8_t schnorr_verify_core(const uint32_t* pkw, const uint32_t* mw, cons
   for (int i = 0; i < 8; i++) eq = eq && (ax.v[i] == rx.v[i]);
   return eq ? KGV_ST_VALID : KGV_ST_INVALID;
 }
+// single-signature form (audit kernel, host unit tests)
+template <class Tab, class GLoad, class Trace = NoTrace>
+KGV_HD uint8_t schnorr_verify_core(const uint32_t* pkw, const uint32_t* mw, const uint32_t* sigw, Tab& tab, const uint32_t* gtab,
+                                   GLoad gload, Trace trace = Trace()) {
+  fe X, Y, zt, rx, zi;
+  uint8_t st = schnorr_phase1(X, Y, zt, rx, pkw, mw, sigw, tab, gtab, gload, trace);
+  if (st != KGV_ST_PENDING) return st;
+  fe_inv(zi, zt);
+  return schnorr_phase2(X, Y, zi, rx, trace);
+}
 
-// ECDSA verification with libsecp256k1 semantics. pkw: 8 big-endian words of x, tag = first key byte.
-template <class Tab, class GLoad>
-KGV_HD uint8_t ecdsa_verify_core(uint32_t tag, const uint32_t* pkw, const uint32_t* mw, const uint32_t* sigw, Tab& tab,
-                                 const uint32_t* gtab, GLoad gload) {
+// ECDSA verification with libsecp256k1 semantics, phase 1: parsing and range checks.
+// pkw: 8 big-endian words of x, tag = first key byte.  Returns a final verdict or KGV_ST_PENDING with
+// the key (qx,qy), r, s (to be inverted, possibly batched) and the reduced message m.
+KGV_HD uint8_t ecdsa_phase1(fe& qx, fe& qy, uint32_t* r, uint32_t* s, uint32_t* m, uint32_t tag, const uint32_t* pkw, const uint32_t* mw,
+                            const uint32_t* sigw) {
   if (tag != 2u && tag != 3u) return KGV_ST_PK_PARSE;
-  fe qx, qy;
   limbs_from_be_words(qx.v, pkw);
   if (!fe_words_lt_p(qx.v)) return KGV_ST_PK_PARSE;
   if (!ge_lift_x(qy, qx, tag == 3u)) return KGV_ST_PK_PARSE;
-  uint32_t r[8], s[8], m[8];
   limbs_from_be_words(r, sigw);
   limbs_from_be_words(s, sigw + 8);
   if (sc_ge_n(r) || sc_ge_n(s)) return KGV_ST_SIG_PARSE;  // from_compact rejects overflow
@@ -80,8 +99,13 @@ KGV_HD uint8_t ecdsa_verify_core(uint32_t tag, const uint32_t* pkw, const uint32
   sc_reduce_once(m);
   if (sc_is_high(s)) return KGV_ST_INVALID;               // verify requires low S
   if (is_zero8(r) || is_zero8(s)) return KGV_ST_INVALID;
-  uint32_t sn[8], u1[8], u2[8];
-  sc_inv(sn, s);
+  return KGV_ST_PENDING;
+}
+// phase 2: sn = s^-1 mod n.  R = (m/s)*G + (r/s)*Q, valid iff x(R) mod n == r.
+template <class Tab, class GLoad>
+KGV_HD uint8_t ecdsa_phase2(const fe& qx, const fe& qy, const uint32_t* r, const uint32_t* sn, const uint32_t* m, Tab& tab, const uint32_t* gtab,
+                            GLoad gload) {
+  uint32_t u1[8], u2[8];
   sc_mul(u1, sn, m);
   sc_mul(u2, sn, r);
   gej R;
@@ -104,6 +128,16 @@ KGV_HD uint8_t ecdsa_verify_core(uint32_t tag, const uint32_t* pkw, const uint32
   for (int i = 0; i < 8; i++) rf.v[i] = rn[i];
   fe_mul(t, rf, zt2);
   return fe_equal(t, R.x) ? KGV_ST_VALID : KGV_ST_INVALID;
+}
+template <class Tab, class GLoad>
+KGV_HD uint8_t ecdsa_verify_core(uint32_t tag, const uint32_t* pkw, const uint32_t* mw, const uint32_t* sigw, Tab& tab,
+                                 const uint32_t* gtab, GLoad gload) {
+  fe qx, qy;
+  uint32_t r[8], s[8], m[8], sn[8];
+  uint8_t st = ecdsa_phase1(qx, qy, r, s, m, tag, pkw, mw, sigw);
+  if (st != KGV_ST_PENDING) return st;
+  sc_inv(sn, s);
+  return ecdsa_phase2(qx, qy, r, sn, m, tab, gtab, gload);
 }
 
 // One entry of the generator tables: v * B for v in [1, 65535], B affine; result affine.

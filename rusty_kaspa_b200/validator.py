@@ -19,7 +19,7 @@ from .verifier import _c_batch
 RESULT_DTYPE = np.dtype([("fee", "<u8"), ("fail_input", "<u4"), ("status", "u1"), ("script_err", "u1"), ("pad_", "u1", (2,))])
 assert RESULT_DTYPE.itemsize == 16
 
-FLAGS_FULL, FLAGS_SKIP_SCRIPT_CHECKS, FLAGS_SKIP_MASS_CHECK = 0, 1, 2
+FLAGS_FULL, FLAGS_SKIP_SCRIPT_CHECKS, FLAGS_SKIP_MASS_CHECK, FLAGS_SCRIPTS_ONLY = 0, 1, 2, 3
 MAX_SOMPI = 29_000_000_000 * 100_000_000
 TX_OK, TX_NEEDS_HOST_VM, TX_SKIPPED_COINBASE = 0, 11, 12
 

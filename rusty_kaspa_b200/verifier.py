@@ -89,6 +89,10 @@ class GpuContext:
         import torch
         self.use_stream(torch.cuda.current_stream(self.device).cuda_stream)
 
+    def reset_stream(self):
+        """back to the context's private stream"""
+        self._check(self._lib.kgv_reset_stream(self._h))
+
     def synchronize(self):
         self._check(self._lib.kgv_synchronize(self._h))
 

@@ -11,6 +11,8 @@ void hs_fe_mul(const uint8_t* a, const uint8_t* b, uint8_t* r) { fe x, y, z; loa
 void hs_fe_sqr(const uint8_t* a, uint8_t* r) { fe x, z; load(x, a); fe_sqr(z, x); store(r, z); }
 void hs_fe_add(const uint8_t* a, const uint8_t* b, uint8_t* r) { fe x, y, z; load(x, a); load(y, b); fe_add(z, x, y); store(r, z); }
 void hs_fe_sub(const uint8_t* a, const uint8_t* b, uint8_t* r) { fe x, y, z; load(x, a); load(y, b); fe_sub(z, x, y); store(r, z); }
+void hs_fe_mul8(const uint8_t* a, uint8_t* r) { fe x, z; load(x, a); fe_mul8(z, x); store(r, z); }
+void hs_fe_mul3(const uint8_t* a, uint8_t* r) { fe x, z; load(x, a); fe_mul3(z, x); store(r, z); }
 void hs_fe_norm(const uint8_t* a, uint8_t* r) { fe x; load(x, a); fe_normalize(x); store(r, x); }
 void hs_fe_inv(const uint8_t* a, uint8_t* r) { fe x, z; load(x, a); fe_inv(z, x); store(r, z); }
 int hs_fe_sqrt(const uint8_t* a, uint8_t* r) { fe x, z; load(x, a); bool ok = fe_sqrt(z, x); store(r, z); return ok; }

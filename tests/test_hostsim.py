@@ -52,6 +52,8 @@ def edge(rnd):
         return 2**256 - 1 - rnd.randrange(0, 5)
     if c < 0.8:
         return (2**256 - 1) ^ (1 << rnd.randrange(256))
+    if c < 0.85:
+        return rnd.randrange(2**96) | ((2**160 - 1) << 96)  # upper limbs all ones: the rare carry-propagation path
     if c < 0.9:
         return rnd.choice([0, 1, P, P - 1, P + 1, 2**255, 2**224 - 1, 0xFFFFFFFF << (32 * rnd.randrange(8))])
     return (rnd.randrange(2**256) | (0xFFFFFFFFFFFFFFFF << (64 * rnd.randrange(3)))) & (2**256 - 1)
@@ -75,6 +77,10 @@ def test_field_arithmetic(arith):
         assert iv() % P == (a + b) % P
         arith.hs_fe_sub(le(a), le(b), o)
         assert iv() % P == (a - b) % P
+        arith.hs_fe_mul8(le(a), o)
+        assert iv() % P == 8 * a % P
+        arith.hs_fe_mul3(le(a), o)
+        assert iv() % P == 3 * a % P
         arith.hs_fe_norm(le(a), o)
         assert iv() == a % P
         assert bool(arith.hs_fe_is_zero(le(a))) == (a % P == 0)
