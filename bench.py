@@ -150,7 +150,7 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
-def measure_tx_validation(ctx, dev, n_txs, steps):
+def measure_tx_validation(ctx, dev, n_txs, steps, mix=(1.0, 0.0, 0.0, 0.0), label="config 3"):
     """Secondary metric of BASELINE.json ("txs-validated/sec"): config-3-shaped window of independent
     1-in/2-out and 2-in/2-out P2PK Schnorr transactions validated against the GPU UTXO table by ONE
     kgv_validate_txs call (populate + context rules + sighash + verify + resolve), device-resident batch,
@@ -162,7 +162,7 @@ def measure_tx_validation(ctx, dev, n_txs, steps):
     from rusty_kaspa_b200.validator import RESULT_DTYPE
     from rusty_kaspa_b200.verifier import _KgvTxBatch
     t0 = time.perf_counter()
-    fkeys, fentries, txs = simgen.funded_window(n_txs)
+    fkeys, fentries, txs = simgen.funded_window(n_txs, mix=mix)
     b = build_batch(txs)
     earr, earena = simgen.entries_to_arrays(fentries)
     gen_s = time.perf_counter() - t0
@@ -199,7 +199,8 @@ def measure_tx_validation(ctx, dev, n_txs, steps):
     apply_s = time.perf_counter() - t0
     assert n_after == 2 * len(txs)
     us.close()
-    return {"workload": "window of independent P2PK-Schnorr txs (50% 1-in/2-out, 50% 2-in/2-out) vs GPU UTXO table, one kgv_validate_txs call",
+    return {"workload": label + ": window of independent txs (50% 1-in/2-out, 50% 2-in/2-out), spent-output mix (P2PK Schnorr, P2PK ECDSA, P2SH 2-of-3 Schnorr, P2SH 2-of-3 ECDSA) = "
+                        + str(tuple(mix)) + ", vs GPU UTXO table, one kgv_validate_txs call",
             "n_txs": len(txs), "n_sig_checks": n_sigs, "txs_per_s": len(txs) / dev_s, "sig_checks_per_s": n_sigs / dev_s,
             "e2e_txs_per_s": len(txs) / e2e_s, "e2e_h2d_bytes": int(b.txs.nbytes + b.inputs.nbytes + b.outputs.nbytes + b.arena.nbytes),
             "apply_accepted_ms": apply_s * 1e3, "ms_per_call": dev_s * 1e3, "generation_s": round(gen_s, 1)}
@@ -327,10 +328,11 @@ def run_ours(args, rank, world, local_rank):
         cpu = {"value": sample / dt, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": f"first {sample} triples of the same batch, C restatement of the reference path (oracle/), {threads} pthreads; verdicts identical to the GPU's"}
 
-    txv = None
+    txv = txv4 = None
     if world == 1 and args.tx_window > 0:
         with torch.cuda.stream(stream):
             txv = measure_tx_validation(ctx, dev, args.tx_window, max(2, min(args.steps, 5)))
+            txv4 = measure_tx_validation(ctx, dev, args.tx_window, max(2, min(args.steps, 5)), mix=(0.5, 0.0, 0.25, 0.25), label="config 4 shape")
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -346,7 +348,7 @@ def run_ours(args, rank, world, local_rank):
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 128 * n * world, "d2h_bytes_per_step": n * world,
                     "steps": e2e_steps, "how": "kgv_schnorr_verify through the C ABI with pinned host buffers: H2D + kernel + D2H + sync inside the timed region (host clock)"},
-            "tx_validation": txv, "gpu_launches": int(launches), "clocks": clocks}
+            "tx_validation": txv, "tx_validation_ecdsa_multisig": txv4, "gpu_launches": int(launches), "clocks": clocks}
     print(json.dumps(line), flush=True)
 
 

@@ -19,6 +19,8 @@
 struct kgv_ctx {
   int device = 0;
   cudaStream_t own_stream = nullptr;
+  cudaStream_t aux_stream = nullptr;              // fork/join side stream: ECDSA items verify beside the Schnorr items
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaStream_t stream = nullptr;
   uint32_t* gtab = nullptr;     // [2][65536][16] u32: v*G and v*2^128*G, affine
   uint8_t* d_in = nullptr;      // staging for host-pointer calls
@@ -53,4 +55,5 @@ int kgv_batch_to_device(kgv_ctx* ctx, const kgv_tx_batch* b, kgv_dev_batch* out,
 
 // Enqueue a verification kernel on device-resident SoA item arrays (no locking, no copies): used by the
 // fused validation path.  ecdsa: pk stride 33, else 32.
-int kgv_launch_verify(kgv_ctx* ctx, const uint8_t* dpk, const uint8_t* dmsg, const uint8_t* dsig, size_t n, uint8_t* dstatus, bool ecdsa);
+int kgv_launch_verify(kgv_ctx* ctx, const uint8_t* dpk, const uint8_t* dmsg, const uint8_t* dsig, size_t n, uint8_t* dstatus, bool ecdsa,
+                      cudaStream_t on = nullptr, bool use_on = false);

@@ -321,6 +321,9 @@ extern "C" int kgv_create(int device, uint32_t flags, kgv_ctx** out) {
     CK(cudaSetDevice(device));
     CK(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
     ctx->stream = ctx->own_stream;
+    CK(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
     CK(cudaMalloc((void**)&ctx->gtab, (size_t)2 * 65536 * 16 * sizeof(uint32_t)));
     k_build_gtab<<<(2 * 65536) / 128, 128, 0, ctx->stream>>>(ctx->gtab);
     CK(cudaGetLastError());
@@ -356,6 +359,9 @@ extern "C" void kgv_destroy(kgv_ctx* ctx) {
   if (ctx->d_out) cudaFree(ctx->d_out);
   if (ctx->d_batch) cudaFree(ctx->d_batch);
   if (ctx->d_scratch) cudaFree(ctx->d_scratch);
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+  if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
@@ -388,19 +394,22 @@ extern "C" uint64_t kgv_launch_count(const kgv_ctx* ctx) { return ctx ? ctx->lau
 // ---------------------------------------------------------------------------------------------
 // signature verification entry points
 // ---------------------------------------------------------------------------------------------
-int kgv_launch_verify(kgv_ctx* ctx, const uint8_t* dpk, const uint8_t* dmsg, const uint8_t* dsig, size_t n, uint8_t* dst, bool ecdsa) {
+int kgv_launch_verify(kgv_ctx* ctx, const uint8_t* dpk, const uint8_t* dmsg, const uint8_t* dsig, size_t n, uint8_t* dst, bool ecdsa,
+                      cudaStream_t on, bool use_on) {
   if (n == 0) return KGV_OK;
+  cudaStream_t st = use_on ? on : ctx->stream;
   const int smem = KGV_BLOCK * 128 * (int)sizeof(uint32_t);
-  const size_t per_block = (size_t)KGV_BLOCK * KGV_ITEMS;
-  size_t want = (n + per_block - 1) / per_block;
-  unsigned blocks = (unsigned)(want < (size_t)ctx->resident_blocks ? want : (size_t)ctx->resident_blocks);  // one resident wave, persistent
+  // one resident wave, persistent; items are strided by the grid size, so a batch smaller than the wave still
+  // spreads over every SM (one item per thread) instead of packing KGV_ITEMS items into a quarter of the threads
+  size_t want = (n + KGV_BLOCK - 1) / KGV_BLOCK;
+  unsigned blocks = (unsigned)(want < (size_t)ctx->resident_blocks ? want : (size_t)ctx->resident_blocks);
   bool aligned = (((uintptr_t)dmsg | (uintptr_t)dsig | (ecdsa ? 0 : (uintptr_t)dpk)) & 31) == 0;
   if (ecdsa) {
-    if (aligned) k_ecdsa_verify<true><<<blocks, KGV_BLOCK, smem, ctx->stream>>>(dpk, dmsg, dsig, n, dst, ctx->gtab);
-    else k_ecdsa_verify<false><<<blocks, KGV_BLOCK, smem, ctx->stream>>>(dpk, dmsg, dsig, n, dst, ctx->gtab);
+    if (aligned) k_ecdsa_verify<true><<<blocks, KGV_BLOCK, smem, st>>>(dpk, dmsg, dsig, n, dst, ctx->gtab);
+    else k_ecdsa_verify<false><<<blocks, KGV_BLOCK, smem, st>>>(dpk, dmsg, dsig, n, dst, ctx->gtab);
   } else {
-    if (aligned) k_schnorr_verify<true><<<blocks, KGV_BLOCK, smem, ctx->stream>>>(dpk, dmsg, dsig, n, dst, ctx->gtab);
-    else k_schnorr_verify<false><<<blocks, KGV_BLOCK, smem, ctx->stream>>>(dpk, dmsg, dsig, n, dst, ctx->gtab);
+    if (aligned) k_schnorr_verify<true><<<blocks, KGV_BLOCK, smem, st>>>(dpk, dmsg, dsig, n, dst, ctx->gtab);
+    else k_schnorr_verify<false><<<blocks, KGV_BLOCK, smem, st>>>(dpk, dmsg, dsig, n, dst, ctx->gtab);
   }
   CK(cudaGetLastError());
   ctx->launches++;

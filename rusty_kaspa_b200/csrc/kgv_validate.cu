@@ -741,6 +741,7 @@ static int validate_core(kgv_ctx* ctx, kgv_utxo_table* table, const kgv_tx_batch
       ctx->launches += 2;
       STAGE("emit+reused");
     }
+    if (ns && ne) CK(cudaEventRecord(ctx->ev_fork, st));  // fork point: everything both item kinds depend on is queued
     if (ns) {
       k_item_msgs<<<nblk(ns, 128), 128, 0, st>>>(v, reu, itx, plans, (const ItemRef*)(I + i_refs), ns, false, (uint32_t*)(I + i_msgs));
       CK(cudaGetLastError());
@@ -751,12 +752,21 @@ static int validate_core(kgv_ctx* ctx, kgv_utxo_table* table, const kgv_tx_batch
       STAGE("verify schnorr");
     }
     if (ne) {
-      k_item_msgs<<<nblk(ne, 128), 128, 0, st>>>(v, reu, itx, plans, (const ItemRef*)(I + i_refe), ne, true, (uint32_t*)(I + i_msge));
+      // with both kinds present the ECDSA items run on the side stream so the two (often sub-wave) verify
+      // launches share the SMs instead of queueing behind each other
+      const bool fork = ns != 0 && !kgv_debug_on();
+      cudaStream_t se = fork ? ctx->aux_stream : st;
+      if (fork) CK(cudaStreamWaitEvent(se, ctx->ev_fork, 0));
+      k_item_msgs<<<nblk(ne, 128), 128, 0, se>>>(v, reu, itx, plans, (const ItemRef*)(I + i_refe), ne, true, (uint32_t*)(I + i_msge));
       CK(cudaGetLastError());
       ctx->launches++;
       STAGE("msgs ecdsa");
-      rc = kgv_launch_verify(ctx, I + i_pke, I + i_msge, I + i_sige, ne, I + i_ste, true);
+      rc = kgv_launch_verify(ctx, I + i_pke, I + i_msge, I + i_sige, ne, I + i_ste, true, se, true);
       if (rc) return rc;
+      if (fork) {
+        CK(cudaEventRecord(ctx->ev_join, se));
+        CK(cudaStreamWaitEvent(st, ctx->ev_join, 0));
+      }
       STAGE("verify ecdsa");
     }
     k_resolve<<<nblk(ni, 128), 128, 0, st>>>(v, ni, itx, dres, plans, I + i_sts, I + i_ste, ierr);

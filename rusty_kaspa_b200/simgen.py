@@ -257,41 +257,43 @@ class SimDag:
         return tx
 
 
-def funded_window(n_txs, seed=0x6B61737061, n_keys=4096, n_nonces=4096, storage_mass_parameter=DEFAULT_STORAGE_MASS_PARAMETER, two_input_fraction=0.5):
-    """BASELINE config 3 as one pre-verification window: `n_txs` mutually independent P2PK-Schnorr transactions
-    (50 % 1-in/2-out, 50 % 2-in/2-out) spending distinct funding outputs, i.e. what ~n_txs/150 consecutive
-    10-BPS blocks carry.  Returns (funding_keys36 (m,36) u8, funding_entries list of entry dicts, txs list of tx dicts).
-    The funding outputs are to be loaded into the UTXO set first (kgv_utxo_apply_diff)."""
-    rng = np.random.default_rng(seed)
-    keys = W.ScalarPointPool(n_keys, seed, b"win-keys")
-    nonces = W.ScalarPointPool(n_nonces, seed, b"win-nonces")
+def funded_window(n_txs, seed=0x6B61737061, n_keys=4096, n_nonces=4096, storage_mass_parameter=DEFAULT_STORAGE_MASS_PARAMETER, two_input_fraction=0.5,
+                  mix=(1.0, 0.0, 0.0, 0.0)):
+    """One pre-verification window of `n_txs` mutually independent transactions spending distinct funding outputs
+    (what ~n_txs/150 consecutive 10-BPS blocks carry).  mix = fractions of (P2PK Schnorr, P2PK ECDSA, P2SH 2-of-3
+    Schnorr multisig, P2SH 2-of-3 ECDSA multisig) among the SPENT outputs: (1,0,0,0) is BASELINE config 3,
+    (0.5,0,0.25,0.25)-like mixes are config 4.  Returns (funding_keys36 (m,36) u8, funding entry dicts, tx dicts);
+    the funding outputs are to be loaded into the UTXO set first (kgv_utxo_apply_diff)."""
+    dag = SimDag(seed=seed, n_keys=n_keys, n_nonces=n_nonces, storage_mass_parameter=storage_mass_parameter, mix=mix)
+    rng = dag.rng
     fund_keys, fund_entries, txs = [], [], []
     for t in range(n_txs):
         n_in = 2 if rng.random() < two_input_fraction else 1
-        ins, ents, kidx = [], [], []
+        ins, ents, meta = [], [], []
         for _ in range(n_in):
-            k = int(rng.integers(0, keys.count))
+            kind, ks, redeem, spk = dag._new_output_script()
             txid = hashlib.blake2b(struct.pack("<QQ", seed & 0xFFFFFFFFFFFF, len(fund_keys)), digest_size=32).digest()
             amount = int(rng.integers(10**8, 10**11))
-            spk = bytes([0x20]) + keys.xs[k] + bytes([0xAC])
             fund_keys.append(txid + struct.pack("<I", 0))
             fund_entries.append({"amount": amount, "spk_version": 0, "script": spk, "block_daa_score": 1, "is_coinbase": False})
-            ins.append({"txid": txid, "index": 0, "sigscript": b"", "sequence": 0, "sig_op_count": 1})
+            ins.append({"txid": txid, "index": 0, "sigscript": b"", "sequence": 0, "sig_op_count": 1 if kind in (KIND_P2PK, KIND_P2PK_ECDSA) else 3})
             ents.append(fund_entries[-1])
-            kidx.append(k)
+            meta.append((kind, ks, redeem))
         total = sum(e["amount"] for e in ents)
         outs = []
         for v in ((total - 1) // 2, total - 1 - (total - 1) // 2):
-            k = int(rng.integers(0, keys.count))
-            outs.append({"value": v, "spk_version": 0, "script": bytes([0x20]) + keys.xs[k] + bytes([0xAC])})
+            k = int(rng.integers(0, dag.keys.count))
+            outs.append({"value": v, "spk_version": 0, "script": bytes([0x20]) + dag.keys.xs[k] + bytes([0xAC])})
         tx = {"version": 0, "inputs": ins, "outputs": outs, "lock_time": 0, "subnetwork_id": SUBNET_NATIVE, "gas": 0, "payload": b"", "mass": 0}
-        tx["mass"] = storage_mass([(e["amount"], 34) for e in ents], [(o["value"], 34) for o in outs], storage_mass_parameter)
-        for idx in range(n_in):
-            msg = sighash_all(tx, ents, idx, False)
-            j = int(rng.integers(0, nonces.count))
-            e = W._challenge(nonces.xs[j], keys.xs[kidx[idx]], msg)
-            s = (nonces.scalars[j] + e * keys.scalars[kidx[idx]]) % N
-            tx["inputs"][idx]["sigscript"] = bytes([0x41]) + nonces.xs[j] + s.to_bytes(32, "big") + bytes([SIGHASH_ALL])
+        tx["mass"] = storage_mass([(e["amount"], len(e["script"])) for e in ents], [(o["value"], 34) for o in outs], storage_mass_parameter)
+        for idx, (kind, ks, redeem) in enumerate(meta):
+            ecdsa = kind in (KIND_P2PK_ECDSA, KIND_MS_ECDSA)
+            msg = sighash_all(tx, ents, idx, ecdsa)
+            if kind in (KIND_P2PK, KIND_P2PK_ECDSA):
+                tx["inputs"][idx]["sigscript"] = bytes([0x41]) + dag._sign(ks[0], msg, ecdsa) + bytes([SIGHASH_ALL])
+            else:
+                pair = sorted(int(x) for x in rng.choice(3, size=2, replace=False))
+                tx["inputs"][idx]["sigscript"] = b"".join(bytes([0x41]) + dag._sign(ks[p], msg, ecdsa) + bytes([SIGHASH_ALL]) for p in pair) + _push(redeem)
         txs.append(tx)
     return np.frombuffer(b"".join(fund_keys), dtype=np.uint8).reshape(-1, 36).copy(), fund_entries, txs
 
