@@ -150,6 +150,21 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+# Issue cycles per Schnorr verify per SM sub-partition for the shipping kernel's instruction stream:
+# 1.32e5 IMAD.WIDE x 4.3 cycles + 3.25e5 other instructions x 1 cycle, per warp of 32 verifies (ncu instruction
+# counts, profiles/r01_schnorr_verify_ncu_summary.json; per-instruction costs, profiles/r01_pipe_microbench.txt).
+ISSUE_CYCLES_PER_WARP_VERIFY = 1.32e5 * 4.3 + 3.25e5 * 1.0
+SCHEDULERS = 148 * 4
+
+
+def integer_issue_roofline(n_items, kernel_ms, clocks):
+    mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    peak = SCHEDULERS * mhz * 1e6 * 32.0 / ISSUE_CYCLES_PER_WARP_VERIFY
+    achieved = n_items / (kernel_ms * 1e-3)
+    return {"bound": "integer issue (IMAD.WIDE 4.3 cyc, other 1 cyc per warp instruction per scheduler, measured)", "achieved": achieved,
+            "peak": peak, "unit": "verifies/s", "frac": achieved / peak, "sm_mhz": mhz}
+
+
 def measure_tx_validation(ctx, dev, n_txs, steps, mix=(1.0, 0.0, 0.0, 0.0), label="config 3"):
     """Secondary metric of BASELINE.json ("txs-validated/sec"): config-3-shaped window of independent
     1-in/2-out and 2-in/2-out P2PK Schnorr transactions validated against the GPU UTXO table by ONE
@@ -343,8 +358,8 @@ def run_ours(args, rank, world, local_rank):
                        "parallelism": f"{world} independent shard(s), one process per GPU", "generation_s": round(gen_s, 1)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": peak_src, "kernel": "k_schnorr_verify", "kernel_ms": kern_ms_avg,
-                         "note": "integer-ALU (IMAD.WIDE issue) bound by construction: 129 algorithmic bytes per verify vs ~4e5 integer instructions; "
-                                 "see DESIGN.md for the IMAD-issue roofline"},
+                         "note": "integer-issue bound by construction: 129 algorithmic bytes per verify vs 4.6e5 integer instructions; the binding roofline is integer_issue",
+                         "integer_issue": integer_issue_roofline(n, kern_ms_avg, clocks)},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 128 * n * world, "d2h_bytes_per_step": n * world,
                     "steps": e2e_steps, "how": "kgv_schnorr_verify through the C ABI with pinned host buffers: H2D + kernel + D2H + sync inside the timed region (host clock)"},

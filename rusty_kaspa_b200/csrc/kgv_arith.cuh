@@ -2,8 +2,8 @@
 //
 // One number per thread, 8 x 32-bit little-endian limbs held in registers.  Products are
 // built from IMAD.WIDE.U32(.X) carry chains (mad.lo.cc / madc.hi.cc pairs, which ptxas fuses
-// into one IMAD.WIDE.U32.X each); measured on B200 (tools/microbench/pipes.cu): IMAD.WIDE
-// issues at 64 lanes/clk/SM (2 issue cycles per warp instruction), IADD3 at 128 lanes/clk/SM.
+// into one IMAD.WIDE.U32.X each); measured on B200 (tools/microbench/pipes.cu, femul.cu): an
+// IMAD.WIDE costs ~4.3 cycles per warp instruction per SM sub-partition, IADD3 ~1.
 //
 // Replaces, for the GPU path, the field arithmetic of the C libsecp256k1 that the reference
 // reaches through crypto/txscript/src/lib.rs:593 / :628 (`sig.verify`).

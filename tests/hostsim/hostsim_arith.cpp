@@ -18,5 +18,6 @@ void hs_fe_inv(const uint8_t* a, uint8_t* r) { fe x, z; load(x, a); fe_inv(z, x)
 int hs_fe_sqrt(const uint8_t* a, uint8_t* r) { fe x, z; load(x, a); bool ok = fe_sqrt(z, x); store(r, z); return ok; }
 int hs_fe_is_zero(const uint8_t* a) { fe x; load(x, a); return fe_is_zero(x); }
 void hs_mul_wide(const uint8_t* a, const uint8_t* b, uint8_t* r) { fe x, y; load(x, a); load(y, b); uint32_t t[16]; mul_wide(t, x.v, y.v); memcpy(r, t, 64); }
+void hs_fe_reduce_wide(const uint8_t* t64, uint8_t* r) { uint32_t t[16]; memcpy(t, t64, 64); fe z; fe_reduce_wide(z, t); store(r, z); }
 void hs_sqr_wide(const uint8_t* a, uint8_t* r) { fe x; load(x, a); uint32_t t[16]; sqr_wide(t, x.v); memcpy(r, t, 64); }
 }

@@ -94,6 +94,36 @@ def test_field_arithmetic(arith):
             assert iv() ** 2 % P == a % P
 
 
+def test_reduce_wide_rare_carry_paths(arith):
+    """512-bit inputs crafted so that the second fold's carry runs through limb 3, through limbs 4..7, and past
+    2^256 (the normally untaken branches of fe_reduce_wide)."""
+    rnd = random.Random(11)
+    C = 2**32 + 977
+    o = ctypes.create_string_buffer(32)
+    hit = [0, 0, 0]
+    for it in range(3000):
+        hi = rnd.randrange(2**255, 2**256) if it % 2 else rnd.randrange(1, 2**256)
+        kind = it % 3
+        if kind == 0:    # carry leaves limb 3 only
+            xs = (rnd.randrange(2**128) << 128) | (2**128 - 1 - rnd.randrange(2**20))
+        elif kind == 1:  # ripples through some of limbs 4..7
+            k = rnd.randrange(1, 4)
+            xs = (rnd.randrange(2**(32 * (4 - k))) << (32 * (4 + k))) | (2**(32 * (4 + k)) - 1 - rnd.randrange(2**20))
+        else:            # wraps past 2^256
+            xs = 2**256 - 1 - rnd.randrange(2**20)
+        lo = (xs - hi * C) % 2**256
+        t = lo + (hi << 256)
+        arith.hs_fe_reduce_wide(t.to_bytes(64, "little"), o)
+        got = int.from_bytes(o.raw, "little")
+        assert got % P == t % P, (hex(t), hex(got))
+        top = (lo + hi * C) >> 256
+        s2 = xs + top * C
+        hit[0] += (xs % 2**128 + top * C) >> 128 > 0
+        hit[1] += kind == 1 and (xs % 2**160 + top * C) >> 160 > 0
+        hit[2] += s2 >> 256 > 0
+    assert min(hit) > 100, hit
+
+
 def limbs(x, n=8):
     return (ctypes.c_uint32 * n)(*[(x >> (32 * i)) & 0xFFFFFFFF for i in range(n)])
 

@@ -43,6 +43,26 @@ __global__ void __launch_bounds__(256) probe(uint32_t* out, uint32_t seed, unsig
       } else if (MODE == 8) {  // IMAD + IADD3 1:1
         asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(y), "r"(x));
         asm volatile("add.u32 %0, %0, %1;" : "+r"(b[i]) : "r"(x));
+      } else if (MODE == 10) {  // IMAD.WIDE, all operands distinct registers (no operand reuse)
+        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[i]) : "r"(a[i]), "r"(b[i]));
+      } else if (MODE == 11) {  // same through C++ (lets ptxas pick the form)
+        w[i] += (uint64_t)a[i] * b[i];
+      } else if (MODE == 12) {  // 32-bit IMAD, distinct operands
+        asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(a[i]) : "r"(b[i]), "r"(b[(i + 1) % ILP]));
+      } else if (MODE == 13) {  // IMAD.WIDE distinct, accumulator chain of length 2 (two products per accumulator per pass)
+        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[i / 2]) : "r"(a[i]), "r"(b[i]));
+      } else if (MODE == 14) {  // product without addend + xor consume (IMAD.WIDE RZ + 2 LOP3)
+        uint64_t t;
+        asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(t) : "r"(a[i]), "r"(b[i]));
+        w[i] ^= t;
+      } else if (MODE == 15) {  // IMAD.WIDE accumulate, multiplicand = own low word (nothing loop-invariant)
+        asm volatile("{\n\t.reg .b32 lo, hi;\n\tmov.b64 {lo, hi}, %0;\n\tmad.wide.u32 %0, lo, %1, %0;\n\t}" : "+l"(w[i]) : "r"(b[i]));
+      } else if (MODE == 16) {  // IMAD.WIDE without addend, multiplicand = own low word
+        asm volatile("{\n\t.reg .b32 lo, hi;\n\tmov.b64 {lo, hi}, %0;\n\tmul.wide.u32 %0, lo, %1;\n\t}" : "+l"(w[i]) : "r"(b[i]));
+      } else if (MODE == 17) {  // carry form: (hi:lo) = lo * b + (hi:lo) via mad.lo.cc / madc.hi (one IMAD.WIDE.U32 with carry out... )
+        asm volatile("{\n\t.reg .b32 lo, hi, t;\n\tmov.b64 {lo, hi}, %0;\n\tmov.b32 t, lo;\n\tmad.lo.cc.u32 lo, t, %1, lo;\n\tmadc.hi.u32 hi, t, %1, hi;\n\tmov.b64 %0, {lo, hi};\n\t}" : "+l"(w[i]) : "r"(b[i]));
+      } else if (MODE == 18) {  // 32-bit IMAD, multiplicand = own value, distinct operands
+        asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(b[i]), "r"(b[(i + 3) % ILP]));
       } else if (MODE == 9) {  // IMAD.WIDE with carry-in/out chain via add.cc on 64-bit halves
         asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[i]) : "r"(a[i]), "r"(y));
         asm volatile("add.cc.u32 %0, %0, %1;\n\taddc.u32 %0, %0, %1;" : "+r"(b[i]) : "r"(x));
@@ -89,5 +109,14 @@ int main() {
   run<7>("mad.lo.cc/madc.hi.cc/addc", 3, n, out, cyc);
   run<8>("IMAD + IADD 1:1", 2, n, out, cyc);
   run<9>("IMAD.WIDE + 2x IADD.cc", 3, n, out, cyc);
+  run<10>("IMAD.WIDE distinct operands", 1, n, out, cyc);
+  run<11>("IMAD.WIDE distinct (C++)", 1, n, out, cyc);
+  run<12>("IMAD distinct operands", 1, n, out, cyc);
+  run<13>("IMAD.WIDE distinct, chain 2", 1, n, out, cyc);
+  run<14>("mul.wide + xor.b64", 1, n, out, cyc);
+  run<15>("IMAD.WIDE acc, dependent operand", 1, n, out, cyc);
+  run<16>("IMAD.WIDE RZ, dependent operand", 1, n, out, cyc);
+  run<17>("mad.lo.cc+madc.hi dependent", 1, n, out, cyc);
+  run<18>("IMAD dependent operand", 1, n, out, cyc);
   return 0;
 }
