@@ -154,6 +154,21 @@ uint64_t ok_state_count(const ok_state* s);
 /* order-independent digest of the composed set: sum mod 2^256 of the MuHashElement hashes (consensus/core/src/muhash.rs:47-59) */
 void ok_state_digest(const ok_state* s, uint8_t out[32]);
 
+/* ---- MuHash (ok_muhash.c): crypto/muhash/src/lib.rs, u3072.rs, consensus/core/src/muhash.rs ---- */
+typedef struct { uint64_t num[48], den[48]; } ok_muhash; /* canonical residues modulo 2^3072 - 1103717 */
+void ok_muhash_init(ok_muhash* m);
+void ok_muhash_expand(const uint8_t hash32[32], uint8_t out384[384]);
+void ok_muhash_add_element(ok_muhash* m, const void* data, size_t n);
+void ok_muhash_remove_element(ok_muhash* m, const void* data, size_t n);
+void ok_muhash_combine(ok_muhash* m, const ok_muhash* o);
+void ok_muhash_serialize(ok_muhash* m, uint8_t out384[384]);
+void ok_muhash_finalize(ok_muhash* m, uint8_t out32[32]);
+int ok_muhash_deserialize(ok_muhash* m, const uint8_t in384[384]);
+void ok_muhash_raw(const ok_muhash* m, uint8_t num384[384], uint8_t den384[384]);
+void ok_muhash_add_utxo(ok_muhash* m, const uint8_t key36[36], const ok_utxo_entry* e, const uint8_t* bytes);
+void ok_muhash_add_transaction(ok_muhash* m, const ok_batch* b, const ok_utxo_entry* entries, size_t tx, uint64_t block_daa_score);
+void ok_muhash_accepted(ok_muhash* m, const ok_batch* b, const ok_utxo_entry* entries, const uint8_t* accept, uint64_t pov_daa_score);
+
 #ifdef __cplusplus
 }
 #endif

@@ -213,3 +213,60 @@ def sighash_schnorr(tx, entries, idx, hash_type):
 
 def sighash_ecdsa(tx, entries, idx, hash_type):
     return sha256_domain(b"TransactionSigningHashECDSA", sighash_schnorr(tx, entries, idx, hash_type))
+
+
+# ---------------------------------------------------------------------------------------------
+# MuHash (crypto/muhash/src/lib.rs, u3072.rs; consensus/core/src/muhash.rs) — big-int twin of ok_muhash.c
+# ---------------------------------------------------------------------------------------------
+MUHASH_P = 2**3072 - 1103717
+
+
+def _chacha20_block(key_words, counter):
+    s = [0x61707865, 0x3320646E, 0x79622D32, 0x6B206574] + list(key_words) + [counter & 0xFFFFFFFF, counter >> 32, 0, 0]
+    x = list(s)
+
+    def qr(a, b, c, d):
+        x[a] = (x[a] + x[b]) & 0xFFFFFFFF; x[d] ^= x[a]; x[d] = ((x[d] << 16) | (x[d] >> 16)) & 0xFFFFFFFF
+        x[c] = (x[c] + x[d]) & 0xFFFFFFFF; x[b] ^= x[c]; x[b] = ((x[b] << 12) | (x[b] >> 20)) & 0xFFFFFFFF
+        x[a] = (x[a] + x[b]) & 0xFFFFFFFF; x[d] ^= x[a]; x[d] = ((x[d] << 8) | (x[d] >> 24)) & 0xFFFFFFFF
+        x[c] = (x[c] + x[d]) & 0xFFFFFFFF; x[b] ^= x[c]; x[b] = ((x[b] << 7) | (x[b] >> 25)) & 0xFFFFFFFF
+
+    for _ in range(10):
+        qr(0, 4, 8, 12); qr(1, 5, 9, 13); qr(2, 6, 10, 14); qr(3, 7, 11, 15)
+        qr(0, 5, 10, 15); qr(1, 6, 11, 12); qr(2, 7, 8, 13); qr(3, 4, 9, 14)
+    return struct.pack("<16I", *[(a + b) & 0xFFFFFFFF for a, b in zip(x, s)])
+
+
+def muhash_element(data):
+    """lib.rs:161-166 data_to_element: keyed BLAKE2b -> ChaCha20Rng seed -> 384 keystream bytes, little-endian integer."""
+    h = blake2b_keyed(b"MuHashElement", data)
+    key = struct.unpack("<8I", h)
+    return int.from_bytes(b"".join(_chacha20_block(key, c) for c in range(6)), "little")
+
+
+class MuHash:
+    def __init__(self):
+        self.num, self.den = 1, 1
+
+    def add_element(self, data):
+        self.num = self.num * muhash_element(data) % MUHASH_P
+
+    def remove_element(self, data):
+        self.den = self.den * muhash_element(data) % MUHASH_P
+
+    def combine(self, other):
+        self.num = self.num * other.num % MUHASH_P
+        self.den = self.den * other.den % MUHASH_P
+
+    def serialize(self):
+        self.num = self.num * pow(self.den, MUHASH_P - 2, MUHASH_P) % MUHASH_P
+        self.den = 1
+        return self.num.to_bytes(384, "little")
+
+    def finalize(self):
+        return blake2b_keyed(b"MuHashFinalize", self.serialize())
+
+
+def utxo_element_bytes(txid, index, daa, amount, is_coinbase, spk_version, script):
+    """consensus/core/src/muhash.rs:47-59 write_utxo"""
+    return txid + struct.pack("<IQQ", index, daa, amount) + (b"\x01" if is_coinbase else b"\x00") + struct.pack("<HQ", spk_version, len(script)) + script

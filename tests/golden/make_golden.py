@@ -3,7 +3,7 @@
 
 Run in the build container (needs /root/reference; the GPU box does not have it):
     python tests/golden/make_golden.py
-Outputs (committed): tests/golden/{hashers,tx_hashing,sighash,check_scripts_kat,simpa_goref_1060.json.gz}
+Outputs (committed): tests/golden/{hashers,tx_hashing,sighash,check_scripts_kat,muhash}.json, simpa_goref_1060.json.gz, script_tests.json.gz
 
 Everything is parsed out of the reference's Rust test sources / test data at run time — nothing is
 retyped by hand — and each fixture records the file:line range it came from:
@@ -14,6 +14,7 @@ retyped by hand — and each fixture records the file:line range it came from:
                                                            real mainnet Schnorr P2PK / 2-of-4 P2SH multisig spends
   testing/integration/testdata/dags_for_json_tests/goref-1060-tx-265-blocks/blocks.json.gz
                                                            simpa-generated DAG: 224 signed inputs, all valid
+  crypto/muhash/src/lib.rs:17-21,189-238,290-327,430-444   MuHash known answers (empty, 3 vectors, pre-computed, serialize, parse)
 """
 import gzip
 import json
@@ -296,6 +297,33 @@ def script_tests():
                                   "rows": out})
 
 
+# ------------------------------------------------------------------------------------ muhash
+def muhash():
+    src = read("crypto/muhash/src/lib.rs")
+    ints = lambda txt: bytes(int(x, 0) for x in re.findall(r"0x[0-9a-fA-F]+|\d+", txt))
+    m = re.search(r"pub const EMPTY_MUHASH: Hash = Hash::from_bytes\(\[(.*?)\]\);", src, re.S)
+    empty = ints(m.group(1))
+    assert len(empty) == 32
+    vecs = []
+    tv = src[src.index("const TEST_VECTORS: [TestVector; 3] = ["):src.index("fn element_from_byte")]
+    for m in re.finditer(r"data: &\[(.*?)\],\s*multiset_hash: Hash::from_bytes\(\[(.*?)\]\),\s*cumulative_hash: Hash::from_bytes\(\[(.*?)\]\),", tv, re.S):
+        d, mh, ch = ints(m.group(1)), ints(m.group(2)), ints(m.group(3))
+        assert len(mh) == 32 and len(ch) == 32
+        vecs.append({"data": d.hex(), "multiset_hash": mh.hex(), "cumulative_hash": ch.hex()})
+    assert len(vecs) == 3
+    pre = re.search(r'fn test_new_pre_computed\(\) \{\s*let expected = "([0-9a-f]{64})";', src).group(1)
+    ser_src = src[src.index("fn test_serialize()"):]
+    ser = ints(re.search(r"let expected = \[(.*?)\];", ser_src, re.S).group(1))
+    assert len(ser) == 384
+    prime_diff = int(re.search(r"pub const PRIME_DIFF: Limb = (\d+);", read("crypto/muhash/src/u3072.rs")).group(1))
+    dump("muhash.json", {"source": "crypto/muhash/src/lib.rs:17-21 (EMPTY_MUHASH), :189-238 (TEST_VECTORS), :290-298 (test_new_pre_computed), "
+                                   ":301-327 (test_serialize), :430-444 (test_parse_muhash_fail); crypto/muhash/src/u3072.rs:22 (PRIME_DIFF)",
+                         "prime_diff": prime_diff, "empty_muhash": empty.hex(), "test_vectors": vecs,
+                         "pre_computed": {"add": ["00" + "00" * 31, "01" + "00" * 31], "remove": ["02" + "00" * 31], "finalized": pre},
+                         "serialize": {"add": ["01" + "00" * 31, "02" + "00" * 31], "serialized": ser.hex()},
+                         "parse_fail": {"overflow": "9b28ef" + "ff" * 381, "ok": "0028ef" + "ff" * 381, "all_ff_overflows": True}})
+
+
 if __name__ == "__main__":
     if not os.path.isdir(REF):
         sys.exit("needs /root/reference (run in the build container)")
@@ -305,3 +333,4 @@ if __name__ == "__main__":
     check_scripts_kat()
     simpa_fixture()
     script_tests()
+    muhash()
