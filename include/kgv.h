@@ -239,6 +239,33 @@ int kgv_validate_txs(kgv_ctx* ctx, kgv_utxo_table* t, const kgv_tx_batch* batch,
 int kgv_utxo_apply_accepted(kgv_ctx* ctx, kgv_utxo_table* t, const kgv_tx_batch* batch, const uint8_t* accept, uint64_t pov_daa_score);
 
 /* ------------------------------------------------------------------------------------------------
+ * K8 MuHash: crypto/muhash/src/lib.rs, u3072.rs; consensus/core/src/muhash.rs.
+ * A MuHash is the pair (numerator, denominator) of residues modulo 2^3072 - 1103717 (lib.rs:32-35); every function
+ * here reads / writes them as 384 little-endian bytes each, CANONICAL (in [0, p)) on output.  The reference's
+ * transient non-canonical representations (u3072.rs:49-57) are unobservable through serialize()/finalize().
+ * Pointers of one call are all host or all device.
+ * ------------------------------------------------------------------------------------------------ */
+/* MuHash::add_element / remove_element (lib.rs:61-74) for n byte strings data[offsets[i] .. offsets[i+1]):
+ * remove[i] != 0 multiplies the element into the denominator, else into the numerator (remove may be NULL).
+ * Starts from the empty MuHash (1, 1). */
+int kgv_muhash_elements(kgv_ctx* ctx, const uint8_t* data, const uint64_t* offsets, const uint8_t* remove, size_t n, uint8_t* numerator384,
+                        uint8_t* denominator384);
+/* The MuHash half of validate_transactions_with_muhash_in_parallel (utxo_validation.rs:282-309): MuHash::from_transaction
+ * (consensus/core/src/muhash.rs:16-27,35-39) of every tx with accept[i] != 0, all combined.  Populated entries come
+ * from batch->entries, or from `table` when it is non-NULL (call BEFORE kgv_utxo_apply_accepted erases them). */
+int kgv_muhash_txs(kgv_ctx* ctx, kgv_utxo_table* table, const kgv_tx_batch* batch, const uint8_t* accept, uint64_t pov_daa_score,
+                   uint8_t* numerator384, uint8_t* denominator384);
+/* MuHash::combine (lib.rs:91-96): a.numerator *= b.numerator, a.denominator *= b.denominator */
+int kgv_muhash_combine(kgv_ctx* ctx, uint8_t* numerator_a, uint8_t* denominator_a, const uint8_t* numerator_b, const uint8_t* denominator_b);
+/* MuHash::serialize + finalize (lib.rs:98-115): serialized = numerator / denominator (0 has inverse 0, u3072.rs:163-165),
+ * hash = BLAKE2b-256 keyed "MuHashFinalize".  Sequential by nature (one modular inversion: 3 072 dependent squarings);
+ * the reference calls it once per chain block outside the parallel section.  serialized384 may be NULL. */
+int kgv_muhash_finalize(kgv_ctx* ctx, const uint8_t* numerator384, const uint8_t* denominator384, uint8_t* serialized384, uint8_t* hash32);
+/* MuHash::add_utxo (consensus/core/src/muhash.rs:28-33) over every live entry of the table: the UTXO-set commitment
+ * numerator (denominator 1). */
+int kgv_utxo_muhash(kgv_ctx* ctx, kgv_utxo_table* t, uint8_t* numerator384);
+
+/* ------------------------------------------------------------------------------------------------
  * Host script engine for non-standard scripts (KGV_TX_NEEDS_HOST_VM)
  * Complete restatement of TxScriptEngine (crypto/txscript/src/lib.rs:83-98,276-643, opcodes/mod.rs,
  * data_stack.rs); signature checks are resolved by a verdict provider, never computed on the CPU.

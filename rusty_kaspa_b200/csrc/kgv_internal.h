@@ -31,6 +31,8 @@ struct kgv_ctx {
   size_t d_batch_cap = 0;
   uint8_t* d_scratch = nullptr; // per-call device scratch (sub-hashes, sig items, ...)
   size_t d_scratch_cap = 0;
+  uint8_t* d_mu = nullptr;      // MuHash element arrays, product-tree levels and wide-product scratch rows
+  size_t d_mu_cap = 0;
   uint64_t launches = 0;
   int resident_blocks = 148 * KGV_BLOCKS_PER_SM;  // verification kernels: blocks that fit the device at once (persistent grid)
   std::mutex mu;
@@ -57,3 +59,11 @@ int kgv_batch_to_device(kgv_ctx* ctx, const kgv_tx_batch* b, kgv_dev_batch* out,
 // fused validation path.  ecdsa: pk stride 33, else 32.
 int kgv_launch_verify(kgv_ctx* ctx, const uint8_t* dpk, const uint8_t* dmsg, const uint8_t* dsig, size_t n, uint8_t* dstatus, bool ecdsa,
                       cudaStream_t on = nullptr, bool use_on = false);
+
+// ---- MuHash product trees (kgv_muhash.cu) ----
+// Reserve the level-0 element arrays of the two trees (denominator = removed elements, numerator = added elements):
+// element e of a tree with n elements has its limb block i at E + (i*n + e)*8 words (kgv_u3072.cuh layout, stride n).
+int kgv_mu_reserve(kgv_ctx* ctx, size_t n_den, size_t n_num, uint32_t** e_den, uint32_t** e_num);
+// Multiply each tree down to one value (denominator on ctx->stream, numerator on the side stream) and write the two
+// canonical residues (384 little-endian bytes each) to host or device memory.
+int kgv_mu_reduce(kgv_ctx* ctx, size_t n_den, size_t n_num, uint8_t* out_num384, uint8_t* out_den384);

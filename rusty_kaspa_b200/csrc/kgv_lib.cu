@@ -359,6 +359,7 @@ extern "C" void kgv_destroy(kgv_ctx* ctx) {
   if (ctx->d_out) cudaFree(ctx->d_out);
   if (ctx->d_batch) cudaFree(ctx->d_batch);
   if (ctx->d_scratch) cudaFree(ctx->d_scratch);
+  if (ctx->d_mu) cudaFree(ctx->d_mu);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);

@@ -13,6 +13,7 @@
 //   k_resolve         per input : replay of the script engine over the verdicts  (lib.rs:488-571)
 //   k_tx_finalize     per tx    : first failing input -> TxRuleError class       (:162-200)
 #include "kgv_internal.h"
+#include "kgv_muhash.cuh"
 #include "kgv_txhash.cuh"
 
 #include <cstdio>
@@ -509,6 +510,65 @@ __global__ void __launch_bounds__(128) k_tx_ids_dev(BatchView b, uint32_t n_txs,
 }
 
 // ---------------------------------------------------------------------------------------------
+// K8 MuHash elements (consensus/core/src/muhash.rs:16-33): one element per thread, written straight into level 0
+// of its product tree.  Inputs of accepted txs -> denominator tree (the populated entry they spend), outputs ->
+// numerator tree (entry = (value, spk, pov_daa_score, tx.is_coinbase)); everything else gets the identity.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_muhash_tx_elements(BatchView b, size_t n_inputs, size_t n_outputs, const uint32_t* __restrict__ input_tx,
+                                                            const uint32_t* __restrict__ output_tx, const uint8_t* __restrict__ accept,
+                                                            const uint64_t* __restrict__ txids, uint64_t pov, uint32_t* __restrict__ e_den,
+                                                            uint32_t* __restrict__ e_num) {
+  size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < n_inputs) {
+    const uint32_t ti = input_tx[g];
+    const DevEntry& e = b.entries[g];
+    if (!accept[ti] || !e.found) { u3072_store_one(e_den, n_inputs, g); return; }
+    const kgv_input& in = b.inputs[g];
+    uint32_t k[8];
+#pragma unroll
+    for (int w = 0; w < 8; w++)
+      k[w] = (uint32_t)in.prev_txid[4 * w] | ((uint32_t)in.prev_txid[4 * w + 1] << 8) | ((uint32_t)in.prev_txid[4 * w + 2] << 16) | ((uint32_t)in.prev_txid[4 * w + 3] << 24);
+    uint64_t d[4];
+    muhash_utxo_digest(d, k, in.prev_index, e.block_daa_score, e.amount, e.is_coinbase != 0, e.spk_version, e.script, e.script_len);
+    muhash_expand_store(e_den, n_inputs, g, d);
+    return;
+  }
+  g -= n_inputs;
+  if (g >= n_outputs) return;
+  const uint32_t ti = output_tx[g];
+  if (!accept[ti]) { u3072_store_one(e_num, n_outputs, g); return; }
+  const kgv_tx& tx = b.txs[ti];
+  const kgv_output& out = b.outputs[g];
+  uint32_t k[8];
+#pragma unroll
+  for (int w = 0; w < 4; w++) { k[2 * w] = (uint32_t)txids[4 * (size_t)ti + w]; k[2 * w + 1] = (uint32_t)(txids[4 * (size_t)ti + w] >> 32); }
+  uint64_t d[4];
+  muhash_utxo_digest(d, k, (uint32_t)(g - tx.first_output), pov, out.value, tx_is_coinbase(tx), out.spk_version, b.bytes + out.script_off, out.script_len);
+  muhash_expand_store(e_num, n_outputs, g, d);
+}
+// live entries of table slots [first, first + n) -> elements (empty slots: identity)
+__global__ void __launch_bounds__(128) k_muhash_table_elements(TableView t, uint64_t first, size_t n, uint32_t* __restrict__ e_num) {
+  size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n) return;
+  const UtxoSlot* s = &t.slots[first + g];
+  if (s->state != SLOT_FULL) { u3072_store_one(e_num, n, g); return; }
+  DevEntry e;
+  slot_to_entry(e, t, s);
+  uint32_t k[8];
+#pragma unroll
+  for (int w = 0; w < 8; w++) k[w] = s->key[w];
+  uint64_t d[4];
+  muhash_utxo_digest(d, k, s->key[8], e.block_daa_score, e.amount, e.is_coinbase != 0, e.spk_version, e.script, e.script_len);
+  muhash_expand_store(e_num, n, g, d);
+}
+// contiguous 384-byte values -> level-0 layout
+__global__ void k_u3072_scatter(const uint32_t* __restrict__ values, size_t n, uint32_t* __restrict__ e) {
+  size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n) return;
+  for (int i = 0; i < KGV_U3072_BLOCKS; i++) u3072_store_block(e, n, g, i, values + 96 * g + 8 * i);
+}
+
+// ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
 static TableView view_of(const kgv_utxo_table* t) { return TableView{t->slots, t->mask, t->overflow, t->overflow_cap, t->counters}; }
@@ -830,4 +890,102 @@ extern "C" int kgv_utxo_apply_accepted(kgv_ctx* ctx, kgv_utxo_table* t, const kg
   if (no) { k_apply_insert<<<nblk(no, 128), 128, 0, st>>>(view_of(t), v, no, (const uint32_t*)(S + o_otx), dacc, (const uint64_t*)(S + o_ids), pov_daa_score); CK(cudaGetLastError()); ctx->launches++; }
   if (!kgv_ptr_is_device(accept)) CK(cudaStreamSynchronize(st));
   return KGV_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K8 entry points
+// ---------------------------------------------------------------------------------------------
+extern "C" int kgv_muhash_txs(kgv_ctx* ctx, kgv_utxo_table* table, const kgv_tx_batch* batch, const uint8_t* accept, uint64_t pov_daa_score,
+                              uint8_t* numerator384, uint8_t* denominator384) {
+  if (!ctx) return KGV_ERR_ARG;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  if (!batch || !numerator384 || !denominator384 || (batch->n_txs && !accept)) { ctx->err = "null argument"; return KGV_ERR_ARG; }
+  if (kgv_ptr_is_device(numerator384) != kgv_ptr_is_device(denominator384)) { ctx->err = "outputs must both be host or both be device pointers"; return KGV_ERR_ARG; }
+  CK(cudaSetDevice(ctx->device));
+  kgv_dev_batch d;
+  d.n_txs = d.n_inputs = d.n_outputs = d.n_bytes = 0;
+  if (batch->n_txs) {
+    int rc = kgv_batch_to_device(ctx, batch, &d, table == nullptr);
+    if (rc) return rc;
+  }
+  const size_t nt = d.n_txs, ni = d.n_inputs, no = d.n_outputs;
+  uint32_t *e_den = nullptr, *e_num = nullptr;
+  int rc = kgv_mu_reserve(ctx, ni, no, &e_den, &e_num);
+  if (rc) return rc;
+  if (nt) {
+    size_t o_ent = 0, o_itx = al256(o_ent + ni * sizeof(DevEntry)), o_otx = al256(o_itx + ni * 4), o_ids = al256(o_otx + no * 4), o_acc = al256(o_ids + nt * 32);
+    rc = kgv_reserve(ctx, &ctx->d_scratch, &ctx->d_scratch_cap, al256(o_acc + nt));
+    if (rc) return rc;
+    uint8_t* S = ctx->d_scratch;
+    cudaStream_t st = ctx->stream;
+    const uint8_t* dacc = accept;
+    if (!kgv_ptr_is_device(accept)) {
+      CK(cudaMemcpyAsync(S + o_acc, accept, nt, cudaMemcpyHostToDevice, st));
+      dacc = S + o_acc;
+    }
+    DevEntry* dent = (DevEntry*)(S + o_ent);
+    if (ni) {
+      if (table) k_populate<<<nblk(ni, 128), 128, 0, st>>>(view_of(table), d.inputs, ni, dent);
+      else k_entries_from_batch<<<nblk(ni, 128), 128, 0, st>>>(d.entries, d.bytes, ni, dent);
+      CK(cudaGetLastError());
+      ctx->launches++;
+    }
+    BatchView v{d.txs, d.inputs, d.outputs, dent, d.bytes};
+    k_tx_ids_dev<<<nblk(nt, 128), 128, 0, st>>>(v, (uint32_t)nt, (uint64_t*)(S + o_ids));
+    CK(cudaGetLastError());
+    k_input_tx_index<<<nblk(nt, 128), 128, 0, st>>>(d.txs, (uint32_t)nt, (uint32_t*)(S + o_itx));
+    CK(cudaGetLastError());
+    k_output_tx_index<<<nblk(nt, 128), 128, 0, st>>>(d.txs, (uint32_t)nt, (uint32_t*)(S + o_otx));
+    CK(cudaGetLastError());
+    if (ni + no) {
+      k_muhash_tx_elements<<<nblk(ni + no, 128), 128, 0, st>>>(v, ni, no, (const uint32_t*)(S + o_itx), (const uint32_t*)(S + o_otx), dacc,
+                                                               (const uint64_t*)(S + o_ids), pov_daa_score, e_den, e_num);
+      CK(cudaGetLastError());
+    }
+    ctx->launches += 4;
+  }
+  return kgv_mu_reduce(ctx, ni, no, numerator384, denominator384);
+}
+
+// MuHash of the whole UTXO set (the pruning-point / virtual UTXO commitment: MuHash::add_utxo for every entry,
+// consensus/core/src/muhash.rs:28-33).  The table is walked in chunks; chunk products are multiplied in a last tree.
+extern "C" int kgv_utxo_muhash(kgv_ctx* ctx, kgv_utxo_table* t, uint8_t* numerator384) {
+  if (!ctx || !t) return KGV_ERR_ARG;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  if (!numerator384) { ctx->err = "null argument"; return KGV_ERR_ARG; }
+  CK(cudaSetDevice(ctx->device));
+  const uint64_t slots = t->mask + 1;
+  const size_t chunk = slots < ((uint64_t)1 << 17) ? (size_t)slots : ((size_t)1 << 17);
+  const size_t n_chunks = (size_t)((slots + chunk - 1) / chunk);
+  int rc = kgv_reserve(ctx, &ctx->d_out, &ctx->d_out_cap, (n_chunks + 1) * 384);
+  if (rc) return rc;
+  uint8_t* prods = ctx->d_out;                    // n_chunks x 384 B, contiguous values
+  uint8_t* dummy_den = ctx->d_out + n_chunks * 384;
+  for (size_t c = 0; c < n_chunks; c++) {
+    const uint64_t first = (uint64_t)c * chunk;
+    const size_t n = (size_t)((slots - first) < chunk ? (slots - first) : chunk);
+    uint32_t *e_den = nullptr, *e_num = nullptr;
+    rc = kgv_mu_reserve(ctx, 0, n, &e_den, &e_num);
+    if (rc) return rc;
+    k_muhash_table_elements<<<nblk(n, 128), 128, 0, ctx->stream>>>(view_of(t), first, n, e_num);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    rc = kgv_mu_reduce(ctx, 0, n, prods + 384 * c, dummy_den);
+    if (rc) return rc;
+  }
+  if (n_chunks == 1) {
+    const bool dev = kgv_ptr_is_device(numerator384);
+    CK(cudaMemcpyAsync(numerator384, prods, 384, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->stream));
+    if (!dev) CK(cudaStreamSynchronize(ctx->stream));
+    return KGV_OK;
+  }
+  uint32_t *e_den = nullptr, *e_num = nullptr;
+  rc = kgv_mu_reserve(ctx, 0, n_chunks, &e_den, &e_num);
+  if (rc) return rc;
+  k_u3072_scatter<<<nblk(n_chunks, 128), 128, 0, ctx->stream>>>((const uint32_t*)prods, n_chunks, e_num);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  if (kgv_ptr_is_device(numerator384)) return kgv_mu_reduce(ctx, 0, n_chunks, numerator384, dummy_den);
+  uint8_t den_host[384];
+  return kgv_mu_reduce(ctx, 0, n_chunks, numerator384, den_host);
 }

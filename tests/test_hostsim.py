@@ -18,7 +18,7 @@ LAMBDA = 0x5363AD4CC05C30E0A5261C028812645A122E22EA20816678DF02967C1B23BD72
 
 def _build(name):
     src, out = os.path.join(HS, name + ".cpp"), os.path.join(HS, "lib" + name + ".so")
-    hdrs = [os.path.join(HS, "..", "..", "rusty_kaspa_b200", "csrc", f) for f in ("kgv_arith.cuh", "kgv_secp.cuh", "kgv_sha256.cuh", "kgv_verify.cuh")]
+    hdrs = [os.path.join(HS, "..", "..", "rusty_kaspa_b200", "csrc", f) for f in ("kgv_arith.cuh", "kgv_secp.cuh", "kgv_sha256.cuh", "kgv_verify.cuh", "kgv_u3072.cuh", "kgv_blake2b.cuh")]
     if not os.path.exists(out) or any(os.path.getmtime(h) > os.path.getmtime(out) for h in hdrs + [src]):
         subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", out, src], check=True)
     return ctypes.CDLL(out)
@@ -186,3 +186,57 @@ def test_verify_cores_match_oracle(secp, oracle):
         assert got == oracle.ok_ecdsa_verify(pk[i].tobytes(), msg[i].tobytes(), sig[i].tobytes()), (i, kind[i])
         seen.add(got)
     assert seen == {0, 1, 2, 3}
+
+
+def test_u3072_field_and_element_expansion():
+    """MuHash field (modulo 2^3072 - 1103717) and ChaCha20 element expansion of kgv_u3072.cuh against Python integers:
+    products incl. values >= p, the crafted second-level wrap of the fold, the block-transposed layout, canonicalisation."""
+    L = _build("hostsim_u3072")
+    MP = pyref.MUHASH_P
+    arr = lambda v, n=96: (ctypes.c_uint32 * n)(*[(v >> (32 * i)) & 0xFFFFFFFF for i in range(n)])
+    rnd = random.Random(3)
+
+    def big():
+        c = rnd.random()
+        if c < 0.5:
+            return rnd.getrandbits(3072)
+        if c < 0.7:
+            return rnd.choice([0, 1, 2, MP - 1, MP, MP + 1, 2**3072 - 1, 2**3072 - 2, 1103717, 1103716, 2**3071])
+        if c < 0.85:
+            return (2**3072 - 1) ^ rnd.getrandbits(40)
+        return (2**3072 - 1) ^ (rnd.getrandbits(64) << (32 * rnd.randrange(94)))
+
+    for _ in range(300):
+        a, b = big(), big()
+        r, w = (ctypes.c_uint32 * 96)(), (ctypes.c_uint32 * 192)()
+        L.hs_u3072_mul_mod(arr(a), arr(b), r, w)
+        assert val(w) == a * b
+        assert val(r) % MP == a * b % MP and val(r) < 2**3072
+        c = (ctypes.c_uint32 * 96)()
+        L.hs_u3072_canonical(r, c)
+        assert val(c) == a * b % MP
+        L.hs_u3072_canonical(arr(a), c)
+        assert val(c) == a % MP
+    for it in range(200):  # low half of (lo + hi * PRIME_DIFF) all ones: the extra fold ripples to the top
+        hi = rnd.getrandbits(3072) if it % 2 else 2**3072 - 1 - rnd.getrandbits(30)
+        lo = ((2**3072 - 1) - rnd.getrandbits(20) - hi * 1103717) % 2**3072
+        r = (ctypes.c_uint32 * 96)()
+        L.hs_u3072_fold(arr(lo + (hi << 3072), 192), r)
+        assert val(r) % MP == (lo + (hi << 3072)) % MP and val(r) < 2**3072
+    S, SS = 5, 3  # strided (block-transposed) arrays
+    vals = [rnd.getrandbits(3072) for _ in range(S)]
+    A = (ctypes.c_uint32 * (96 * S))()
+    for e, v in enumerate(vals):
+        for blk in range(12):
+            for j in range(8):
+                A[(blk * S + e) * 8 + j] = (v >> (32 * (8 * blk + j))) & 0xFFFFFFFF
+    scratch = (ctypes.c_uint32 * (192 * SS))()
+    sz = ctypes.c_size_t
+    L.hs_u3072_mul_mod_strided(A, sz(S), sz(1), sz(3), sz(4), scratch, sz(SS), sz(2))
+    get = lambda e: sum(A[(blk * S + e) * 8 + j] << (32 * (8 * blk + j)) for blk in range(12) for j in range(8))
+    assert get(4) % MP == vals[1] * vals[3] % MP and [get(e) for e in range(4)] == vals[:4]
+    for _ in range(50):
+        d = bytes(rnd.randrange(256) for _ in range(rnd.randrange(0, 100)))
+        o = (ctypes.c_uint32 * 96)()
+        L.hs_muhash_expand(pyref.blake2b_keyed(b"MuHashElement", d), o)
+        assert val(o) == pyref.muhash_element(d)
