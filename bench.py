@@ -204,6 +204,22 @@ def measure_tx_validation(ctx, dev, n_txs, steps, mix=(1.0, 0.0, 0.0, 0.0), labe
     dev_s = e0.elapsed_time(e1) * 1e-3 / steps
     st = np.frombuffer(dres.cpu().numpy().tobytes(), dtype=RESULT_DTYPE)
     assert (st["status"] == 0).all()
+    # K8: the MuHash half of validate_transactions_with_muhash_in_parallel for the same window (all accepted)
+    dacc = torch.ones(len(b.txs), dtype=torch.uint8, device=dev)
+    dmu = torch.zeros(768, dtype=torch.uint8, device=dev)
+    mu_call = lambda: ctx._check(lib.kgv_muhash_txs(h, us._h, C.byref(cb), dacc.data_ptr(), 10, dmu.data_ptr(), dmu.data_ptr() + 384))
+    mu_call(); stream.synchronize()
+    m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    m0.record(stream)
+    for _ in range(steps):
+        mu_call()
+    m1.record(stream)
+    stream.synchronize()
+    mu_s = m0.elapsed_time(m1) * 1e-3 / steps
+    mu_dev = dmu.cpu().numpy().tobytes()
+    from rusty_kaspa_b200 import MuHash
+    mu_host = MuHash.from_transactions(ctx, b, np.ones(len(b.txs), dtype=np.uint8), 10, utxo_set=us)
+    assert mu_dev[:384] == mu_host.numerator and mu_dev[384:] == mu_host.denominator and mu_host.numerator != (1).to_bytes(384, "little")
     t0 = time.perf_counter()
     for _ in range(steps):
         tv.validate_transactions_in_parallel(us, b, 10)
@@ -218,7 +234,11 @@ def measure_tx_validation(ctx, dev, n_txs, steps, mix=(1.0, 0.0, 0.0, 0.0), labe
                         + str(tuple(mix)) + ", vs GPU UTXO table, one kgv_validate_txs call",
             "n_txs": len(txs), "n_sig_checks": n_sigs, "txs_per_s": len(txs) / dev_s, "sig_checks_per_s": n_sigs / dev_s,
             "e2e_txs_per_s": len(txs) / e2e_s, "e2e_h2d_bytes": int(b.txs.nbytes + b.inputs.nbytes + b.outputs.nbytes + b.arena.nbytes),
-            "apply_accepted_ms": apply_s * 1e3, "ms_per_call": dev_s * 1e3, "generation_s": round(gen_s, 1)}
+            "apply_accepted_ms": apply_s * 1e3, "ms_per_call": dev_s * 1e3,
+            "muhash": {"what": "kgv_muhash_txs: MuHash::from_transaction of every tx of the window, combined (K8)", "elements": int(b.n_inputs + len(b.outputs)),
+                       "ms_per_call": mu_s * 1e3, "u3072_mults_per_s": (int(b.n_inputs + len(b.outputs)) - 2) / mu_s,
+                       "txs_per_s_validate_plus_muhash": len(txs) / (dev_s + mu_s)},
+            "generation_s": round(gen_s, 1)}
 
 
 def run_ours(args, rank, world, local_rank):

@@ -150,6 +150,13 @@ class TransactionValidator:
         results["fee"][idx] = fees
         return results
 
+    def validate_transactions_with_muhash_in_parallel(self, utxo_set, batch, pov_daa_score, flags=FLAGS_FULL):
+        """utxo_validation.rs:282-309: as validate_transactions_in_parallel, plus the combined MuHash::from_transaction of the
+        accepted transactions.  Returns (RESULT_DTYPE[n_txs], MuHash)."""
+        from .muhash import MuHash
+        res = self.validate_transactions_in_parallel(utxo_set, batch, pov_daa_score, flags)
+        return res, MuHash.from_transactions(self.ctx, batch, (res["status"] == 0).astype(np.uint8), pov_daa_score, utxo_set=utxo_set)
+
     def validate_transactions_in_parallel(self, utxo_set, batch, pov_daa_score, flags=FLAGS_FULL):
         """Populate from the GPU UTXO set, then validate. Returns RESULT_DTYPE[n_txs] (coinbase: status 12)."""
         res = np.zeros(batch.n_txs, dtype=RESULT_DTYPE)

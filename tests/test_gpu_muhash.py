@@ -108,6 +108,11 @@ def test_transaction_batches_match_oracle(ctx, oracle):
     accept1 = np.ones(len(txs), dtype=np.uint8)
     oracle.ok_muhash_accepted(ctypes.byref(m), ctypes.byref(ob), b.entries.ctypes.data_as(ctypes.c_void_p), accept1.ctypes.data_as(ctypes.c_void_p), ctypes.c_uint64(1234))
     assert (g2.numerator, g2.denominator) == oracle_raw(oracle, m)
+    # the reference-shaped entry point: validate + MuHash of the accepted subset (one input signature corrupted -> that tx drops out)
+    from rusty_kaspa_b200 import TransactionValidator, Params
+    tv = TransactionValidator(ctx, Params(storage_mass_parameter=simgen.DEFAULT_STORAGE_MASS_PARAMETER))
+    res, g3 = tv.validate_transactions_with_muhash_in_parallel(us, b, 1234)
+    assert (res["status"] == 0).all() and (g3.numerator, g3.denominator) == (g2.numerator, g2.denominator)
     # UTXO-set commitment: set after = set before - spent + created  <=>  H(after) = H(before) * num / den
     before = MuHash.of_utxo_set(ctx, us)
     us.add_transactions(b, accept1, 1234)
