@@ -42,6 +42,24 @@ __global__ void __launch_bounds__(128) k_u3072_tree_level(const uint32_t* __rest
     }
   }
 }
+// the same level with one multiplication per 16-lane group (kgv_u3072.cuh, cooperative form): ~10x shorter per-level
+// latency, used while a level has too few multiplications to fill the machine with one thread each
+#define KGV_COOP_GROUPS 8  // groups (multiplications) per 128-thread block
+__global__ void __launch_bounds__(128) k_u3072_tree_level_coop(const uint32_t* __restrict__ in, size_t n_in, uint32_t* __restrict__ out) {
+  __shared__ U3072Coop sm[KGV_COOP_GROUPS];
+  const size_t n_out = (n_in + 1) / 2;
+  const int grp = threadIdx.x >> 4, lane = threadIdx.x & 15;
+  const size_t t = (size_t)blockIdx.x * KGV_COOP_GROUPS + grp;
+  const bool have = t < n_out;
+  const bool mul = have && 2 * t + 1 < n_in;
+  u3072_coop_mul_mod(sm[grp], lane, mul, out, n_out, t, in, n_in, 2 * t, in, n_in, 2 * t + 1);
+  if (have && !mul && lane < KGV_U3072_BLOCKS) {
+    uint32_t r[8];
+    u3072_load_block(r, in, n_in, 2 * t, lane);
+    u3072_store_block(out, n_out, t, lane, r);
+  }
+}
+
 // canonical residue of a single value (stride `s`, element 0) as 384 little-endian bytes; n == 0: the value one
 __global__ void k_u3072_emit(const uint32_t* __restrict__ a, size_t s, int is_empty, uint32_t* __restrict__ out96) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
@@ -103,7 +121,8 @@ static int reduce_one(kgv_ctx* ctx, uint8_t* base, size_t n, cudaStream_t st) {
   size_t k = n;
   while (k > 1) {
     size_t h = (k + 1) / 2;
-    k_u3072_tree_level<<<nblk(h, 128), 128, 0, st>>>(cur, k, nxt, m.wide);
+    if (h <= 8192) k_u3072_tree_level_coop<<<nblk(h, KGV_COOP_GROUPS), 128, 0, st>>>(cur, k, nxt);
+    else k_u3072_tree_level<<<nblk(h, 128), 128, 0, st>>>(cur, k, nxt, m.wide);
     CK(cudaGetLastError());
     ctx->launches++;
     uint32_t* t = cur; cur = nxt; nxt = t;
@@ -169,16 +188,17 @@ extern "C" int kgv_muhash_elements(kgv_ctx* ctx, const uint8_t* data, const uint
 }
 
 // a <- a * b for both fields (crypto/muhash/src/lib.rs:91-96 combine); all four are 384-byte little-endian residues
-__global__ void k_muhash_combine(uint32_t* __restrict__ w) {  // w: [a_num | a_den | b_num | b_den | wide 192 | wide 192] contiguous words
-  int t = threadIdx.x;
-  if (blockIdx.x != 0 || t > 1) return;
-  uint32_t* a = w + 96 * t;
-  const uint32_t* b = w + 96 * (2 + t);
-  uint32_t* wide = w + 96 * 4 + 192 * t;
-  u3072_mul_mod(a, 1, 0, wide, 1, 0, a, 1, 0, b, 1, 0);
-  uint32_t r[96];
-  u3072_canonical(r, a, 1, 0);
-  for (int i = 0; i < 96; i++) a[i] = r[i];
+__global__ void k_muhash_combine(uint32_t* __restrict__ w) {  // w: [a_num | a_den | b_num | b_den] contiguous words; one warp: group 0 numerators, group 1 denominators
+  __shared__ U3072Coop sm[2];
+  const int grp = threadIdx.x >> 4, lane = threadIdx.x & 15;
+  uint32_t* a = w + 96 * grp;
+  const uint32_t* b = w + 96 * (2 + grp);
+  u3072_coop_mul_mod(sm[grp], lane, true, a, 1, 0, a, 1, 0, b, 1, 0);
+  if (lane == 0) {
+    uint32_t r[96];
+    u3072_canonical(r, a, 1, 0);
+    for (int i = 0; i < 96; i++) a[i] = r[i];
+  }
 }
 extern "C" int kgv_muhash_combine(kgv_ctx* ctx, uint8_t* num_a, uint8_t* den_a, const uint8_t* num_b, const uint8_t* den_b) {
   if (!ctx) return KGV_ERR_ARG;
@@ -206,18 +226,27 @@ extern "C" int kgv_muhash_combine(kgv_ctx* ctx, uint8_t* num_a, uint8_t* den_a, 
 // finalize (lib.rs:98-115): serialized = numerator / denominator mod p (canonical), hash = BLAKE2b-256 keyed "MuHashFinalize".
 // The inverse is denominator^(p-2): p - 2 = (2^3051 - 1) * 2^21 + 993433, i.e. 3 072 squarings and ~30 multiplications,
 // strictly sequential.  OFF the data-parallel path (the reference finalizes once per chain block in sequential code):
-// one thread, ~0.1 s.  w: [num | den | cur | saved | wide 192] contiguous words; out: 96 words serialized + 8 words hash.
+// one 16-lane group multiplying cooperatively, a few ms.  w: [num | den | cur | saved] contiguous words; out: 96 words serialized + 8 words hash.
+// one real function for the many call sites of the exponentiation ladder (contiguous operands, stride 1)
+static __device__ __noinline__ void coop_mul_contig(U3072Coop* sm, int lane, bool act, uint32_t* r, const uint32_t* a, const uint32_t* b) {
+  u3072_coop_mul_mod(*sm, lane, act, r, 1, 0, a, 1, 0, b, 1, 0);
+}
 __global__ void k_muhash_finalize(uint32_t* __restrict__ w, uint32_t* __restrict__ out) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  uint32_t *num = w, *den = w + 96, *cur = w + 192, *saved = w + 288, *wide = w + 384;
-  auto mul = [&](uint32_t* r, const uint32_t* a, const uint32_t* b) { u3072_mul_mod(r, 1, 0, wide, 1, 0, a, 1, 0, b, 1, 0); };
-  auto copy = [&](uint32_t* d, const uint32_t* s) { for (int i = 0; i < 96; i++) d[i] = s[i]; };
+  __shared__ U3072Coop sm;
+  const int lane = threadIdx.x & 15;
+  const bool act = threadIdx.x < 16;  // one 16-lane group does the arithmetic; the other half of the warp only keeps the warp syncs company
+  uint32_t *num = w, *den = w + 96, *cur = w + 192, *saved = w + 288;
+  auto mul = [&](uint32_t* r, const uint32_t* a, const uint32_t* b) { coop_mul_contig(&sm, lane, act, r, a, b); };
+  auto copy = [&](uint32_t* d, const uint32_t* s_) {
+    if (act) for (int i = lane; i < 96; i += 16) d[i] = s_[i];
+    __syncwarp();
+  };
   // cur = den^(2^k - 1) with k following the bits of 3051 = 0b101111101011 from the top
   copy(cur, den);
   int k = 1;
   for (int bit = 10; bit >= 0; bit--) {
     copy(saved, cur);
-    for (int s = 0; s < k; s++) mul(cur, cur, cur);
+    for (int q = 0; q < k; q++) mul(cur, cur, cur);
     mul(cur, cur, saved);
     k *= 2;
     if ((3051 >> bit) & 1) { mul(cur, cur, cur); mul(cur, cur, den); k += 1; }
@@ -227,14 +256,16 @@ __global__ void k_muhash_finalize(uint32_t* __restrict__ w, uint32_t* __restrict
     if ((993433u >> bit) & 1u) mul(cur, cur, den);
   }
   mul(num, num, cur);
-  uint32_t r[96];
-  u3072_canonical(r, num, 1, 0);
-  Blake2b h;
-  b2b_init_muhash_finalize(h);
-  for (int i = 0; i < 96; i++) { out[i] = r[i]; b2b_u32(h, r[i]); }
-  uint64_t d[4];
-  b2b_final(h, d);
-  for (int i = 0; i < 4; i++) { out[96 + 2 * i] = (uint32_t)d[i]; out[96 + 2 * i + 1] = (uint32_t)(d[i] >> 32); }
+  if (threadIdx.x == 0) {
+    uint32_t r[96];
+    u3072_canonical(r, num, 1, 0);
+    Blake2b h;
+    b2b_init_muhash_finalize(h);
+    for (int i = 0; i < 96; i++) { out[i] = r[i]; b2b_u32(h, r[i]); }
+    uint64_t d[4];
+    b2b_final(h, d);
+    for (int i = 0; i < 4; i++) { out[96 + 2 * i] = (uint32_t)d[i]; out[96 + 2 * i + 1] = (uint32_t)(d[i] >> 32); }
+  }
 }
 extern "C" int kgv_muhash_finalize(kgv_ctx* ctx, const uint8_t* numerator384, const uint8_t* denominator384, uint8_t* serialized384, uint8_t* hash32) {
   if (!ctx) return KGV_ERR_ARG;

@@ -221,4 +221,148 @@ KGV_HD void u3072_store_one(uint32_t* E, size_t es, size_t e) {
   u3072_store_block(E, es, e, 0, z);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Cooperative multiplication: one product by a group of 16 lanes of a warp (12 of them do arithmetic).
+// The thread-per-product form above is issue-efficient but one product is ~1e5 dependent cycles; a product tree with
+// fewer than ~1e5 products per level is then latency-bound.  Here the 144 block products are dealt to 12 lanes BY
+// OUTPUT COLUMN (columns are independent until carries are resolved), 13 block products on the longest lane:
+//   phase 0  lanes 0..11 stage one limb block of A and of B each in shared memory
+//   phase 1  lane l sums its columns (17-limb sums, no carries between columns)            -> cols[k][17]
+//   phase 2  lane b assembles product block b from the three column pieces that overlap it -> w[b][8], carry[b]
+//   phase 2b lane 0 ripples the (0..2) block carries
+//   phase 3  lane i folds block 12+i into block i with 2^3072 == PRIME_DIFF               -> w[i][8], carry[i]
+//   phase 3b lane 0 ripples those carries and folds the last overflow
+//   phase 4  lanes 0..11 write the result blocks
+// Each phase is a plain function of (lane, shared state) so that the host unit-test build can run the lanes in a loop.
+// ---------------------------------------------------------------------------------------------
+struct U3072Coop {
+  uint32_t a[96], b[96];
+  uint32_t cols[23][17];
+  uint32_t w[24][8];
+  uint32_t carry[24];
+};
+
+// columns of lane l (second entry -1: none)
+KGV_HD void u3072_coop_columns(int lane, int& k0, int& k1) {
+  if (lane < 6) { k0 = lane; k1 = 11 - lane; }            // 13 block products
+  else if (lane < 11) { k0 = 6 + lane; k1 = 28 - lane; }  // lanes 6..10: (12,22) (13,21) (14,20) (15,19) (16,18): 12 block products
+  else if (lane == 11) { k0 = 17; k1 = -1; }              // 6 block products
+  else { k0 = -1; k1 = -1; }
+}
+KGV_HD void u3072_coop_phase1(int lane, U3072Coop& s) {
+  int ks[2];
+  u3072_coop_columns(lane, ks[0], ks[1]);
+#pragma unroll 1
+  for (int c = 0; c < 2; c++) {
+    const int k = ks[c];
+    if (k < 0) continue;
+    uint32_t acc[17];
+#pragma unroll
+    for (int i = 0; i < 17; i++) acc[i] = 0;
+    const int i0 = k < KGV_U3072_BLOCKS ? 0 : k - (KGV_U3072_BLOCKS - 1);
+    const int i1 = k < KGV_U3072_BLOCKS ? k : KGV_U3072_BLOCKS - 1;
+#pragma unroll 1
+    for (int i = i0; i <= i1; i++) {
+      uint32_t x[8], y[8], t[16];
+#pragma unroll
+      for (int j = 0; j < 8; j++) { x[j] = s.a[8 * i + j]; y[j] = s.b[8 * (k - i) + j]; }
+      u3072_blockmul(t, x, y);
+      u3072_acc_add16(acc, t);
+    }
+#pragma unroll
+    for (int i = 0; i < 17; i++) s.cols[k][i] = acc[i];
+  }
+}
+KGV_HD void u3072_coop_phase2(int lane, U3072Coop& s) {
+#pragma unroll 1
+  for (int blk = lane; blk < 24; blk += 16) {
+    uint64_t c = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      if (blk <= 22) c += s.cols[blk][j];
+      if (blk >= 1) c += s.cols[blk - 1][8 + j];
+      if (j == 0 && blk >= 2) c += s.cols[blk - 2][16];
+      s.w[blk][j] = (uint32_t)c;
+      c >>= 32;
+    }
+    s.carry[blk] = (uint32_t)c;
+  }
+}
+// w[blk] += v (v < 2^32), returns the carry out of the block
+KGV_HD uint32_t u3072_coop_block_add(uint32_t* w, uint32_t v) {
+  uint64_t c = v;
+  for (int j = 0; j < 8 && c; j++) { c += w[j]; w[j] = (uint32_t)c; c >>= 32; }
+  return (uint32_t)c;
+}
+KGV_HD void u3072_coop_phase2b(int lane, U3072Coop& s) {
+  if (lane != 0) return;
+  uint32_t cin = 0;
+#pragma unroll 1
+  for (int blk = 0; blk < 24; blk++) {
+    uint32_t ov = cin ? u3072_coop_block_add(s.w[blk], cin) : 0u;
+    cin = s.carry[blk] + ov;
+  }
+  // cin == 0 here: the product of two numbers < 2^3072 fits 24 blocks
+}
+KGV_HD void u3072_coop_phase3(int lane, U3072Coop& s) {
+  if (lane >= KGV_U3072_BLOCKS) return;
+  uint64_t c = 0;
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    c += (uint64_t)s.w[KGV_U3072_BLOCKS + lane][j] * KGV_MUHASH_PRIME_DIFF + s.w[lane][j];
+    s.w[lane][j] = (uint32_t)c;
+    c >>= 32;
+  }
+  s.carry[lane] = (uint32_t)c;  // < 2^22
+}
+KGV_HD void u3072_coop_phase3b(int lane, U3072Coop& s) {
+  if (lane != 0) return;
+  uint32_t cin = 0;
+#pragma unroll 1
+  for (int blk = 0; blk < KGV_U3072_BLOCKS; blk++) {
+    uint32_t ov = cin ? u3072_coop_block_add(s.w[blk], cin) : 0u;
+    cin = s.carry[blk] + ov;
+  }
+  uint64_t f = cin;  // units of 2^3072, < 2^22 + 2
+  while (f) {
+    uint64_t add = f * KGV_MUHASH_PRIME_DIFF;  // < 2^44
+    f = 0;
+#pragma unroll 1
+    for (int blk = 0; blk < KGV_U3072_BLOCKS && add; blk++) {
+      for (int j = 0; j < 8 && add; j++) {
+        uint64_t t = (uint64_t)s.w[blk][j] + (uint32_t)add;
+        s.w[blk][j] = (uint32_t)t;
+        add = (add >> 32) + (t >> 32);
+      }
+    }
+    f = add;
+  }
+}
+
+#if defined(__CUDACC__)
+// R[re] = A[ae] * B[be] mod p by the 16-lane group this thread belongs to (lane = position in the group).
+// All 32 lanes of the warp must call this together (both groups run the phases in lockstep); `active` = this group has work.
+__device__ __forceinline__ void u3072_coop_mul_mod(U3072Coop& s, int lane, bool active, uint32_t* R, size_t rs, size_t re, const uint32_t* A, size_t as, size_t ae,
+                                                   const uint32_t* B, size_t bs, size_t be) {
+  if (active && lane < KGV_U3072_BLOCKS) {
+    u3072_load_block(s.a + 8 * lane, A, as, ae, lane);
+    u3072_load_block(s.b + 8 * lane, B, bs, be, lane);
+  }
+  __syncwarp();
+  if (active) u3072_coop_phase1(lane, s);
+  __syncwarp();
+  if (active) u3072_coop_phase2(lane, s);
+  __syncwarp();
+  if (active) u3072_coop_phase2b(lane, s);
+  __syncwarp();
+  if (active) u3072_coop_phase3(lane, s);
+  __syncwarp();
+  if (active) u3072_coop_phase3b(lane, s);
+  __syncwarp();
+  if (active && lane < KGV_U3072_BLOCKS) u3072_store_block(R, rs, re, lane, s.w[lane]);
+  __syncwarp();
+}
+#endif
+
 }  // namespace kgv

@@ -23,3 +23,18 @@ void hs_muhash_expand(const uint8_t* digest32, uint32_t* out96) {
   muhash_expand_store(out96, 1, 0, d);
 }
 }
+extern "C" {
+// the cooperative multiplier with its 16 lanes run in a loop, phase by phase
+int hs_u3072_coop_mul_mod(const uint32_t* a, const uint32_t* b, uint32_t* r) {
+  static U3072Coop s;
+  for (int i = 0; i < 96; i++) { s.a[i] = a[i]; s.b[i] = b[i]; }
+  for (int l = 0; l < 16; l++) u3072_coop_phase1(l, s);
+  for (int l = 0; l < 16; l++) u3072_coop_phase2(l, s);
+  int bad = s.cols[22][16] != 0;
+  for (int l = 0; l < 16; l++) u3072_coop_phase2b(l, s);
+  for (int l = 0; l < 16; l++) u3072_coop_phase3(l, s);
+  for (int l = 0; l < 16; l++) u3072_coop_phase3b(l, s);
+  for (int i = 0; i < 96; i++) r[i] = s.w[i / 8][i % 8];
+  return bad;
+}
+}
