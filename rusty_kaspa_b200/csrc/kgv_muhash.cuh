@@ -8,20 +8,20 @@
 
 namespace kgv {
 
-// keyed BLAKE2b-256 whose key block is absorbed explicitly (no tabulated midstate for these two domains)
-KGV_HD void b2b_init_keyed_explicit(Blake2b& h, const char* key, uint32_t keylen) {
-  b2b_init(h, B2B_UNKEYED);
+// keyed BLAKE2b-256 for the two MuHash domains: the (<= 16 byte) key is given as two little-endian words and placed
+// directly into the key block.  Deliberately NO local byte array for the key: nvcc's stack colouring was caught
+// overlapping such an array with another live local array (tools/repro/).
+KGV_HD void b2b_init_keyed_words(Blake2b& h, uint64_t k0, uint64_t k1, uint32_t keylen) {
+  b2b_init(h, B2B_UNKEYED);  // zeroes the block
   h.h[0] = kB2bIV[0] ^ (0x01010000ull ^ ((uint64_t)keylen << 8) ^ 32ull);
-  for (uint32_t b = 0; b < 128; b++) b2b_byte(h, b < keylen ? (uint32_t)(uint8_t)key[b] : 0u);
+  h.m[0] = k0;
+  h.m[1] = k1;
+  h.fill = 128;  // a full key block is pending: compressed as a middle block when data follows, as the last block otherwise
+  h.t = 128;
+  h.fresh = false;
 }
-KGV_HD void b2b_init_muhash_element(Blake2b& h) {
-  const char dom[13] = {'M', 'u', 'H', 'a', 's', 'h', 'E', 'l', 'e', 'm', 'e', 'n', 't'};
-  b2b_init_keyed_explicit(h, dom, 13);
-}
-KGV_HD void b2b_init_muhash_finalize(Blake2b& h) {
-  const char dom[14] = {'M', 'u', 'H', 'a', 's', 'h', 'F', 'i', 'n', 'a', 'l', 'i', 'z', 'e'};
-  b2b_init_keyed_explicit(h, dom, 14);
-}
+KGV_HD void b2b_init_muhash_element(Blake2b& h) { b2b_init_keyed_words(h, 0x6C4568736148754Dull, 0x000000746E656D65ull, 13); }   // "MuHashElement"
+KGV_HD void b2b_init_muhash_finalize(Blake2b& h) { b2b_init_keyed_words(h, 0x694668736148754Dull, 0x0000657A696C616Eull, 14); }  // "MuHashFinalize"
 
 // digest of write_utxo(outpoint, entry): txid given as 8 little-endian u32 words
 KGV_HD void muhash_utxo_digest(uint64_t* d4, const uint32_t* txid8, uint32_t index, uint64_t block_daa_score, uint64_t amount, bool is_coinbase,

@@ -231,12 +231,8 @@ __global__ void k_utxo_digest(TableView t, unsigned long long* __restrict__ acc)
   if (s->state != SLOT_FULL) return;
   DevEntry e;
   slot_to_entry(e, t, s);
-  // keyed BLAKE2b "MuHashElement": midstate is not tabulated, so hash the key block explicitly
   Blake2b h;
-  b2b_init(h, B2B_UNKEYED);
-  h.h[0] = kB2bIV[0] ^ (0x01010000ull ^ (13ull << 8) ^ 32ull);
-  const char dom[13] = {'M', 'u', 'H', 'a', 's', 'h', 'E', 'l', 'e', 'm', 'e', 'n', 't'};
-  for (int b = 0; b < 128; b++) b2b_byte(h, b < 13 ? (uint32_t)dom[b] : 0u);
+  b2b_init_muhash_element(h);
   for (int w = 0; w < 9; w++) b2b_u32(h, s->key[w]);
   b2b_u64(h, e.block_daa_score);
   b2b_u64(h, e.amount);

@@ -2,7 +2,7 @@
 // unit tests (tests/test_hostsim.py).  Test infrastructure only.
 #include <string.h>
 #include "../../rusty_kaspa_b200/csrc/kgv_u3072.cuh"
-#include "../../rusty_kaspa_b200/csrc/kgv_blake2b.cuh"
+#include "../../rusty_kaspa_b200/csrc/kgv_muhash.cuh"
 using namespace kgv;
 extern "C" {
 // contiguous 96-limb little-endian numbers (stride 1)
@@ -36,5 +36,16 @@ int hs_u3072_coop_mul_mod(const uint32_t* a, const uint32_t* b, uint32_t* r) {
   for (int l = 0; l < 16; l++) u3072_coop_phase3b(l, s);
   for (int i = 0; i < 96; i++) r[i] = s.w[i / 8][i % 8];
   return bad;
+}
+}
+extern "C" {
+// keyed BLAKE2b of the two MuHash domains (which = 0 "MuHashElement", 1 "MuHashFinalize") over raw bytes
+void hs_muhash_domain_hash(int which, const uint8_t* data, size_t n, uint8_t* out32) {
+  Blake2b h;
+  if (which) b2b_init_muhash_finalize(h); else b2b_init_muhash_element(h);
+  for (size_t i = 0; i < n; i++) b2b_byte(h, data[i]);
+  uint64_t d[4];
+  b2b_final(h, d);
+  memcpy(out32, d, 32);
 }
 }

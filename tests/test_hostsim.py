@@ -18,7 +18,7 @@ LAMBDA = 0x5363AD4CC05C30E0A5261C028812645A122E22EA20816678DF02967C1B23BD72
 
 def _build(name):
     src, out = os.path.join(HS, name + ".cpp"), os.path.join(HS, "lib" + name + ".so")
-    hdrs = [os.path.join(HS, "..", "..", "rusty_kaspa_b200", "csrc", f) for f in ("kgv_arith.cuh", "kgv_secp.cuh", "kgv_sha256.cuh", "kgv_verify.cuh", "kgv_u3072.cuh", "kgv_blake2b.cuh")]
+    hdrs = [os.path.join(HS, "..", "..", "rusty_kaspa_b200", "csrc", f) for f in ("kgv_arith.cuh", "kgv_secp.cuh", "kgv_sha256.cuh", "kgv_verify.cuh", "kgv_u3072.cuh", "kgv_blake2b.cuh", "kgv_muhash.cuh")]
     if not os.path.exists(out) or any(os.path.getmtime(h) > os.path.getmtime(out) for h in hdrs + [src]):
         subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", out, src], check=True)
     return ctypes.CDLL(out)
@@ -235,6 +235,13 @@ def test_u3072_field_and_element_expansion():
     L.hs_u3072_mul_mod_strided(A, sz(S), sz(1), sz(3), sz(4), scratch, sz(SS), sz(2))
     get = lambda e: sum(A[(blk * S + e) * 8 + j] << (32 * (8 * blk + j)) for blk in range(12) for j in range(8))
     assert get(4) % MP == vals[1] * vals[3] % MP and [get(e) for e in range(4)] == vals[:4]
+    for n in (0, 1, 13, 127, 128, 129, 300):  # the two keyed domains (key block pending as the last / a middle block)
+        d = bytes(rnd.randrange(256) for _ in range(n))
+        o32 = ctypes.create_string_buffer(32)
+        L.hs_muhash_domain_hash(0, d, ctypes.c_size_t(n), o32)
+        assert o32.raw == pyref.blake2b_keyed(b"MuHashElement", d)
+        L.hs_muhash_domain_hash(1, d, ctypes.c_size_t(n), o32)
+        assert o32.raw == pyref.blake2b_keyed(b"MuHashFinalize", d)
     for _ in range(50):
         d = bytes(rnd.randrange(256) for _ in range(rnd.randrange(0, 100)))
         o = (ctypes.c_uint32 * 96)()
