@@ -239,6 +239,18 @@ int kgv_validate_txs(kgv_ctx* ctx, kgv_utxo_table* t, const kgv_tx_batch* batch,
 int kgv_utxo_apply_accepted(kgv_ctx* ctx, kgv_utxo_table* t, const kgv_tx_batch* batch, const uint8_t* accept, uint64_t pov_daa_score);
 
 /* ------------------------------------------------------------------------------------------------
+ * Merkle roots: crypto/merkle/src/lib.rs:3-30 calc_merkle_root / merkle_hash.
+ * ------------------------------------------------------------------------------------------------ */
+/* n_groups independent trees over one flattened array of 32-byte hashes: group g = hashes [first[g], first[g+1]).
+ * `first` (n_groups + 1 offsets) is a HOST array; hashes32 / roots32 are both host or both device.  An empty group
+ * yields ZERO_HASH, a single hash is its own root.  Serves hash_merkle_root (with kgv_tx_hashes) and
+ * calc_accepted_id_merkle_root's inner root (utxo_validation.rs:401-410, with kgv_tx_ids of the accepted txs). */
+int kgv_merkle_roots(kgv_ctx* ctx, const uint8_t* hashes32, const uint32_t* first, uint32_t n_groups, uint8_t* roots32);
+/* calc_hash_merkle_root (consensus/core/src/merkle.rs:5-7; checked by body_validation_in_isolation.rs:34-40) for every
+ * block of a batch: block b = transactions [block_first_tx[b], block_first_tx[b+1]) (host array of n_blocks + 1). */
+int kgv_block_hash_merkle_roots(kgv_ctx* ctx, const kgv_tx_batch* batch, const uint32_t* block_first_tx, uint32_t n_blocks, uint8_t* roots32);
+
+/* ------------------------------------------------------------------------------------------------
  * K8 MuHash: crypto/muhash/src/lib.rs, u3072.rs; consensus/core/src/muhash.rs.
  * A MuHash is the pair (numerator, denominator) of residues modulo 2^3072 - 1103717 (lib.rs:32-35); every function
  * here reads / writes them as 384 little-endian bytes each, CANONICAL (in [0, p)) on output.  The reference's

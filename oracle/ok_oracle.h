@@ -110,6 +110,8 @@ void ok_tx_id(const ok_batch* b, size_t tx, uint8_t out[32]);
 void ok_tx_hash(const ok_batch* b, size_t tx, uint8_t out[32]);
 void ok_tx_ids(const ok_batch* b, uint8_t* out32, int nthreads);
 void ok_tx_hashes(const ok_batch* b, uint8_t* out32, int nthreads);
+/* crypto/merkle/src/lib.rs:3-30 (calc_merkle_root over n 32-byte hashes; n == 0 -> ZERO_HASH) */
+void ok_merkle_root(const uint8_t* hashes32, size_t n, uint8_t out[32]);
 /* consensus/core/src/hashing/sighash.rs:140-277; entries[] is indexed like b->inputs (one populated
  * UTXO entry per input, scripts in b->bytes); input_index is relative to the tx. */
 void ok_sighash(const ok_batch* b, const ok_utxo_entry* entries, size_t tx, uint32_t input_index, uint8_t hash_type, int ecdsa, uint8_t out[32]);

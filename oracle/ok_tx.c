@@ -174,3 +174,28 @@ void ok_sighash(const ok_batch* b, const ok_utxo_entry* entries, size_t tx, uint
   if (ecdsa) ok_sha256_domain("TransactionSigningHashECDSA", sh, 32, out); /* :267-277 */
   else memcpy(out, sh, 32);
 }
+
+/* crypto/merkle/src/lib.rs:3-30 calc_merkle_root + merkle_hash (keyed BLAKE2b "MerkleBranchHash" of left || right):
+ * levels are padded to the next power of two; a pair whose left child is missing is missing, a missing right child
+ * counts as ZERO_HASH; no hashes at all -> ZERO_HASH.  Used for hash_merkle_root (consensus/core/src/merkle.rs:5-7,
+ * body_validation_in_isolation.rs:34-40) and accepted_id_merkle_root (utxo_validation.rs:401-410). */
+void ok_merkle_root(const uint8_t* hashes32, size_t n, uint8_t out[32]) {
+  if (n == 0) { memset(out, 0, 32); return; }
+  size_t pot = 1;
+  while (pot < n) pot <<= 1;
+  uint8_t* cur = (uint8_t*)malloc(pot * 32);
+  memcpy(cur, hashes32, n * 32);
+  size_t have = n; /* entries [0, have) present, the rest missing */
+  for (size_t width = pot; width > 1; width >>= 1) {
+    size_t nh = (have + 1) / 2;
+    for (size_t i = 0; i < nh; i++) {
+      uint8_t buf[64];
+      memcpy(buf, cur + 64 * i, 32);
+      if (2 * i + 1 < have) memcpy(buf + 32, cur + 64 * i + 32, 32); else memset(buf + 32, 0, 32);
+      ok_blake2b_keyed("MerkleBranchHash", buf, 64, cur + 32 * i);
+    }
+    have = nh;
+  }
+  memcpy(out, cur, 32);
+  free(cur);
+}

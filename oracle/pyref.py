@@ -270,3 +270,18 @@ class MuHash:
 def utxo_element_bytes(txid, index, daa, amount, is_coinbase, spk_version, script):
     """consensus/core/src/muhash.rs:47-59 write_utxo"""
     return txid + struct.pack("<IQQ", index, daa, amount) + (b"\x01" if is_coinbase else b"\x00") + struct.pack("<HQ", spk_version, len(script)) + script
+
+
+def merkle_root(hashes):
+    """crypto/merkle/src/lib.rs:3-30, literally (array of 2*pot-1 optional nodes)"""
+    if not hashes:
+        return bytes(32)
+    pot = 1
+    while pot < len(hashes):
+        pot *= 2
+    nodes = list(hashes) + [None] * (2 * pot - 1 - len(hashes))
+    off = pot
+    for i in range(0, 2 * pot - 2, 2):
+        nodes[off] = None if nodes[i] is None else blake2b_keyed(b"MerkleBranchHash", nodes[i] + (nodes[i + 1] if nodes[i + 1] is not None else bytes(32)))
+        off += 1
+    return nodes[-1]

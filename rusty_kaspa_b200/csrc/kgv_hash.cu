@@ -3,6 +3,7 @@
 // the batch (HBM-bound side of the path) — the ALU work is 12 BLAKE2b rounds per 128 B.
 #include "kgv_internal.h"
 #include "kgv_txhash.cuh"
+#include "kgv_muhash.cuh"
 
 #include <cstdio>
 
@@ -175,5 +176,148 @@ extern "C" int kgv_sighash(kgv_ctx* ctx, const kgv_tx_batch* batch, const kgv_si
     CK(cudaMemcpyAsync(out32, dout, n_items * 32, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
   }
+  return KGV_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Merkle roots (crypto/merkle/src/lib.rs:3-30): many independent trees (one per block) level by level; one thread per
+// pair.  Group g owns positions [first[g], first[g+1]) of the flattened hash array; after `level` levels it has
+// have = ceil(n_g / 2^level) nodes left, packed at the start of its range.  A finished group (have == 1) carries its
+// root forward so that every root ends in the same buffer.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_merkle_group_index(const uint32_t* __restrict__ first, uint32_t n_groups, uint32_t* __restrict__ gid) {
+  uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_groups) return;
+  for (uint32_t p = first[g]; p < first[g + 1]; p++) gid[p] = g;
+}
+__global__ void __launch_bounds__(128) k_merkle_level(const uint64_t* __restrict__ cur, uint64_t* __restrict__ nxt, const uint32_t* __restrict__ first,
+                                                      const uint32_t* __restrict__ gid, size_t n_total, uint32_t level) {
+  size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_total) return;
+  const uint32_t g = gid[p];
+  const uint32_t f = first[g], n = first[g + 1] - f;
+  const uint32_t li = (uint32_t)(p - f);
+  const uint32_t have = (uint32_t)((((uint64_t)n) + ((1ull << level) - 1)) >> level);
+  if (have == 1) {  // finished: carry the root
+    if (li == 0) {
+#pragma unroll
+      for (int k = 0; k < 4; k++) nxt[4 * (size_t)f + k] = cur[4 * (size_t)f + k];
+    }
+    return;
+  }
+  const uint32_t nh = (have + 1) / 2;
+  if (li >= nh) return;
+  Blake2b h;
+  b2b_init_keyed_words(h, 0x7242656C6B72654Dull, 0x6873614868636E61ull, 16);  // "MerkleBranchHash"
+#pragma unroll
+  for (int k = 0; k < 4; k++) b2b_u64(h, cur[4 * ((size_t)f + 2 * li) + k]);
+  const bool right = 2 * li + 1 < have;
+#pragma unroll
+  for (int k = 0; k < 4; k++) b2b_u64(h, right ? cur[4 * ((size_t)f + 2 * li + 1) + k] : 0ull);  // missing right child: ZERO_HASH
+  uint64_t d[4];
+  b2b_final(h, d);
+#pragma unroll
+  for (int k = 0; k < 4; k++) nxt[4 * ((size_t)f + li) + k] = d[k];
+}
+__global__ void k_merkle_collect(const uint64_t* __restrict__ cur, const uint32_t* __restrict__ first, uint32_t n_groups, uint64_t* __restrict__ roots) {
+  uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_groups) return;
+  const bool empty = first[g + 1] == first[g];
+#pragma unroll
+  for (int k = 0; k < 4; k++) roots[4 * (size_t)g + k] = empty ? 0ull : cur[4 * (size_t)first[g] + k];  // no hashes: ZERO_HASH
+}
+
+// dh: device array of n_total hashes (modified: used as one of the two ping-pong buffers); first_host: n_groups + 1 offsets on the HOST
+static int merkle_core(kgv_ctx* ctx, uint64_t* dh, size_t n_total, const uint32_t* first_host, uint32_t n_groups, uint64_t* droots) {
+  uint32_t max_n = 0;
+  for (uint32_t g = 0; g < n_groups; g++) {
+    if (first_host[g + 1] < first_host[g] || first_host[g + 1] > n_total) { ctx->err = "merkle group offsets not monotone / out of range"; return KGV_ERR_ARG; }
+    uint32_t n = first_host[g + 1] - first_host[g];
+    if (n > max_n) max_n = n;
+  }
+  size_t o_first = 0, o_gid = al256((n_groups + 1) * 4), o_buf = al256(o_gid + n_total * 4);
+  int rc = kgv_reserve(ctx, &ctx->d_scratch, &ctx->d_scratch_cap, al256(o_buf + n_total * 32 + 32));
+  if (rc) return rc;
+  uint8_t* S = ctx->d_scratch;
+  uint32_t* dfirst = (uint32_t*)(S + o_first);
+  uint32_t* dgid = (uint32_t*)(S + o_gid);
+  uint64_t* other = (uint64_t*)(S + o_buf);
+  cudaStream_t st = ctx->stream;
+  CK(cudaMemcpyAsync(dfirst, first_host, (n_groups + 1) * 4, cudaMemcpyHostToDevice, st));
+  if (n_total) {
+    k_merkle_group_index<<<(n_groups + 127) / 128, 128, 0, st>>>(dfirst, n_groups, dgid);
+    CK(cudaGetLastError());
+    ctx->launches++;
+  }
+  uint64_t* cur = dh;
+  uint64_t* nxt = other;
+  for (uint32_t level = 0; ((uint64_t)1 << level) < max_n; level++) {
+    k_merkle_level<<<(unsigned)((n_total + 127) / 128), 128, 0, st>>>(cur, nxt, dfirst, dgid, n_total, level);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    uint64_t* t = cur; cur = nxt; nxt = t;
+  }
+  k_merkle_collect<<<(n_groups + 127) / 128, 128, 0, st>>>(cur, dfirst, n_groups, droots);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  return KGV_OK;
+}
+
+extern "C" int kgv_merkle_roots(kgv_ctx* ctx, const uint8_t* hashes32, const uint32_t* first, uint32_t n_groups, uint8_t* roots32) {
+  if (!ctx) return KGV_ERR_ARG;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  if (n_groups == 0) return KGV_OK;
+  if (!first || !roots32) { ctx->err = "null argument"; return KGV_ERR_ARG; }
+  if (kgv_ptr_is_device(first)) { ctx->err = "merkle group offsets must be a host array"; return KGV_ERR_ARG; }
+  const size_t n_total = first[n_groups];
+  if (n_total && !hashes32) { ctx->err = "null argument"; return KGV_ERR_ARG; }
+  CK(cudaSetDevice(ctx->device));
+  const bool dev = n_total ? kgv_ptr_is_device(hashes32) != 0 : kgv_ptr_is_device(roots32) != 0;
+  if ((kgv_ptr_is_device(roots32) != 0) != dev) { ctx->err = "hashes and roots must both be host or both be device pointers"; return KGV_ERR_ARG; }
+  // working copy of the hashes (the tree overwrites its input buffer) + device roots
+  int rc = kgv_reserve(ctx, &ctx->d_in, &ctx->d_in_cap, al256(n_total * 32 + 32) + (size_t)n_groups * 32);
+  if (rc) return rc;
+  uint64_t* dh = (uint64_t*)ctx->d_in;
+  uint64_t* dr = (uint64_t*)(ctx->d_in + al256(n_total * 32 + 32));
+  if (n_total) CK(cudaMemcpyAsync(dh, hashes32, n_total * 32, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
+  rc = merkle_core(ctx, dh, n_total, first, n_groups, dr);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(roots32, dr, (size_t)n_groups * 32, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->stream));
+  if (!dev) CK(cudaStreamSynchronize(ctx->stream));
+  return KGV_OK;
+}
+
+// calc_hash_merkle_root (consensus/core/src/merkle.rs:5-7) for every block of a batch: block b = transactions
+// [block_first_tx[b], block_first_tx[b+1]) (host array); tx hashes never leave the device.
+extern "C" int kgv_block_hash_merkle_roots(kgv_ctx* ctx, const kgv_tx_batch* batch, const uint32_t* block_first_tx, uint32_t n_blocks, uint8_t* roots32) {
+  if (!ctx) return KGV_ERR_ARG;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  if (n_blocks == 0) return KGV_OK;
+  if (!batch || !block_first_tx || !roots32) { ctx->err = "null argument"; return KGV_ERR_ARG; }
+  if (kgv_ptr_is_device(block_first_tx)) { ctx->err = "block offsets must be a host array"; return KGV_ERR_ARG; }
+  if (block_first_tx[n_blocks] > batch->n_txs) { ctx->err = "block offsets exceed the batch"; return KGV_ERR_ARG; }
+  CK(cudaSetDevice(ctx->device));
+  kgv_dev_batch d;
+  d.n_txs = 0;
+  if (batch->n_txs) {
+    int rc = kgv_batch_to_device(ctx, batch, &d, false);
+    if (rc) return rc;
+  }
+  const size_t nt = block_first_tx[n_blocks];
+  int rc = kgv_reserve(ctx, &ctx->d_in, &ctx->d_in_cap, al256(nt * 32 + 32) + (size_t)n_blocks * 32);
+  if (rc) return rc;
+  uint64_t* dh = (uint64_t*)ctx->d_in;
+  uint64_t* dr = (uint64_t*)(ctx->d_in + al256(nt * 32 + 32));
+  if (nt) {
+    BatchView v{d.txs, d.inputs, d.outputs, nullptr, d.bytes};
+    k_tx_digest<true><<<(unsigned)((nt + 127) / 128), 128, 0, ctx->stream>>>(v, (uint32_t)nt, dh);
+    CK(cudaGetLastError());
+    ctx->launches++;
+  }
+  rc = merkle_core(ctx, dh, nt, block_first_tx, n_blocks, dr);
+  if (rc) return rc;
+  const bool dev = kgv_ptr_is_device(roots32) != 0;
+  CK(cudaMemcpyAsync(roots32, dr, (size_t)n_blocks * 32, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->stream));
+  if (!dev) CK(cudaStreamSynchronize(ctx->stream));
   return KGV_OK;
 }

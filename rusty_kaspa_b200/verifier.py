@@ -148,6 +148,23 @@ class GpuContext:
         self._check(self._lib.kgv_tx_hashes(self._h, ctypes.byref(cb), out.ctypes.data))
         return out
 
+    def merkle_roots(self, hashes32, first):
+        """calc_merkle_root (crypto/merkle/src/lib.rs:3-30) of every group of 32-byte hashes: group g = rows [first[g], first[g+1]).
+        Returns (n_groups, 32) uint8."""
+        h = np.ascontiguousarray(hashes32, dtype=np.uint8).reshape(-1, 32)
+        f = np.ascontiguousarray(first, dtype=np.uint32)
+        out = np.zeros((len(f) - 1, 32), dtype=np.uint8)
+        self._check(self._lib.kgv_merkle_roots(self._h, h.ctypes.data if len(h) else None, f.ctypes.data, len(f) - 1, out.ctypes.data))
+        return out
+
+    def block_hash_merkle_roots(self, batch, block_first_tx):
+        """calc_hash_merkle_root of every block of the batch (block b = txs [block_first_tx[b], block_first_tx[b+1]))."""
+        f = np.ascontiguousarray(block_first_tx, dtype=np.uint32)
+        out = np.zeros((len(f) - 1, 32), dtype=np.uint8)
+        cb = _c_batch(batch, with_entries=False)
+        self._check(self._lib.kgv_block_hash_merkle_roots(self._h, ctypes.byref(cb), f.ctypes.data, len(f) - 1, out.ctypes.data))
+        return out
+
     def sighash(self, batch, items):
         """items: array of SIGHASH_ITEM_DTYPE or list of (tx, abs_input, hash_type, ecdsa). Returns (n, 32) uint8."""
         if not isinstance(items, np.ndarray):

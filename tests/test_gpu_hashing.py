@@ -59,3 +59,32 @@ def test_sighash_rejects_unknown_hash_type(gpu_ctx):
 def test_empty_batch(gpu_ctx):
     b = build_batch([])
     assert gpu_ctx.tx_ids(b).shape == (0, 32)
+
+
+@pytest.mark.gpu
+def test_merkle_roots_match_the_fixture_and_the_oracle(oracle):
+    """kgv_block_hash_merkle_roots on the 266 blocks of the simpa DAG fixture (header hashMerkleRoot), kgv_merkle_roots on ragged
+    random groups (empty, single, odd, powers of two +-1, 1000) against the oracle."""
+    import ctypes
+    import random
+    import rusty_kaspa_b200 as rk
+    from rusty_kaspa_b200.txbatch import build_batch
+    from golden_util import load, tx_from_json
+    fx = load("simpa_goref_1060.json.gz")
+    txs, first = [], [0]
+    for b in fx["blocks"]:
+        txs += [tx_from_json(t) for t in b["transactions"]]
+        first.append(len(txs))
+    ctx = rk.GpuContext(0)
+    roots = ctx.block_hash_merkle_roots(build_batch(txs), first)
+    assert [r.tobytes().hex() for r in roots] == [b["hash_merkle_root"] for b in fx["blocks"]]
+    rnd = random.Random(8)
+    sizes = [0, 1, 2, 3, 4, 5, 7, 8, 9, 0, 31, 32, 33, 1000, 1, 64, 65, 127]
+    hs = np.frombuffer(bytes(rnd.randrange(256) for _ in range(32 * sum(sizes))), dtype=np.uint8).reshape(-1, 32)
+    f = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint32)
+    got = ctx.merkle_roots(hs, f)
+    for g, n in enumerate(sizes):
+        out = ctypes.create_string_buffer(32)
+        oracle.ok_merkle_root(hs[f[g]:f[g + 1]].tobytes(), ctypes.c_size_t(n), out)
+        assert got[g].tobytes() == out.raw, (g, n)
+    ctx.close()

@@ -82,3 +82,29 @@ def test_simpa_dag_every_signed_input_verifies(oracle):
             assert oracle.ok_schnorr_verify(spk[1:33], msg, ss[1:65]) == 1
             n += 1
     assert n == 224
+
+
+def test_hash_merkle_roots_of_the_simpa_dag(oracle):
+    """hashMerkleRoot of all 266 blocks of the reference's simpa-generated DAG fixture: tx hash (hashing/tx.rs:16-20, coinbase
+    included) + calc_merkle_root (crypto/merkle/src/lib.rs:3-30); then C oracle == literal Python restatement on 0..70 hashes."""
+    import ctypes
+    import random
+    from golden_util import load, tx_from_json
+    import pyref
+
+    def c_root(hs):
+        out = ctypes.create_string_buffer(32)
+        oracle.ok_merkle_root(b"".join(hs), ctypes.c_size_t(len(hs)), out)
+        return out.raw
+
+    fx = load("simpa_goref_1060.json.gz")
+    sizes = set()
+    for b in fx["blocks"]:
+        hs = [pyref.tx_hash(tx_from_json(t)) for t in b["transactions"]]
+        sizes.add(len(hs))
+        assert c_root(hs).hex() == b["hash_merkle_root"] == pyref.merkle_root(hs).hex()
+    assert len(fx["blocks"]) == 266 and max(sizes) >= 5
+    rnd = random.Random(2)
+    for n in list(range(0, 20)) + [31, 32, 33, 63, 64, 65, 70]:
+        hs = [bytes(rnd.randrange(256) for _ in range(32)) for _ in range(n)]
+        assert c_root(hs) == pyref.merkle_root(hs), n
