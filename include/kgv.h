@@ -250,6 +250,17 @@ int kgv_merkle_roots(kgv_ctx* ctx, const uint8_t* hashes32, const uint32_t* firs
  * block of a batch: block b = transactions [block_first_tx[b], block_first_tx[b+1]) (host array of n_blocks + 1). */
 int kgv_block_hash_merkle_roots(kgv_ctx* ctx, const kgv_tx_batch* batch, const uint32_t* block_first_tx, uint32_t n_blocks, uint8_t* roots32);
 
+/* Block-body set checks of validate_body_in_isolation (body_validation_in_isolation.rs:13-23,95-131) for many blocks at
+ * once: check_duplicate_transactions, check_block_double_spends, check_no_chained_transactions, in that order; the
+ * reported item is the first offender in the reference's iteration order (the tx index for duplicates, the absolute
+ * input index otherwise).  grid y dimension = n_blocks (<= 65535 per call). */
+#define KGV_BLOCK_OK 0u
+#define KGV_BLOCK_DUPLICATE_TRANSACTIONS 1u      /* RuleError::DuplicateTransactions(tx id of txs[index]) */
+#define KGV_BLOCK_DOUBLE_SPEND_IN_SAME_BLOCK 2u  /* RuleError::DoubleSpendInSameBlock(inputs[index].previous_outpoint) */
+#define KGV_BLOCK_CHAINED_TRANSACTION 3u         /* RuleError::ChainedTransaction(inputs[index].previous_outpoint) */
+typedef struct kgv_block_check { uint32_t status, index; } kgv_block_check;
+int kgv_block_set_checks(kgv_ctx* ctx, const kgv_tx_batch* batch, const uint32_t* block_first_tx, uint32_t n_blocks, kgv_block_check* out);
+
 /* ------------------------------------------------------------------------------------------------
  * K8 MuHash: crypto/muhash/src/lib.rs, u3072.rs; consensus/core/src/muhash.rs.
  * A MuHash is the pair (numerator, denominator) of residues modulo 2^3072 - 1103717 (lib.rs:32-35); every function

@@ -112,6 +112,8 @@ void ok_tx_ids(const ok_batch* b, uint8_t* out32, int nthreads);
 void ok_tx_hashes(const ok_batch* b, uint8_t* out32, int nthreads);
 /* crypto/merkle/src/lib.rs:3-30 (calc_merkle_root over n 32-byte hashes; n == 0 -> ZERO_HASH) */
 void ok_merkle_root(const uint8_t* hashes32, size_t n, uint8_t out[32]);
+/* body_validation_in_isolation.rs:95-131 for the block [t0, t1) of the batch (see ok_tx.c) */
+int ok_block_set_checks(const ok_batch* b, uint32_t t0, uint32_t t1, uint32_t* index);
 /* consensus/core/src/hashing/sighash.rs:140-277; entries[] is indexed like b->inputs (one populated
  * UTXO entry per input, scripts in b->bytes); input_index is relative to the tx. */
 void ok_sighash(const ok_batch* b, const ok_utxo_entry* entries, size_t tx, uint32_t input_index, uint8_t hash_type, int ecdsa, uint8_t out[32]);

@@ -199,3 +199,28 @@ void ok_merkle_root(const uint8_t* hashes32, size_t n, uint8_t out[32]) {
   memcpy(out, cur, 32);
   free(cur);
 }
+
+/* body_validation_in_isolation.rs:13-23,95-131: check_duplicate_transactions, check_block_double_spends,
+ * check_no_chained_transactions for the block made of transactions [t0, t1) of the batch; returns 0 ok, 1 duplicate
+ * transactions, 2 double spend in the same block, 3 chained transaction; *index = first offender in the reference's
+ * iteration order (tx index / absolute input index). */
+int ok_block_set_checks(const ok_batch* b, uint32_t t0, uint32_t t1, uint32_t* index) {
+  *index = 0;
+  if (t0 == t1) return 0;
+  uint32_t nt = t1 - t0;
+  uint8_t* ids = (uint8_t*)malloc((size_t)nt * 32);
+  for (uint32_t t = 0; t < nt; t++) ok_tx_id(b, t0 + t, ids + 32 * (size_t)t);
+  int rc = 0;
+  for (uint32_t t = 0; t < nt && !rc; t++)
+    for (uint32_t j = 0; j < t; j++)
+      if (!memcmp(ids + 32 * (size_t)j, ids + 32 * (size_t)t, 32)) { rc = 1; *index = t0 + t; break; }
+  uint32_t i0 = b->txs[t0].first_input, i1 = b->txs[t1 - 1].first_input + b->txs[t1 - 1].n_inputs;
+  for (uint32_t i = i0; i < i1 && !rc; i++)
+    for (uint32_t j = i0; j < i; j++)
+      if (b->inputs[j].prev_index == b->inputs[i].prev_index && !memcmp(b->inputs[j].prev_txid, b->inputs[i].prev_txid, 32)) { rc = 2; *index = i; break; }
+  for (uint32_t i = i0; i < i1 && !rc; i++)
+    for (uint32_t t = 0; t < nt; t++)
+      if (b->inputs[i].prev_index < b->txs[t0 + t].n_outputs && !memcmp(ids + 32 * (size_t)t, b->inputs[i].prev_txid, 32)) { rc = 3; *index = i; break; }
+  free(ids);
+  return rc;
+}

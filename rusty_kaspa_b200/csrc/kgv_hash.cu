@@ -321,3 +321,119 @@ extern "C" int kgv_block_hash_merkle_roots(kgv_ctx* ctx, const kgv_tx_batch* bat
   if (!dev) CK(cudaStreamSynchronize(ctx->stream));
   return KGV_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Block-body set checks (consensus/src/pipeline/body_processor/body_validation_in_isolation.rs:95-131), many blocks at
+// once.  Blocks hold a few hundred transactions, so each item simply scans the earlier items of its own block
+// (O(n^2) compares of 32/36-byte keys per block, all blocks in parallel); the FIRST offender in the reference's
+// iteration order is kept with atomicMin.
+// ---------------------------------------------------------------------------------------------
+struct BlockCheckAcc { unsigned int dup_tx, double_spend, chained; };
+
+__device__ __forceinline__ bool same_outpoint(const kgv_input& a, const kgv_input& b) {
+  if (a.prev_index != b.prev_index) return false;
+  const uint32_t* x = reinterpret_cast<const uint32_t*>(a.prev_txid);
+  const uint32_t* y = reinterpret_cast<const uint32_t*>(b.prev_txid);
+  bool eq = true;
+#pragma unroll
+  for (int k = 0; k < 8; k++) eq = eq && x[k] == y[k];
+  return eq;
+}
+__global__ void __launch_bounds__(128) k_block_set_checks(const kgv_tx* __restrict__ txs, const kgv_input* __restrict__ inputs, const uint64_t* __restrict__ ids,
+                                                          const uint32_t* __restrict__ block_first_tx, BlockCheckAcc* __restrict__ acc) {
+  const uint32_t b = blockIdx.y;
+  const uint32_t t0 = block_first_tx[b], t1 = block_first_tx[b + 1];
+  if (t0 == t1) return;
+  const uint32_t i0 = txs[t0].first_input, i1 = txs[t1 - 1].first_input + txs[t1 - 1].n_inputs;
+  const uint32_t item = blockIdx.x * blockDim.x + threadIdx.x;
+  // check_duplicate_transactions (:120-129): first tx whose id already occurred
+  if (item < t1 - t0) {
+    const uint32_t t = t0 + item;
+    const uint64_t a0 = ids[4 * (size_t)t], a1 = ids[4 * (size_t)t + 1], a2 = ids[4 * (size_t)t + 2], a3 = ids[4 * (size_t)t + 3];
+    for (uint32_t j = t0; j < t; j++)
+      if (ids[4 * (size_t)j] == a0 && ids[4 * (size_t)j + 1] == a1 && ids[4 * (size_t)j + 2] == a2 && ids[4 * (size_t)j + 3] == a3) { atomicMin(&acc[b].dup_tx, t); break; }
+  }
+  if (item < i1 - i0) {
+    const uint32_t i = i0 + item;
+    const kgv_input in = inputs[i];
+    // check_block_double_spends (:95-103): first input whose outpoint already occurred
+    for (uint32_t j = i0; j < i; j++)
+      if (same_outpoint(inputs[j], in)) { atomicMin(&acc[b].double_spend, i); break; }
+    // check_no_chained_transactions (:105-118): first input spending an output created in this block
+    const uint64_t* pid = reinterpret_cast<const uint64_t*>(in.prev_txid);  // 8-byte aligned: kgv_input is 56 bytes, prev_txid first
+    for (uint32_t j = t0; j < t1; j++)
+      if (in.prev_index < txs[j].n_outputs && ids[4 * (size_t)j] == pid[0] && ids[4 * (size_t)j + 1] == pid[1] && ids[4 * (size_t)j + 2] == pid[2] &&
+          ids[4 * (size_t)j + 3] == pid[3]) { atomicMin(&acc[b].chained, i); break; }
+  }
+}
+__global__ void k_block_set_checks_final(const BlockCheckAcc* __restrict__ acc, uint32_t n_blocks, kgv_block_check* __restrict__ out) {
+  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n_blocks) return;
+  BlockCheckAcc a = acc[b];
+  kgv_block_check r;
+  // order of validate_body_in_isolation (:13-23): duplicates, then double spends, then chained transactions
+  if (a.dup_tx != 0xFFFFFFFFu) { r.status = KGV_BLOCK_DUPLICATE_TRANSACTIONS; r.index = a.dup_tx; }
+  else if (a.double_spend != 0xFFFFFFFFu) { r.status = KGV_BLOCK_DOUBLE_SPEND_IN_SAME_BLOCK; r.index = a.double_spend; }
+  else if (a.chained != 0xFFFFFFFFu) { r.status = KGV_BLOCK_CHAINED_TRANSACTION; r.index = a.chained; }
+  else { r.status = KGV_BLOCK_OK; r.index = 0; }
+  out[b] = r;
+}
+
+extern "C" int kgv_block_set_checks(kgv_ctx* ctx, const kgv_tx_batch* batch, const uint32_t* block_first_tx, uint32_t n_blocks, kgv_block_check* out) {
+  if (!ctx) return KGV_ERR_ARG;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  if (n_blocks == 0) return KGV_OK;
+  if (n_blocks > 65535) { ctx->err = "at most 65535 blocks per call"; return KGV_ERR_ARG; }
+  if (!batch || !block_first_tx || !out) { ctx->err = "null argument"; return KGV_ERR_ARG; }
+  if (kgv_ptr_is_device(block_first_tx)) { ctx->err = "block offsets must be a host array"; return KGV_ERR_ARG; }
+  uint32_t max_tx = 0;
+  for (uint32_t b = 0; b < n_blocks; b++) {
+    if (block_first_tx[b + 1] < block_first_tx[b] || block_first_tx[b + 1] > batch->n_txs) { ctx->err = "block offsets not monotone / out of range"; return KGV_ERR_ARG; }
+    if (block_first_tx[b + 1] - block_first_tx[b] > max_tx) max_tx = block_first_tx[b + 1] - block_first_tx[b];
+  }
+  CK(cudaSetDevice(ctx->device));
+  kgv_dev_batch d;
+  d.n_txs = d.n_inputs = 0;
+  if (batch->n_txs) {
+    int rc = kgv_batch_to_device(ctx, batch, &d, false);
+    if (rc) return rc;
+  }
+  const size_t nt = block_first_tx[n_blocks];
+  size_t o_ids = 0, o_first = al256(nt * 32 + 32), o_acc = al256(o_first + (n_blocks + 1) * 4), o_out = al256(o_acc + (size_t)n_blocks * sizeof(BlockCheckAcc));
+  int rc = kgv_reserve(ctx, &ctx->d_scratch, &ctx->d_scratch_cap, al256(o_out + (size_t)n_blocks * sizeof(kgv_block_check)));
+  if (rc) return rc;
+  uint8_t* S = ctx->d_scratch;
+  cudaStream_t st = ctx->stream;
+  CK(cudaMemcpyAsync(S + o_first, block_first_tx, (n_blocks + 1) * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemsetAsync(S + o_acc, 0xFF, (size_t)n_blocks * sizeof(BlockCheckAcc), st));
+  if (nt) {
+    BatchView v{d.txs, d.inputs, d.outputs, nullptr, d.bytes};
+    k_tx_digest<false><<<(unsigned)((nt + 127) / 128), 128, 0, st>>>(v, (uint32_t)nt, (uint64_t*)(S + o_ids));
+    CK(cudaGetLastError());
+    // items per block = max(#txs, #inputs).  Host batches: exact maximum; device-resident batches: the tx records cannot be
+    // read here, so the grid covers the worst case (all inputs in one block) and the kernel bounds itself.
+    uint32_t max_items = max_tx;
+    if (!kgv_ptr_is_device(batch->txs)) {
+      for (uint32_t b = 0; b < n_blocks; b++) {
+        uint32_t t0 = block_first_tx[b], t1 = block_first_tx[b + 1];
+        if (t0 == t1) continue;
+        uint32_t ni = batch->txs[t1 - 1].first_input + batch->txs[t1 - 1].n_inputs - batch->txs[t0].first_input;
+        if (ni > max_items) max_items = ni;
+      }
+    } else if (d.n_inputs > max_items) {
+      max_items = (uint32_t)d.n_inputs;
+    }
+    if (max_items == 0) max_items = 1;
+    dim3 grid((max_items + 127) / 128, n_blocks);
+    k_block_set_checks<<<grid, 128, 0, st>>>(d.txs, d.inputs, (const uint64_t*)(S + o_ids), (const uint32_t*)(S + o_first), (BlockCheckAcc*)(S + o_acc));
+    CK(cudaGetLastError());
+    ctx->launches += 2;
+  }
+  k_block_set_checks_final<<<(n_blocks + 127) / 128, 128, 0, st>>>((const BlockCheckAcc*)(S + o_acc), n_blocks, (kgv_block_check*)(S + o_out));
+  CK(cudaGetLastError());
+  ctx->launches++;
+  const bool dev = kgv_ptr_is_device(out) != 0;
+  CK(cudaMemcpyAsync(out, S + o_out, (size_t)n_blocks * sizeof(kgv_block_check), dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+  if (!dev) CK(cudaStreamSynchronize(st));
+  return KGV_OK;
+}

@@ -165,6 +165,15 @@ class GpuContext:
         self._check(self._lib.kgv_block_hash_merkle_roots(self._h, ctypes.byref(cb), f.ctypes.data, len(f) - 1, out.ctypes.data))
         return out
 
+    def block_set_checks(self, batch, block_first_tx):
+        """duplicate-tx / double-spend / chained-tx checks of validate_body_in_isolation for every block of the batch.
+        Returns a structured array (status, index), see KGV_BLOCK_* in include/kgv.h."""
+        f = np.ascontiguousarray(block_first_tx, dtype=np.uint32)
+        out = np.zeros(len(f) - 1, dtype=np.dtype([("status", "<u4"), ("index", "<u4")]))
+        cb = _c_batch(batch, with_entries=False)
+        self._check(self._lib.kgv_block_set_checks(self._h, ctypes.byref(cb), f.ctypes.data, len(f) - 1, out.ctypes.data))
+        return out
+
     def sighash(self, batch, items):
         """items: array of SIGHASH_ITEM_DTYPE or list of (tx, abs_input, hash_type, ecdsa). Returns (n, 32) uint8."""
         if not isinstance(items, np.ndarray):

@@ -88,3 +88,59 @@ def test_merkle_roots_match_the_fixture_and_the_oracle(oracle):
         oracle.ok_merkle_root(hs[f[g]:f[g + 1]].tobytes(), ctypes.c_size_t(n), out)
         assert got[g].tobytes() == out.raw, (g, n)
     ctx.close()
+
+
+@pytest.mark.gpu
+def test_block_set_checks(oracle):
+    """duplicate-tx / double-spend / chained-tx checks (body_validation_in_isolation.rs:95-131): every block of the simpa DAG
+    fixture passes; generated blocks with injected offenders get the oracle's (status, first offender)."""
+    import copy
+    import ctypes
+    import rusty_kaspa_b200 as rk
+    from rusty_kaspa_b200 import simgen
+    from rusty_kaspa_b200.txbatch import build_batch
+    from golden_util import load, tx_from_json
+    ctx = rk.GpuContext(0)
+    fx = load("simpa_goref_1060.json.gz")
+    txs, first = [], [0]
+    for b in fx["blocks"]:
+        txs += [tx_from_json(t) for t in b["transactions"]]
+        first.append(len(txs))
+    res = ctx.block_set_checks(build_batch(txs), first)
+    assert (res["status"] == 0).all()
+    # generated window cut into blocks of 1..40 txs, offenders injected into some blocks
+    _, _, wtxs = simgen.funded_window(400, n_keys=16, n_nonces=16)
+    rng = np.random.default_rng(4)
+    blocks, k = [], 0
+    while k < len(wtxs):
+        n = int(rng.integers(1, 40))
+        blocks.append([copy.deepcopy(t) for t in wtxs[k:k + n]])
+        k += n
+    for bi, blk in enumerate(blocks):
+        kind = bi % 5
+        if kind == 1 and len(blk) >= 2:      # duplicate transaction
+            blk.append(copy.deepcopy(blk[int(rng.integers(0, len(blk)))]))
+        elif kind == 2 and len(blk) >= 2:    # double spend: a later tx re-spends an earlier outpoint
+            a, c = sorted(rng.choice(len(blk), size=2, replace=False))
+            blk[c]["inputs"][0]["txid"], blk[c]["inputs"][0]["index"] = blk[a]["inputs"][-1]["txid"], blk[a]["inputs"][-1]["index"]
+        elif kind == 3 and len(blk) >= 2:    # chained: spends an output created in the same block (any position)
+            a, c = rng.choice(len(blk), size=2, replace=False)
+            blk[c]["inputs"][-1]["txid"], blk[c]["inputs"][-1]["index"] = simgen.tx_id(blk[a]), int(rng.integers(0, len(blk[a]["outputs"])))
+        elif kind == 4 and len(blk) >= 3:    # both a double spend and a chained tx: the double spend is reported
+            blk[2]["inputs"][0]["txid"], blk[2]["inputs"][0]["index"] = blk[0]["inputs"][0]["txid"], blk[0]["inputs"][0]["index"]
+            blk[1]["inputs"][0]["txid"], blk[1]["inputs"][0]["index"] = simgen.tx_id(blk[0]), 0
+    flat, first = [], [0]
+    for blk in blocks:
+        flat += blk
+        first.append(len(flat))
+    batch = build_batch(flat)
+    got = ctx.block_set_checks(batch, first)
+    ob = oracle_tx.ok_batch(batch)
+    seen = set()
+    for bi in range(len(blocks)):
+        idx = ctypes.c_uint32()
+        st = oracle.ok_block_set_checks(ctypes.byref(ob), ctypes.c_uint32(first[bi]), ctypes.c_uint32(first[bi + 1]), ctypes.byref(idx))
+        assert (int(got[bi]["status"]), int(got[bi]["index"])) == (st, idx.value if st else 0), bi
+        seen.add(st)
+    assert seen == {0, 1, 2, 3}
+    ctx.close()
