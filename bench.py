@@ -241,6 +241,54 @@ def measure_tx_validation(ctx, dev, n_txs, steps, mix=(1.0, 0.0, 0.0, 0.0), labe
             "generation_s": round(gen_s, 1)}
 
 
+def measure_ecdsa(ctx, dev, stream, n, steps):
+    """Secondary: kgv_ecdsa_verify (33-byte compressed keys, low-S rule, tri-state verdicts), device-resident triples."""
+    import torch
+    from rusty_kaspa_b200 import workload as W
+    t0 = time.perf_counter()
+    pk, msg, sig, kind = W.ecdsa_triples(1 << 14, seed=0x45434453, n_keys=4096, n_nonces=4096)
+    pk, msg, sig, kind = W.tile_triples(pk, msg, sig, kind, n)
+    gen_s = time.perf_counter() - t0
+    dpk, dmsg, dsig = (torch.from_numpy(a).to(dev) for a in (pk, msg, sig))
+    dst = torch.empty(n, dtype=torch.uint8, device=dev)
+    for _ in range(2):
+        ctx.verify_ecdsa_batch(dpk, dmsg, dsig, n=n, status=dst)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        ctx.verify_ecdsa_batch(dpk, dmsg, dsig, n=n, status=dst)
+    e1.record(stream)
+    stream.synchronize()
+    s = e0.elapsed_time(e1) * 1e-3 / steps
+    st = dst.cpu().numpy()
+    assert int((st == 1).sum()) == int((kind == 0).sum()) and not (st[kind != 0] == 1).any()
+    return {"what": "kgv_ecdsa_verify, device-resident", "n": n, "verifies_per_s": n / s, "ms_per_call": s * 1e3, "generation_s": round(gen_s, 1)}
+
+
+def measure_small_batches(ctx):
+    """Mempool-shaped use: latency of ONE kgv_validate_txs call on small host-resident batches
+    (upload + populate + context rules + scripts + verdict download), median of 20 calls."""
+    from rusty_kaspa_b200 import GpuUtxoSet, Params, TransactionValidator, simgen
+    from rusty_kaspa_b200.txbatch import build_batch
+    fkeys, fentries, txs = simgen.funded_window(256, n_keys=64, n_nonces=64)
+    earr, earena = simgen.entries_to_arrays(fentries)
+    us = GpuUtxoSet(ctx, 4096)
+    us.apply_diff(add_keys36=fkeys, add_entries=earr, add_bytes=earena)
+    tv = TransactionValidator(ctx, Params(coinbase_maturity=100, storage_mass_parameter=simgen.DEFAULT_STORAGE_MASS_PARAMETER))
+    out = {}
+    for n in (1, 16, 256):
+        b = build_batch(txs[:n])
+        ts = []
+        for _ in range(23):
+            t0 = time.perf_counter()
+            res = tv.validate_transactions_in_parallel(us, b, 10)
+            ts.append(time.perf_counter() - t0)
+        assert (res["status"] == 0).all()
+        out[str(n)] = round(sorted(ts[3:])[10] * 1e3, 3)
+    us.close()
+    return {"what": "median wall-clock ms of one kgv_validate_txs call, host arrays in, verdicts out", "ms_by_batch_size": out}
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -363,11 +411,13 @@ def run_ours(args, rank, world, local_rank):
         cpu = {"value": sample / dt, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": f"first {sample} triples of the same batch, C restatement of the reference path (oracle/), {threads} pthreads; verdicts identical to the GPU's"}
 
-    txv = txv4 = None
+    txv = txv4 = ecd = small = None
     if world == 1 and args.tx_window > 0:
         with torch.cuda.stream(stream):
             txv = measure_tx_validation(ctx, dev, args.tx_window, max(2, min(args.steps, 5)))
             txv4 = measure_tx_validation(ctx, dev, args.tx_window, max(2, min(args.steps, 5)), mix=(0.5, 0.0, 0.25, 0.25), label="config 4 shape")
+            ecd = measure_ecdsa(ctx, dev, stream, min(n, 1 << 19), 3)
+            small = measure_small_batches(ctx)
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -383,7 +433,7 @@ def run_ours(args, rank, world, local_rank):
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 128 * n * world, "d2h_bytes_per_step": n * world,
                     "steps": e2e_steps, "how": "kgv_schnorr_verify through the C ABI with pinned host buffers: H2D + kernel + D2H + sync inside the timed region (host clock)"},
-            "tx_validation": txv, "tx_validation_ecdsa_multisig": txv4, "gpu_launches": int(launches), "clocks": clocks}
+            "tx_validation": txv, "tx_validation_ecdsa_multisig": txv4, "ecdsa": ecd, "small_batches": small, "gpu_launches": int(launches), "clocks": clocks}
     emit_json_line(line)
 
 

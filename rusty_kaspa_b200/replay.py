@@ -36,8 +36,11 @@ class DagReplayer:
         self.us.close()
 
     # ---------------------------------------------------------------------------------------- blockwise
-    def replay_blockwise(self, blocks):
-        """blocks: iterable of (txs, pov_daa_score). Returns the list of per-block RESULT arrays."""
+    def replay_blockwise(self, blocks, multiset=None):
+        """blocks: iterable of (txs, pov_daa_score). Returns the list of per-block RESULT arrays.
+        multiset: optional MuHash that follows the UTXO set the way UtxoProcessingContext.multiset_hash does
+        (utxo_validation.rs:120,144): the coinbase and every accepted transaction of each block are combined into it."""
+        from .muhash import MuHash
         out = []
         for txs, pov in blocks:
             b = txs if isinstance(txs, TxBatch) else build_batch(txs)
@@ -45,6 +48,8 @@ class DagReplayer:
             if (res["status"] == TX_NEEDS_HOST_VM).any():
                 self._host_vm_with_table(b, res)
             acc = ((res["status"] == TX_OK) | (res["status"] == TX_SKIPPED_COINBASE)).astype(np.uint8)
+            if multiset is not None:  # before the spent entries are erased
+                multiset.combine(MuHash.from_transactions(self.ctx, b, acc, pov, utxo_set=self.us))
             self.us.add_transactions(b, acc, pov)
             out.append(res)
         return out

@@ -48,3 +48,22 @@ def test_windowed_equals_blockwise_equals_oracle(gpu_ctx, oracle, mix):
     assert r1.us.digest() == r2.us.digest() == ost.digest()
     assert len({int(s) for e in exp for s in e["status"]}) >= 4
     r1.close(); r2.close(); ost.close()
+
+
+def test_multiset_hash_follows_the_utxo_set(gpu_ctx):
+    """utxo_validation.rs:120,144,189: the running multiset hash (coinbase + accepted txs of every block, K8) stays equal to
+    the MuHash of the whole UTXO set (kgv_utxo_muhash) — checked after every few blocks of a replay with rejected txs."""
+    from rusty_kaspa_b200 import MuHash
+    dag, blocks = _blocks(17, 24, 16, (0.6, 0.2, 0.1, 0.1), 0.15)
+    prm = Params(coinbase_maturity=2, storage_mass_parameter=dag.C)
+    r = DagReplayer(gpu_ctx, prm, 1 << 13)
+    ms = MuHash.of_utxo_set(gpu_ctx, r.us)
+    assert ms.finalize() == MuHash(gpu_ctx).finalize()  # empty set
+    seen_reject = False
+    for w in range(0, len(blocks), 6):
+        res = r.replay_blockwise(blocks[w:w + 6], multiset=ms)
+        seen_reject = seen_reject or any(((x["status"] != 0) & (x["status"] != 12)).any() for x in res)
+        whole = MuHash.of_utxo_set(gpu_ctx, r.us)
+        assert ms.finalize() == whole.finalize(), w
+    assert seen_reject and r.us.count() > 0
+    r.close()
