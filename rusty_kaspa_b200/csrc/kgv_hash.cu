@@ -6,6 +6,7 @@
 #include "kgv_muhash.cuh"
 
 #include <cstdio>
+#include <string>
 
 using namespace kgv;
 
@@ -35,6 +36,32 @@ int kgv_batch_to_device(kgv_ctx* ctx, const kgv_tx_batch* b, kgv_dev_batch* out,
     out->txs = b->txs; out->inputs = b->inputs; out->outputs = b->outputs; out->entries = b->entries; out->bytes = b->bytes;
     return KGV_OK;
   }
+  // host-resident batch: the records are about to drive device-side pointer arithmetic, so every range is checked first
+  // (a device-resident batch is trusted: its producer is device code of the same process)
+  for (size_t i = 0; i < b->n_txs; i++) {
+    const kgv_tx& t = b->txs[i];
+    if ((uint64_t)t.first_input + t.n_inputs > b->n_inputs || (uint64_t)t.first_output + t.n_outputs > b->n_outputs ||
+        (uint64_t)t.payload_off + t.payload_len > b->n_bytes) {
+      ctx->err = "malformed batch: transaction " + std::to_string(i) + " points outside the input / output / byte arrays";
+      return KGV_ERR_ARG;
+    }
+  }
+  for (size_t i = 0; i < b->n_inputs; i++)
+    if ((uint64_t)b->inputs[i].sigscript_off + b->inputs[i].sigscript_len > b->n_bytes) {
+      ctx->err = "malformed batch: signature script of input " + std::to_string(i) + " lies outside the byte arena";
+      return KGV_ERR_ARG;
+    }
+  for (size_t i = 0; i < b->n_outputs; i++)
+    if ((uint64_t)b->outputs[i].script_off + b->outputs[i].script_len > b->n_bytes) {
+      ctx->err = "malformed batch: script of output " + std::to_string(i) + " lies outside the byte arena";
+      return KGV_ERR_ARG;
+    }
+  if (b->entries)
+    for (size_t i = 0; i < b->n_inputs; i++)
+      if (!b->entries[i].pad_[0] && (uint64_t)b->entries[i].script_off + b->entries[i].script_len > b->n_bytes) {
+        ctx->err = "malformed batch: script of entry " + std::to_string(i) + " lies outside the byte arena";
+        return KGV_ERR_ARG;
+      }
   size_t o_tx = 0;
   size_t o_in = al256(o_tx + b->n_txs * sizeof(kgv_tx));
   size_t o_out = al256(o_in + b->n_inputs * sizeof(kgv_input));

@@ -111,3 +111,27 @@ def test_dag_replay_matches_oracle(gpu_ctx, oracle, mix, frac_invalid, blocks, t
     for flags in (1, 2):
         _same_results(tv.validate_transactions_in_parallel(us, b, pov, flags=flags), ost.validate(b, pov, flags, op, threads=2))
     us.close(); ost.close()
+
+
+@pytest.mark.gpu
+def test_malformed_host_batches_are_rejected_not_executed():
+    """records of a host-resident batch that point outside their arrays give KGV_ERR_ARG (no kernel is launched on them)"""
+    import rusty_kaspa_b200 as rk
+    from rusty_kaspa_b200 import simgen, KgvError
+    from rusty_kaspa_b200.txbatch import build_batch
+    _, fe, txs = simgen.funded_window(8, n_keys=8, n_nonces=8)
+    ents, k = [], 0
+    for t in txs:
+        ents.append(fe[k:k + len(t["inputs"])]); k += len(t["inputs"])
+    ctx = rk.GpuContext(0)
+    tv = rk.TransactionValidator(ctx, rk.Params(storage_mass_parameter=simgen.DEFAULT_STORAGE_MASS_PARAMETER))
+    assert (tv.validate_populated_transactions(build_batch(txs, ents), 10)["status"] == 0).all()
+    for field, arr in (("n_inputs", "txs"), ("n_outputs", "txs"), ("payload_len", "txs"), ("sigscript_len", "inputs"), ("script_len", "outputs"), ("script_off", "entries")):
+        b = build_batch(txs, ents)
+        getattr(b, arr)[field][3] = 0x7FFFFFF0
+        with pytest.raises(KgvError):
+            tv.validate_populated_transactions(b, 10)
+        if arr != "entries":
+            with pytest.raises(KgvError):
+                ctx.tx_ids(b)
+    ctx.close()
