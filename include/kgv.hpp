@@ -1,0 +1,323 @@
+// kgv.hpp — C++17 host-side mirror of the reference interface for the validation hot path, on top of the C ABI (kgv.h).
+//
+// The reference is Rust; no Rust toolchain exists in the build image, so the typed host layer a Rust shim would provide
+// is written in C++ (header only, RAII, exceptions for transport errors).  Names and argument meaning follow the
+// reference so that call sites read like the original:
+//   kgv::Transaction / TransactionInput / TransactionOutput / UtxoEntry     consensus/core/src/tx.rs:49-185
+//   kgv::TransactionValidator::validate_populated_transaction_and_get_fee*  consensus/src/processes/transaction_validator/tx_validation_in_utxo_context.rs:34-61
+//   kgv::TransactionValidator::validate_transactions_in_parallel           consensus/src/pipeline/virtual_processor/utxo_validation.rs:262-278
+//   kgv::TransactionValidator::validate_transactions_with_muhash_in_parallel  …:282-309
+//   kgv::UtxoSet (get / write_diff / add_transactions)                      consensus/src/model/stores/utxo_set.rs:107-112, consensus/core/src/utxo/utxo_diff.rs:233-247
+//   kgv::MuHash (add_element / remove_element / combine / finalize / serialize)  crypto/muhash/src/lib.rs:59-121
+//   kgv::SigVerifier (check_schnorr_signatures / check_ecdsa_signatures)    crypto/txscript/src/lib.rs:574-643, batched
+//   kgv::calc_hash_merkle_roots, kgv::check_block_bodies                    consensus/core/src/merkle.rs:5-7, body_validation_in_isolation.rs:95-131
+// (* batched: one verdict per transaction.)  Verdicts are data (status codes of kgv.h); only transport failures throw.
+// There is no CPU execution path behind any of this: without libkgv.so + a CUDA device, Context's constructor throws.
+#pragma once
+#include <array>
+#include <cstdint>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "kgv.h"
+
+namespace kgv {
+
+class Error : public std::runtime_error {
+ public:
+  Error(int code, const std::string& what) : std::runtime_error(what), code_(code) {}
+  int code() const { return code_; }
+
+ private:
+  int code_;
+};
+
+// ---- data model (consensus/core/src/tx.rs) ----
+using Hash = std::array<uint8_t, 32>;
+using SubnetworkId = std::array<uint8_t, 20>;
+inline SubnetworkId subnetwork_id_native() { return SubnetworkId{}; }
+inline SubnetworkId subnetwork_id_coinbase() { SubnetworkId s{}; s[0] = 1; return s; }
+struct ScriptPublicKey { uint16_t version = 0; std::vector<uint8_t> script; };
+struct TransactionOutpoint { Hash transaction_id{}; uint32_t index = 0; };
+struct TransactionInput { TransactionOutpoint previous_outpoint; std::vector<uint8_t> signature_script; uint64_t sequence = 0; uint8_t sig_op_count = 0; };
+struct TransactionOutput { uint64_t value = 0; ScriptPublicKey script_public_key; };
+struct UtxoEntry { uint64_t amount = 0; ScriptPublicKey script_public_key; uint64_t block_daa_score = 0; bool is_coinbase = false; };
+struct Transaction {
+  uint16_t version = 0;
+  std::vector<TransactionInput> inputs;
+  std::vector<TransactionOutput> outputs;
+  uint64_t lock_time = 0;
+  SubnetworkId subnetwork_id{};
+  uint64_t gas = 0;
+  std::vector<uint8_t> payload;
+  uint64_t mass = 0;  // committed storage mass
+};
+
+// Flat SoA form of a list of (optionally populated) transactions: what crosses the ABI.
+class TxBatch {
+ public:
+  // entries: nullptr, or for each transaction one optional entry per input (nullptr element = missing outpoint)
+  void push(const Transaction& tx, const std::vector<const UtxoEntry*>* entries = nullptr) {
+    kgv_tx t{};
+    t.first_input = (uint32_t)inputs_.size();
+    t.n_inputs = (uint32_t)tx.inputs.size();
+    t.first_output = (uint32_t)outputs_.size();
+    t.n_outputs = (uint32_t)tx.outputs.size();
+    t.lock_time = tx.lock_time; t.gas = tx.gas; t.mass = tx.mass; t.version = tx.version;
+    std::memcpy(t.subnetwork_id, tx.subnetwork_id.data(), 20);
+    t.flags = tx.subnetwork_id == subnetwork_id_coinbase() ? 1 : 0;
+    auto pl = put(tx.payload);
+    t.payload_off = pl.first; t.payload_len = pl.second;
+    for (size_t k = 0; k < tx.inputs.size(); k++) {
+      const TransactionInput& in = tx.inputs[k];
+      kgv_input r{};
+      std::memcpy(r.prev_txid, in.previous_outpoint.transaction_id.data(), 32);
+      r.prev_index = in.previous_outpoint.index;
+      auto ss = put(in.signature_script);
+      r.sigscript_off = ss.first; r.sigscript_len = ss.second;
+      r.sig_op_count = in.sig_op_count; r.sequence = in.sequence;
+      inputs_.push_back(r);
+      kgv_utxo_entry e{};
+      const UtxoEntry* ue = entries && k < entries->size() ? (*entries)[k] : nullptr;
+      if (ue) {
+        e.amount = ue->amount; e.block_daa_score = ue->block_daa_score; e.spk_version = ue->script_public_key.version; e.is_coinbase = ue->is_coinbase ? 1 : 0;
+        auto sc = put(ue->script_public_key.script);
+        e.script_off = sc.first; e.script_len = sc.second;
+      } else {
+        e.pad_[0] = 1;  // absent -> MissingTxOutpoints
+      }
+      entries_.push_back(e);
+      populated_ = populated_ || entries != nullptr;
+    }
+    for (const TransactionOutput& o : tx.outputs) {
+      kgv_output r{};
+      r.value = o.value; r.spk_version = o.script_public_key.version;
+      auto sc = put(o.script_public_key.script);
+      r.script_off = sc.first; r.script_len = sc.second;
+      outputs_.push_back(r);
+    }
+    txs_.push_back(t);
+  }
+  // adopt already-flat arrays (e.g. read from disk)
+  void assign(std::vector<kgv_tx> txs, std::vector<kgv_input> inputs, std::vector<kgv_output> outputs, std::vector<kgv_utxo_entry> entries, std::vector<uint8_t> bytes) {
+    txs_ = std::move(txs); inputs_ = std::move(inputs); outputs_ = std::move(outputs); entries_ = std::move(entries); bytes_ = std::move(bytes);
+    populated_ = !entries_.empty();
+  }
+  size_t len() const { return txs_.size(); }
+  size_t n_inputs() const { return inputs_.size(); }
+  size_t n_outputs() const { return outputs_.size(); }
+  kgv_tx_batch view(bool with_entries) const {
+    kgv_tx_batch b{};
+    b.txs = txs_.data(); b.n_txs = txs_.size();
+    b.inputs = inputs_.data(); b.n_inputs = inputs_.size();
+    b.outputs = outputs_.data(); b.n_outputs = outputs_.size();
+    b.entries = (with_entries && populated_) ? entries_.data() : nullptr;
+    b.bytes = bytes_.data(); b.n_bytes = bytes_.size();
+    return b;
+  }
+
+ private:
+  std::pair<uint32_t, uint32_t> put(const std::vector<uint8_t>& v) {
+    uint32_t off = (uint32_t)bytes_.size();
+    bytes_.insert(bytes_.end(), v.begin(), v.end());
+    return {off, (uint32_t)v.size()};
+  }
+  std::vector<kgv_tx> txs_;
+  std::vector<kgv_input> inputs_;
+  std::vector<kgv_output> outputs_;
+  std::vector<kgv_utxo_entry> entries_;
+  std::vector<uint8_t> bytes_{0, 0, 0, 0, 0, 0, 0, 0};
+  bool populated_ = false;
+};
+
+// ---- context ----
+class Context {
+ public:
+  explicit Context(int device = 0) {
+    int rc = kgv_create(device, 0, &h_);
+    if (rc != KGV_OK) throw Error(rc, "kgv_create failed: no usable CUDA device (this library has no CPU path)");
+  }
+  ~Context() { if (h_) kgv_destroy(h_); }
+  Context(const Context&) = delete;
+  Context& operator=(const Context&) = delete;
+  kgv_ctx* get() const { return h_; }
+  void check(int rc) const { if (rc != KGV_OK) throw Error(rc, std::string("libkgv: ") + kgv_last_error(h_)); }
+
+ private:
+  kgv_ctx* h_ = nullptr;
+};
+
+// ---- signatures: batch counterparts of check_schnorr_signature / check_ecdsa_signature ----
+class SigVerifier {
+ public:
+  explicit SigVerifier(Context& c) : c_(c) {}
+  // SoA byte arrays: pk 32*n (x-only) / 33*n (compressed), msg 32*n, sig 64*n.  Returns KGV_SIG_* per triple.
+  std::vector<uint8_t> check_schnorr_signatures(const std::vector<uint8_t>& pk32, const std::vector<uint8_t>& msg32, const std::vector<uint8_t>& sig64) {
+    size_t n = msg32.size() / 32;
+    if (pk32.size() != 32 * n || sig64.size() != 64 * n) throw Error(KGV_ERR_ARG, "check_schnorr_signatures: array sizes disagree");
+    std::vector<uint8_t> st(n);
+    c_.check(kgv_schnorr_verify(c_.get(), pk32.data(), msg32.data(), sig64.data(), n, st.data()));
+    return st;
+  }
+  std::vector<uint8_t> check_ecdsa_signatures(const std::vector<uint8_t>& pk33, const std::vector<uint8_t>& msg32, const std::vector<uint8_t>& sig64) {
+    size_t n = msg32.size() / 32;
+    if (pk33.size() != 33 * n || sig64.size() != 64 * n) throw Error(KGV_ERR_ARG, "check_ecdsa_signatures: array sizes disagree");
+    std::vector<uint8_t> st(n);
+    c_.check(kgv_ecdsa_verify(c_.get(), pk33.data(), msg32.data(), sig64.data(), n, st.data()));
+    return st;
+  }
+
+ private:
+  Context& c_;
+};
+
+// ---- MuHash ----
+class MuHash {
+ public:
+  explicit MuHash(Context& c) : c_(&c) { numerator_[0] = 1; denominator_[0] = 1; }
+  MuHash(Context& c, const std::array<uint8_t, 384>& num, const std::array<uint8_t, 384>& den) : c_(&c), numerator_(num), denominator_(den) {}
+  MuHash& add_element(const std::vector<uint8_t>& data) { return update({data}, {}); }
+  MuHash& remove_element(const std::vector<uint8_t>& data) { return update({}, {data}); }
+  MuHash& update(const std::vector<std::vector<uint8_t>>& add, const std::vector<std::vector<uint8_t>>& remove) {
+    std::vector<uint8_t> data, flags;
+    std::vector<uint64_t> off{0};
+    for (const auto& v : add) { data.insert(data.end(), v.begin(), v.end()); off.push_back(data.size()); flags.push_back(0); }
+    for (const auto& v : remove) { data.insert(data.end(), v.begin(), v.end()); off.push_back(data.size()); flags.push_back(1); }
+    if (flags.empty()) return *this;
+    data.resize(data.size() + 8);
+    MuHash part(*c_);
+    c_->check(kgv_muhash_elements(c_->get(), data.data(), off.data(), flags.data(), flags.size(), part.numerator_.data(), part.denominator_.data()));
+    return combine(part);
+  }
+  MuHash& combine(const MuHash& o) {
+    c_->check(kgv_muhash_combine(c_->get(), numerator_.data(), denominator_.data(), o.numerator_.data(), o.denominator_.data()));
+    return *this;
+  }
+  std::array<uint8_t, 384> serialize() { finalize(); return numerator_; }
+  Hash finalize() {
+    std::array<uint8_t, 384> ser{};
+    Hash h{};
+    c_->check(kgv_muhash_finalize(c_->get(), numerator_.data(), denominator_.data(), ser.data(), h.data()));
+    numerator_ = ser;  // normalize(): numerator /= denominator, denominator = 1
+    denominator_.fill(0); denominator_[0] = 1;
+    return h;
+  }
+  const std::array<uint8_t, 384>& numerator() const { return numerator_; }
+  const std::array<uint8_t, 384>& denominator() const { return denominator_; }
+
+ private:
+  Context* c_;
+  std::array<uint8_t, 384> numerator_{}, denominator_{};
+};
+
+// ---- UTXO set on the GPU ----
+class UtxoSet {
+ public:
+  UtxoSet(Context& c, uint64_t capacity_slots) : c_(c) { c_.check(kgv_utxo_create(c_.get(), capacity_slots, &h_)); }
+  ~UtxoSet() { if (h_) kgv_utxo_destroy(c_.get(), h_); }
+  UtxoSet(const UtxoSet&) = delete;
+  UtxoSet& operator=(const UtxoSet&) = delete;
+  kgv_utxo_table* get() const { return h_; }
+  // write_diff_batch: delete `removed`, then put `added`
+  void write_diff(const std::vector<TransactionOutpoint>& removed, const std::vector<std::pair<TransactionOutpoint, UtxoEntry>>& added) {
+    std::vector<uint8_t> rk(36 * removed.size()), ak(36 * added.size()), rs(removed.size() + 1), as(added.size() + 1), bytes(8);
+    std::vector<kgv_utxo_entry> ae(added.size());
+    for (size_t i = 0; i < removed.size(); i++) key36(rk.data() + 36 * i, removed[i]);
+    for (size_t i = 0; i < added.size(); i++) {
+      key36(ak.data() + 36 * i, added[i].first);
+      const UtxoEntry& e = added[i].second;
+      ae[i].amount = e.amount; ae[i].block_daa_score = e.block_daa_score; ae[i].spk_version = e.script_public_key.version; ae[i].is_coinbase = e.is_coinbase ? 1 : 0;
+      ae[i].script_off = (uint32_t)bytes.size(); ae[i].script_len = (uint32_t)e.script_public_key.script.size();
+      bytes.insert(bytes.end(), e.script_public_key.script.begin(), e.script_public_key.script.end());
+    }
+    c_.check(kgv_utxo_apply_diff(c_.get(), h_, removed.empty() ? nullptr : rk.data(), removed.size(), rs.data(), added.empty() ? nullptr : ak.data(),
+                                 added.empty() ? nullptr : ae.data(), bytes.data(), bytes.size(), added.size(), as.data()));
+  }
+  // UtxoDiff::add_transaction for every accepted transaction of the batch
+  void add_transactions(const TxBatch& b, const std::vector<uint8_t>& accept, uint64_t pov_daa_score) {
+    kgv_tx_batch v = b.view(false);
+    c_.check(kgv_utxo_apply_accepted(c_.get(), h_, &v, accept.data(), pov_daa_score));
+  }
+  uint64_t count() { uint64_t n = 0; c_.check(kgv_utxo_count(c_.get(), h_, &n)); return n; }
+  MuHash muhash() {
+    std::array<uint8_t, 384> num{}, one{};
+    one[0] = 1;
+    c_.check(kgv_utxo_muhash(c_.get(), h_, num.data()));
+    return MuHash(c_, num, one);
+  }
+
+ private:
+  static void key36(uint8_t* k, const TransactionOutpoint& o) {
+    std::memcpy(k, o.transaction_id.data(), 32);
+    for (int i = 0; i < 4; i++) k[32 + i] = (uint8_t)(o.index >> (8 * i));
+  }
+  Context& c_;
+  kgv_utxo_table* h_ = nullptr;
+};
+
+// ---- transaction validation in UTXO context ----
+struct Params {
+  uint64_t coinbase_maturity = 100, storage_mass_parameter = 1000000000000ull, max_sompi = 2900000000000000000ull;  // consensus/core/src/config/params.rs, constants.rs
+};
+enum class TxValidationFlags : uint32_t { Full = KGV_FLAGS_FULL, SkipScriptChecks = KGV_FLAGS_SKIP_SCRIPT_CHECKS, SkipMassCheck = KGV_FLAGS_SKIP_MASS_CHECK };
+
+class TransactionValidator {
+ public:
+  TransactionValidator(Context& c, const Params& p) : c_(c) { p_.coinbase_maturity = p.coinbase_maturity; p_.storage_mass_parameter = p.storage_mass_parameter; p_.max_sompi = p.max_sompi; }
+  // one verdict (status, script error, failing input, fee) per transaction of a populated batch
+  std::vector<kgv_tx_result> validate_populated_transactions(const TxBatch& b, uint64_t pov_daa_score, TxValidationFlags flags = TxValidationFlags::Full, bool host_vm = true) {
+    std::vector<kgv_tx_result> res(b.len());
+    kgv_tx_batch v = b.view(true);
+    c_.check(kgv_validate_populated(c_.get(), &v, pov_daa_score, (uint32_t)flags, &p_, res.data()));
+    if (host_vm) check_scripts_host(v, res);
+    return res;
+  }
+  std::vector<kgv_tx_result> validate_transactions_in_parallel(UtxoSet& utxo_view, const TxBatch& b, uint64_t pov_daa_score, TxValidationFlags flags = TxValidationFlags::Full) {
+    std::vector<kgv_tx_result> res(b.len());
+    kgv_tx_batch v = b.view(false);
+    c_.check(kgv_validate_txs(c_.get(), utxo_view.get(), &v, pov_daa_score, (uint32_t)flags, &p_, res.data()));
+    return res;
+  }
+  std::pair<std::vector<kgv_tx_result>, MuHash> validate_transactions_with_muhash_in_parallel(UtxoSet& utxo_view, const TxBatch& b, uint64_t pov_daa_score,
+                                                                                            TxValidationFlags flags = TxValidationFlags::Full) {
+    auto res = validate_transactions_in_parallel(utxo_view, b, pov_daa_score, flags);
+    std::vector<uint8_t> accept(res.size());
+    for (size_t i = 0; i < res.size(); i++) accept[i] = res[i].status == KGV_TX_OK;
+    MuHash mh(c_);
+    std::array<uint8_t, 384> num{}, den{};
+    kgv_tx_batch v = b.view(false);
+    c_.check(kgv_muhash_txs(c_.get(), utxo_view.get(), &v, accept.data(), pov_daa_score, num.data(), den.data()));
+    return {std::move(res), MuHash(c_, num, den)};
+  }
+
+ private:
+  void check_scripts_host(const kgv_tx_batch& v, std::vector<kgv_tx_result>& res) {
+    std::vector<uint32_t> idx;
+    for (size_t i = 0; i < res.size(); i++) if (res[i].status == KGV_TX_NEEDS_HOST_VM) idx.push_back((uint32_t)i);
+    if (idx.empty()) return;
+    std::vector<kgv_tx_result> out(idx.size());
+    c_.check(kgv_check_scripts_host(c_.get(), &v, idx.data(), idx.size(), out.data()));
+    for (size_t k = 0; k < idx.size(); k++) { uint64_t fee = res[idx[k]].fee; res[idx[k]] = out[k]; res[idx[k]].fee = fee; }
+  }
+  Context& c_;
+  kgv_params p_{};
+};
+
+// ---- block body helpers ----
+inline std::vector<Hash> calc_hash_merkle_roots(Context& c, const TxBatch& b, const std::vector<uint32_t>& block_first_tx) {
+  std::vector<Hash> roots(block_first_tx.size() - 1);
+  kgv_tx_batch v = b.view(false);
+  c.check(kgv_block_hash_merkle_roots(c.get(), &v, block_first_tx.data(), (uint32_t)roots.size(), roots.empty() ? nullptr : roots[0].data()));
+  return roots;
+}
+inline std::vector<kgv_block_check> check_block_bodies(Context& c, const TxBatch& b, const std::vector<uint32_t>& block_first_tx) {
+  std::vector<kgv_block_check> out(block_first_tx.size() - 1);
+  kgv_tx_batch v = b.view(false);
+  c.check(kgv_block_set_checks(c.get(), &v, block_first_tx.data(), (uint32_t)out.size(), out.data()));
+  return out;
+}
+
+}  // namespace kgv
