@@ -336,29 +336,35 @@ __global__ void k_plan(BatchView b, size_t n_inputs, const uint32_t* __restrict_
   cnt_e[i] = ce;
 }
 
-// single-block exclusive scan (inputs per call are at most a few hundred thousand: plumbing, not a hot kernel)
-__global__ void k_exclusive_scan(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, size_t n, uint32_t* __restrict__ total) {
-  __shared__ uint32_t sums[1024];
-  __shared__ uint32_t carry;
-  if (threadIdx.x == 0) carry = 0;
+// exclusive scans of the two per-input item-count arrays (Schnorr / ECDSA), one block each in ONE launch: every thread sums a
+// contiguous chunk, the 1024 chunk sums are scanned in shared memory, then each thread rewrites its chunk.  (Plumbing: a few
+// microseconds for a few hundred thousand inputs; the first version scanned 1024 elements per barrier-laden pass and took
+// 80 us per array for a 49 k-input window.)
+__global__ void __launch_bounds__(1024) k_exclusive_scan2(const uint32_t* __restrict__ in0, uint32_t* __restrict__ out0, const uint32_t* __restrict__ in1,
+                                                          uint32_t* __restrict__ out1, size_t n, uint32_t* __restrict__ totals) {
+  const uint32_t* in = blockIdx.x ? in1 : in0;
+  uint32_t* out = blockIdx.x ? out1 : out0;
+  __shared__ uint32_t part[1024];
+  const size_t per = (n + 1023) / 1024;
+  const size_t a = (size_t)threadIdx.x * per;
+  const size_t b = a + per < n ? a + per : n;
+  uint32_t s = 0;
+  for (size_t i = a; i < b; i++) s += in[i];
+  part[threadIdx.x] = s;
   __syncthreads();
-  for (size_t base = 0; base < n; base += 1024) {
-    size_t i = base + threadIdx.x;
-    uint32_t v = i < n ? in[i] : 0;
-    sums[threadIdx.x] = v;
+  for (int off = 1; off < 1024; off <<= 1) {
+    uint32_t t = threadIdx.x >= off ? part[threadIdx.x - off] : 0;
     __syncthreads();
-    for (int off = 1; off < 1024; off <<= 1) {
-      uint32_t t = threadIdx.x >= off ? sums[threadIdx.x - off] : 0;
-      __syncthreads();
-      sums[threadIdx.x] += t;
-      __syncthreads();
-    }
-    if (i < n) out[i] = carry + sums[threadIdx.x] - v;
-    __syncthreads();
-    if (threadIdx.x == 1023) carry += sums[1023];
+    part[threadIdx.x] += t;
     __syncthreads();
   }
-  if (threadIdx.x == 0) *total = carry;
+  uint32_t run = part[threadIdx.x] - s;  // exclusive prefix of this thread's chunk
+  for (size_t i = a; i < b; i++) {
+    uint32_t v = in[i];
+    out[i] = run;
+    run += v;
+  }
+  if (threadIdx.x == 1023) totals[blockIdx.x] = part[1023];
 }
 
 struct ItemRef { uint32_t input; uint32_t k; };  // which input / which candidate pair
@@ -772,11 +778,9 @@ static int validate_core(kgv_ctx* ctx, kgv_utxo_table* table, const kgv_tx_batch
     k_plan<<<nblk(ni, 128), 128, 0, st>>>(v, ni, itx, dres, plans, cs, ce);
     CK(cudaGetLastError());
     STAGE("plan");
-    k_exclusive_scan<<<1, 1024, 0, st>>>(cs, os, ni, tot);
+    k_exclusive_scan2<<<2, 1024, 0, st>>>(cs, os, ce, oe, ni, tot);
     CK(cudaGetLastError());
-    k_exclusive_scan<<<1, 1024, 0, st>>>(ce, oe, ni, tot + 1);
-    CK(cudaGetLastError());
-    ctx->launches += 3;
+    ctx->launches += 2;
     uint32_t totals[2];
     CK(cudaMemcpyAsync(totals, tot, sizeof totals, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
