@@ -21,6 +21,7 @@ struct kgv_ctx {
   cudaStream_t own_stream = nullptr;
   cudaStream_t aux_stream = nullptr;              // fork/join side stream: ECDSA items verify beside the Schnorr items
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_chunk[32] = {};                  // upload-complete events of the chunked host-pointer verify path
   cudaStream_t stream = nullptr;
   uint32_t* gtab = nullptr;     // [2][65536][16] u32: v*G and v*2^128*G, affine
   uint8_t* d_in = nullptr;      // staging for host-pointer calls

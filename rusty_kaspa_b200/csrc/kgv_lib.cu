@@ -360,6 +360,7 @@ extern "C" void kgv_destroy(kgv_ctx* ctx) {
   if (ctx->d_batch) cudaFree(ctx->d_batch);
   if (ctx->d_scratch) cudaFree(ctx->d_scratch);
   if (ctx->d_mu) cudaFree(ctx->d_mu);
+  for (cudaEvent_t e : ctx->ev_chunk) if (e) cudaEventDestroy(e);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
@@ -436,10 +437,32 @@ static int verify_common(kgv_ctx* ctx, const uint8_t* pk, size_t pk_stride, cons
     if (rc) return rc;
     rc = kgv_reserve(ctx, &ctx->d_out, &ctx->d_out_cap, n);
     if (rc) return rc;
+    dpk = ctx->d_in; dmsg = ctx->d_in + off_msg; dsig = ctx->d_in + off_sig; dst = ctx->d_out;
+    // Large host batches are uploaded in chunks of one full persistent wave (resident threads x KGV_ITEMS signatures) on the
+    // side stream while the previous chunk is being verified: only the first chunk's upload is exposed.
+    const size_t chunk = (size_t)ctx->resident_blocks * KGV_BLOCK * KGV_ITEMS;
+    if (n >= 2 * chunk && (n + chunk - 1) / chunk <= 32) {
+      CK(cudaEventRecord(ctx->ev_fork, ctx->stream));          // the staging buffers may still be read by earlier work of this stream
+      CK(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0));
+      size_t c = 0;
+      for (size_t a = 0; a < n; a += chunk, c++) {
+        const size_t m = n - a < chunk ? n - a : chunk;
+        if (!ctx->ev_chunk[c]) CK(cudaEventCreateWithFlags(&ctx->ev_chunk[c], cudaEventDisableTiming));
+        CK(cudaMemcpyAsync(ctx->d_in + pk_stride * a, pk + pk_stride * a, pk_stride * m, cudaMemcpyHostToDevice, ctx->aux_stream));
+        CK(cudaMemcpyAsync(ctx->d_in + off_msg + 32 * a, msg + 32 * a, 32 * m, cudaMemcpyHostToDevice, ctx->aux_stream));
+        CK(cudaMemcpyAsync(ctx->d_in + off_sig + 64 * a, sig + 64 * a, 64 * m, cudaMemcpyHostToDevice, ctx->aux_stream));
+        CK(cudaEventRecord(ctx->ev_chunk[c], ctx->aux_stream));
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_chunk[c], 0));
+        int rc2 = kgv_launch_verify(ctx, dpk + pk_stride * a, dmsg + 32 * a, dsig + 64 * a, m, dst + a, ecdsa);
+        if (rc2) return rc2;
+      }
+      CK(cudaMemcpyAsync(status, dst, n, cudaMemcpyDeviceToHost, ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));
+      return KGV_OK;
+    }
     CK(cudaMemcpyAsync(ctx->d_in, pk, pk_stride * n, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_in + off_msg, msg, 32 * n, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_in + off_sig, sig, 64 * n, cudaMemcpyHostToDevice, ctx->stream));
-    dpk = ctx->d_in; dmsg = ctx->d_in + off_msg; dsig = ctx->d_in + off_sig; dst = ctx->d_out;
   }
   {
     int rc = kgv_launch_verify(ctx, dpk, dmsg, dsig, n, dst, ecdsa);
