@@ -415,19 +415,17 @@ KGV_HD bool fe_equal(const fe& a, const fe& b) {
 
 // reduce a 512-bit value t[0..15] modulo p into a weakly reduced element
 KGV_HD void fe_reduce_wide(fe& r, const uint32_t* t) {
-  // value = lo + hi * 2^256 == lo + hi*977 + (hi << 32)
-  // q = hi * 977 as a 9-limb number, from two non-overlapping IMAD.WIDE sets
-  uint32_t qe[9], qo[9];
+  // value = lo + hi * 2^256 == lo + hi*977 + (hi << 32).  The multiply-accumulates do the additions for free:
+  //   x  = lo + hi_even * 977          (products at even limbs, accumulated straight onto a copy of lo; x[8] = overflow limb)
+  //   q  = hi + hi_odd * 977           (the odd-limb products and the "hi << 32" term share the offset of one limb)
+  //   x += q << 32                     (the only explicit carry chain of the first fold)
+  uint32_t x[9], q[9];
 #pragma unroll
-  for (int i = 0; i < 9; i++) { qe[i] = 0; qo[i] = 0; }
-  mad_row4(qe, t[8], t[10], t[12], t[14], 977u);  // limbs 0..7 (+qe[8]=0)
-  mad_row4(qo, t[9], t[11], t[13], t[15], 977u);  // limbs 1..8 when shifted
-  uint32_t x[8];
-  uint32_t top0, top1;
-  // x = lo + qe ; carries collect in top
-  top0 = add8(x, t, qe);
-  top1 = 0;
-  // x += (qo << 32) ; x += (hi << 32): both occupy limbs 1..8
+  for (int i = 0; i < 8; i++) { x[i] = t[i]; q[i] = t[8 + i]; }
+  x[8] = 0; q[8] = 0;
+  mad_row4(x, t[8], t[10], t[12], t[14], 977u);
+  mad_row4(q, t[9], t[11], t[13], t[15], 977u);
+  uint32_t top0 = x[8], top1;
 #if defined(__CUDACC__)
   asm("add.cc.u32 %0, %0, %9;\n\t"
       "addc.cc.u32 %1, %1, %10;\n\t"
@@ -437,30 +435,15 @@ KGV_HD void fe_reduce_wide(fe& r, const uint32_t* t) {
       "addc.cc.u32 %5, %5, %14;\n\t"
       "addc.cc.u32 %6, %6, %15;\n\t"
       "addc.cc.u32 %7, %7, %16;\n\t"
-      "addc.u32 %8, %8, 0;"
-      : "+r"(x[1]), "+r"(x[2]), "+r"(x[3]), "+r"(x[4]), "+r"(x[5]), "+r"(x[6]), "+r"(x[7]), "+r"(top0), "+r"(top1)
-      : "r"(qo[0]), "r"(qo[1]), "r"(qo[2]), "r"(qo[3]), "r"(qo[4]), "r"(qo[5]), "r"(qo[6]), "r"(qo[7]));
-  asm("add.cc.u32 %0, %0, %9;\n\t"
-      "addc.cc.u32 %1, %1, %10;\n\t"
-      "addc.cc.u32 %2, %2, %11;\n\t"
-      "addc.cc.u32 %3, %3, %12;\n\t"
-      "addc.cc.u32 %4, %4, %13;\n\t"
-      "addc.cc.u32 %5, %5, %14;\n\t"
-      "addc.cc.u32 %6, %6, %15;\n\t"
-      "addc.cc.u32 %7, %7, %16;\n\t"
-      "addc.u32 %8, %8, 0;"
-      : "+r"(x[1]), "+r"(x[2]), "+r"(x[3]), "+r"(x[4]), "+r"(x[5]), "+r"(x[6]), "+r"(x[7]), "+r"(top0), "+r"(top1)
-      : "r"(t[8]), "r"(t[9]), "r"(t[10]), "r"(t[11]), "r"(t[12]), "r"(t[13]), "r"(t[14]), "r"(t[15]));
+      "addc.u32 %8, %17, 0;"
+      : "+r"(x[1]), "+r"(x[2]), "+r"(x[3]), "+r"(x[4]), "+r"(x[5]), "+r"(x[6]), "+r"(x[7]), "+r"(top0), "=r"(top1)
+      : "r"(q[0]), "r"(q[1]), "r"(q[2]), "r"(q[3]), "r"(q[4]), "r"(q[5]), "r"(q[6]), "r"(q[7]), "r"(q[8]));
 #else
   {
     uint64_t c = 0;
-    for (int i = 1; i < 8; i++) { c += (uint64_t)x[i] + qo[i - 1]; x[i] = (uint32_t)c; c >>= 32; }
-    c += (uint64_t)top0 + qo[7]; top0 = (uint32_t)c; c >>= 32;
-    top1 += (uint32_t)c;
-    c = 0;
-    for (int i = 1; i < 8; i++) { c += (uint64_t)x[i] + t[7 + i]; x[i] = (uint32_t)c; c >>= 32; }
-    c += (uint64_t)top0 + t[15]; top0 = (uint32_t)c; c >>= 32;
-    top1 += (uint32_t)c;
+    for (int i = 1; i < 8; i++) { c += (uint64_t)x[i] + q[i - 1]; x[i] = (uint32_t)c; c >>= 32; }
+    c += (uint64_t)top0 + q[7]; top0 = (uint32_t)c; c >>= 32;
+    top1 = q[8] + (uint32_t)c;
   }
 #endif
   // second fold: (top1:top0) < 2^34 ; top * C = top*977 + (top << 32)
@@ -472,7 +455,22 @@ KGV_HD void fe_reduce_wide(fe& r, const uint32_t* t) {
 #pragma unroll
   for (int i = 0; i < 8; i++) r.v[i] = x[i];
   uint32_t c = add8_small3(r.v, a0, a1, a2);
-  if (c) (void)fe_add_kC(r, 1);  // wrapped: the remainder is tiny, one more fold cannot wrap
+  // c == 1: the sum wrapped past 2^256, so what is left is < (a2:a1:a0) < 2^67 (limbs 3..7 are zero) and the pending
+  // 2^256 == 2^32 + 977 fits into limbs 0..2 without further propagation: three unconditional instructions, no branch
+  uint32_t k = 977u * c;
+#if defined(__CUDACC__)
+  asm("add.cc.u32 %0, %0, %3;\n\t"
+      "addc.cc.u32 %1, %1, %4;\n\t"
+      "addc.u32 %2, %2, 0;"
+      : "+r"(r.v[0]), "+r"(r.v[1]), "+r"(r.v[2])
+      : "r"(k), "r"(c));
+#else
+  {
+    uint64_t w = (uint64_t)r.v[0] + k; r.v[0] = (uint32_t)w; w >>= 32;
+    w += (uint64_t)r.v[1] + c; r.v[1] = (uint32_t)w; w >>= 32;
+    r.v[2] += (uint32_t)w;
+  }
+#endif
 }
 
 // On the device fe_mul / fe_sqr are real (non-inlined) functions taking and returning their
