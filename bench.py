@@ -151,9 +151,9 @@ def run_reference(args, rank, world):
 
 
 # Issue cycles per Schnorr verify per SM sub-partition for the shipping kernel's instruction stream:
-# 1.32e5 IMAD.WIDE x 4.3 cycles + 3.25e5 other instructions x 1 cycle, per warp of 32 verifies (ncu instruction
+# 1.355e5 IMAD.WIDE x 4.3 cycles + 2.743e5 other instructions x 1 cycle, per warp of 32 verifies (ncu instruction
 # counts, profiles/r01_schnorr_verify_ncu_summary.json; per-instruction costs, profiles/r01_pipe_microbench.txt).
-ISSUE_CYCLES_PER_WARP_VERIFY = 1.32e5 * 4.3 + 3.25e5 * 1.0
+ISSUE_CYCLES_PER_WARP_VERIFY = 1.355e5 * 4.3 + 2.743e5 * 1.0
 SCHEDULERS = 148 * 4
 
 
@@ -438,7 +438,7 @@ def run_ours(args, rank, world, local_rank):
                        "parallelism": f"{world} independent shard(s), one process per GPU", "generation_s": round(gen_s, 1)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": peak_src, "kernel": "k_schnorr_verify", "kernel_ms": kern_ms_avg,
-                         "note": "integer-issue bound by construction: 129 algorithmic bytes per verify vs 4.6e5 integer instructions; the binding roofline is integer_issue",
+                         "note": "integer-issue bound by construction: 129 algorithmic bytes per verify vs 4.1e5 integer instructions; the binding roofline is integer_issue",
                          "integer_issue": integer_issue_roofline(n, kern_ms_avg, clocks)},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 128 * n * world, "d2h_bytes_per_step": n * world,
