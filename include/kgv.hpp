@@ -281,6 +281,12 @@ class TransactionValidator {
     c_.check(kgv_validate_txs(c_.get(), utxo_view.get(), &v, pov_daa_score, (uint32_t)flags, &p_, res.data()));
     return res;
   }
+  // validate_mempool_transactions_in_parallel (consensus/src/pipeline/virtual_processor/processor.rs:853-878): same kernels, but every
+  // outcome is returned (Vec<TxResult<()>>); `fee` feeds the host-side feerate check (tx_validation_in_utxo_context.rs:63-73)
+  std::vector<kgv_tx_result> validate_mempool_transactions_in_parallel(UtxoSet& virtual_utxo_view, const TxBatch& b, uint64_t virtual_daa_score,
+                                                                     TxValidationFlags flags = TxValidationFlags::Full) {
+    return validate_transactions_in_parallel(virtual_utxo_view, b, virtual_daa_score, flags);
+  }
   std::pair<std::vector<kgv_tx_result>, MuHash> validate_transactions_with_muhash_in_parallel(UtxoSet& utxo_view, const TxBatch& b, uint64_t pov_daa_score,
                                                                                             TxValidationFlags flags = TxValidationFlags::Full) {
     auto res = validate_transactions_in_parallel(utxo_view, b, pov_daa_score, flags);

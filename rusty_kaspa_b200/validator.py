@@ -150,6 +150,14 @@ class TransactionValidator:
         results["fee"][idx] = fees
         return results
 
+    def validate_mempool_transactions_in_parallel(self, utxo_set, batch, virtual_daa_score, flags=FLAGS_FULL):
+        """consensus/src/pipeline/virtual_processor/processor.rs:853-878: the same UTXO-context validation run for a batch of
+        mempool transactions against the virtual UTXO set; unlike the block path the per-transaction outcome is RETURNED
+        (Vec<TxResult<()>>), not filtered: status / script_err / fail_input say why, `fee` feeds the host-side feerate check
+        (tx_validation_in_utxo_context.rs:63-73, f64, stays on the host).  Partially populated transactions (orphans) show up as
+        MISSING_OUTPOINTS.  Below a few hundred signature checks per call the CPU path is faster."""
+        return self.validate_transactions_in_parallel(utxo_set, batch, virtual_daa_score, flags)
+
     def validate_transactions_with_muhash_in_parallel(self, utxo_set, batch, pov_daa_score, flags=FLAGS_FULL):
         """utxo_validation.rs:282-309: as validate_transactions_in_parallel, plus the combined MuHash::from_transaction of the
         accepted transactions.  Returns (RESULT_DTYPE[n_txs], MuHash)."""
