@@ -9,11 +9,16 @@
  *
  * Parity pinning: hashes, tx-id/tx-hash, sighash, the mainnet Schnorr P2PK and
  * 2-of-4 P2SH multisig KATs and the 224-input simpa fixture are pinned by the
- * reference's own vectors (tests/golden/ *.json, tests/test_oracle_golden.py).
+ * reference's own vectors (tests/golden/ *.json, tests/test_oracle_golden.py);
+ * MuHash by every known answer of crypto/muhash/src/lib.rs (tests/golden/muhash.json,
+ * tests/test_oracle_muhash.py); tx hash + merkle root by the hashMerkleRoot of all 266
+ * headers of the simpa DAG fixture.
  * ECDSA verdicts and the Schnorr edge encodings (r>=p, s>=n, off-curve pk) are
  * NOT covered by any stored vector in the reference: for those "parity
  * unpinned" — they are cross-checked against an independent big-int restatement
- * (oracle/pyref.py) and OpenSSL (`cryptography`) only.
+ * (oracle/pyref.py) and OpenSSL (`cryptography`) only.  Likewise "parity unpinned":
+ * the ERROR cases of the block-body set checks (ok_block_set_checks): the reference's
+ * test blocks for them are Rust literals; the passing case is pinned by the fixture.
  */
 #ifndef OK_ORACLE_H
 #define OK_ORACLE_H
