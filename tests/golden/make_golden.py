@@ -174,13 +174,18 @@ def simpa_fixture():
 
     out_blocks = []
     for b in blocks:
-        out_blocks.append({"hash": b["header"]["hash"], "daa_score": b["header"]["daaScore"], "hash_merkle_root": b["header"]["hashMerkleRoot"],
+        h = b["header"]
+        out_blocks.append({"hash": h["hash"], "daa_score": h["daaScore"], "hash_merkle_root": h["hashMerkleRoot"],
+                           "accepted_id_merkle_root": h["acceptedIdMerkleRoot"], "utxo_commitment": h["utxoCommitment"],
+                           "parents": h["parentsByLevel"][0] if h["parentsByLevel"] else [], "blue_work": h["blueWork"], "blue_score": h["blueScore"],
                            "transactions": [conv_tx(t) for t in b["transactions"]]})
     dump("simpa_goref_1060.json.gz", {"source": rel, "coinbase_maturity": params.get("pre_crescendo_coinbase_maturity", params.get("coinbase_maturity")),
                                    "storage_mass_parameter": params.get("storage_mass_parameter"),
                                    "note": "simpa-generated DAG (simpa/generate-json-tests-data.sh); the reference's json_test replays it and asserts "
                                            "every block ends UTXO-valid, so every signed input here must verify. tx ids are NOT stored: they must be "
-                                           "recomputed (hashing/tx.rs) to resolve the inputs' previous outpoints.",
+                                           "recomputed (hashing/tx.rs) to resolve the inputs' previous outpoints.  Header fields kept: hashMerkleRoot "
+                                           "(calc_hash_merkle_root), utxoCommitment (MuHash of the UTXO set in the block's past), acceptedIdMerkleRoot (KIP-15 "
+                                           "form), level-0 parents and blueWork (selected parent = max (blue_work, hash), processes/ghostdag/ordering.rs).",
                                    "blocks": out_blocks})
 
 

@@ -50,3 +50,32 @@ def apply_sighash_action(tx, entries, action, arg):
         tx["subnetwork_id"] = bytes([6, 6, 6, 4, 2, 0, 1, 3, 3, 7]) + bytes(10)
     else:
         assert action == "NoAction"
+
+
+def simpa_dag_coinbase_only_chain_info():
+    """From the simpa DAG fixture: for every block whose PAST contains only coinbase transactions, the data that determines its
+    header commitments without running GHOSTDAG (selected parent = max (blue_work, hash) among the level-0 parents,
+    consensus/src/processes/ghostdag/ordering.rs:38-42):
+      utxo_commitment(B)          = MuHash of { outputs of coinbase(C) with block_daa_score = daa_score(child of C on B's selected chain),
+                                    is_coinbase = true : C on the selected chain of B, C != B }   (utxo_validation.rs:117-121,189)
+      accepted_id_merkle_root(B)  = merkle_hash(accepted_id_merkle_root(SP(B)), calc_merkle_root([id(coinbase(SP(B)))]))  (KIP-15, :401-410)
+    Returns (blocks_by_hash, eligible hashes in file order, selected_parent function)."""
+    import functools
+    import sys
+    fx = load("simpa_goref_1060.json.gz")
+    by = {}
+    for b in fx["blocks"]:
+        by[b["hash"]] = dict(b, blue_work_int=int(b["blue_work"], 16), txs=[tx_from_json(t) for t in b["transactions"]])
+
+    def sp(h):
+        ps = by[h]["parents"]
+        return max(ps, key=lambda p: (by[p]["blue_work_int"], bytes.fromhex(p))) if ps else None
+
+    sys.setrecursionlimit(10000)
+
+    @functools.lru_cache(None)
+    def past_has_spends(h):
+        return any(len(by[p]["txs"]) > 1 or past_has_spends(p) for p in by[h]["parents"])
+
+    eligible = [b["hash"] for b in fx["blocks"] if not past_has_spends(b["hash"])]
+    return by, eligible, sp

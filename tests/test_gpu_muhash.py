@@ -135,3 +135,41 @@ def test_large_tree_properties(ctx):
     c = MuHash(ctx).update(remove=items)
     a.combine(c)
     assert a.finalize() == MuHash(ctx).finalize()
+
+
+def test_real_header_commitments_of_the_simpa_dag(ctx):
+    """utxoCommitment and acceptedIdMerkleRoot written by the reference into the headers of its simpa DAG fixture, reproduced on the GPU
+    along the longest selected-parent chain whose past holds only coinbase transactions: coinbase outputs go into the GPU UTXO table
+    (kgv_utxo_apply_accepted with the child's daa score), kgv_utxo_muhash + kgv_muhash_finalize give the commitment, kgv_tx_ids +
+    kgv_merkle_roots + one more branch hash the KIP-15 accepted-id root."""
+    from rusty_kaspa_b200 import MuHash, GpuUtxoSet
+    from rusty_kaspa_b200.txbatch import build_batch
+    from golden_util import simpa_dag_coinbase_only_chain_info
+    import pyref
+    by, eligible, sp = simpa_dag_coinbase_only_chain_info()
+    depth = {}
+    for h in eligible:
+        depth[h] = 0 if sp(h) is None else depth[sp(h)] + 1
+    tip = max(eligible, key=lambda h: depth[h])
+    chain = [tip]
+    while sp(chain[-1]) is not None:
+        chain.append(sp(chain[-1]))
+    chain.reverse()
+    assert len(chain) >= 40
+    us = GpuUtxoSet(ctx, capacity_slots=4096)
+    running = MuHash(ctx)
+    checked = 0
+    for parent, child in zip(chain[:-1], chain[1:]):
+        cb = build_batch([by[parent]["txs"][0]])
+        acc = np.ones(1, dtype=np.uint8)
+        # the selected parent's coinbase enters the set from the child's point of view (utxo_validation.rs:117-121)
+        running.combine(MuHash.from_transactions(ctx, cb, acc, by[child]["daa_score"], utxo_set=us))
+        us.add_transactions(cb, acc, by[child]["daa_score"])
+        ids = ctx.tx_ids(cb)
+        inner = ctx.merkle_roots(ids, [0, 1])[0].tobytes()
+        assert pyref.blake2b_keyed(b"MerkleBranchHash", bytes.fromhex(by[parent]["accepted_id_merkle_root"]) + inner).hex() == by[child]["accepted_id_merkle_root"]
+        if checked < 12 or child == tip:  # every finalize is a 3072-bit inversion (~25 ms): sample the chain, always check the tip
+            assert MuHash.of_utxo_set(ctx, us).finalize().hex() == by[child]["utxo_commitment"], child
+            checked += 1
+    assert running.finalize().hex() == by[tip]["utxo_commitment"]
+    us.close()

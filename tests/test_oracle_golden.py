@@ -108,3 +108,22 @@ def test_hash_merkle_roots_of_the_simpa_dag(oracle):
     for n in list(range(0, 20)) + [31, 32, 33, 63, 64, 65, 70]:
         hs = [bytes(rnd.randrange(256) for _ in range(32)) for _ in range(n)]
         assert c_root(hs) == pyref.merkle_root(hs), n
+
+
+def test_blocks_json_reader_matches_the_committed_fixture():
+    """rusty_kaspa_b200.blocks_json reads the reference's own dump format; on the build container (which has /root/reference) its
+    output must equal the committed conversion of the same file (tests/golden/simpa_goref_1060.json.gz)."""
+    import os
+    import pytest
+    from golden_util import load, tx_from_json
+    from rusty_kaspa_b200.blocks_json import load_blocks_json
+    src = "/root/reference/testing/integration/testdata/dags_for_json_tests/goref-1060-tx-265-blocks/blocks.json.gz"
+    if not os.path.exists(src):
+        pytest.skip("reference tree not present (GPU box)")
+    params, blocks = load_blocks_json(src)
+    fx = load("simpa_goref_1060.json.gz")
+    assert len(blocks) == len(fx["blocks"]) == 266
+    for b, g in zip(blocks, fx["blocks"]):
+        assert b["hash"].hex() == g["hash"] and b["daa_score"] == g["daa_score"] and b["hash_merkle_root"].hex() == g["hash_merkle_root"]
+        assert b["transactions"] == [tx_from_json(t) for t in g["transactions"]]
+    assert blocks[0]["utxo_commitment"].hex() == "544eb3142c000f0ad2c76ac41f4222abbababed830eeafee4b6dc56b52d5cac0"  # genesis: EMPTY_MUHASH

@@ -150,3 +150,44 @@ def test_transaction_level(oracle):
         for j, o in enumerate(t["outputs"]):
             p.add_element(pyref.utxo_element_bytes(tid, j, 77, o["value"], False, o["spk_version"], o["script"]))
     assert c_finalize(oracle, m) == p.finalize()
+
+
+def test_real_utxo_commitments_and_accepted_id_roots_of_the_simpa_dag(oracle):
+    """The header fields utxoCommitment and acceptedIdMerkleRoot of the reference's simpa DAG fixture, for the 210 blocks whose past
+    holds only coinbase transactions (no GHOSTDAG needed, see golden_util): written by the reference itself, reproduced by the
+    oracle (coinbase tx id, write_utxo with is_coinbase / block_daa_score, element expansion, product, finalize; merkle_hash)."""
+    import functools
+    from golden_util import simpa_dag_coinbase_only_chain_info
+    by, eligible, sp = simpa_dag_coinbase_only_chain_info()
+    assert len(eligible) >= 200
+
+    @functools.lru_cache(None)
+    def muhash_of(h):
+        """MuHash state (numerator bytes) of block h's past UTXO set, built incrementally along the selected chain"""
+        s = sp(h)
+        m = OkMuHash()
+        if s is None:
+            oracle.ok_muhash_init(ctypes.byref(m))
+            return bytes(m.num)
+        assert oracle.ok_muhash_deserialize(ctypes.byref(m), muhash_of(s)) == 0
+        cb = by[s]["txs"][0]
+        tid = pyref.tx_id(cb)
+        for i, o in enumerate(cb["outputs"]):
+            d = pyref.utxo_element_bytes(tid, i, by[h]["daa_score"], o["value"], True, o["spk_version"], o["script"])
+            oracle.ok_muhash_add_element(ctypes.byref(m), d, len(d))
+        return bytes(m.num)
+
+    n_nonempty = 0
+    for h in eligible:
+        m = OkMuHash()
+        oracle.ok_muhash_deserialize(ctypes.byref(m), muhash_of(h))
+        assert c_finalize(oracle, m).hex() == by[h]["utxo_commitment"], h
+        n_nonempty += by[h]["utxo_commitment"] != "544eb3142c000f0ad2c76ac41f4222abbababed830eeafee4b6dc56b52d5cac0"
+        s = sp(h)
+        if s is not None:
+            root = ctypes.create_string_buffer(32)
+            oracle.ok_merkle_root(pyref.tx_id(by[s]["txs"][0]), ctypes.c_size_t(1), root)
+            out = ctypes.create_string_buffer(32)
+            oracle.ok_blake2b_keyed(b"MerkleBranchHash", bytes.fromhex(by[s]["accepted_id_merkle_root"]) + root.raw, ctypes.c_size_t(64), out)
+            assert out.raw.hex() == by[h]["accepted_id_merkle_root"], h
+    assert n_nonempty >= 190
