@@ -179,7 +179,7 @@ def simpa_fixture():
                            "accepted_id_merkle_root": h["acceptedIdMerkleRoot"], "utxo_commitment": h["utxoCommitment"],
                            "parents": h["parentsByLevel"][0] if h["parentsByLevel"] else [], "blue_work": h["blueWork"], "blue_score": h["blueScore"],
                            "transactions": [conv_tx(t) for t in b["transactions"]]})
-    dump("simpa_goref_1060.json.gz", {"source": rel, "coinbase_maturity": params.get("pre_crescendo_coinbase_maturity", params.get("coinbase_maturity")),
+    dump("simpa_goref_1060.json.gz", {"source": rel, "coinbase_maturity": params.get("blockrate", {}).get("coinbase_maturity", params.get("coinbase_maturity")),
                                    "storage_mass_parameter": params.get("storage_mass_parameter"),
                                    "note": "simpa-generated DAG (simpa/generate-json-tests-data.sh); the reference's json_test replays it and asserts "
                                            "every block ends UTXO-valid, so every signed input here must verify. tx ids are NOT stored: they must be "

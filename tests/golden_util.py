@@ -79,3 +79,32 @@ def simpa_dag_coinbase_only_chain_info():
 
     eligible = [b["hash"] for b in fx["blocks"] if not past_has_spends(b["hash"])]
     return by, eligible, sp
+
+
+def simpa_dag_replay_plan():
+    """The reference's own acceptance order for the simpa DAG fixture, derived from header data only (no GHOSTDAG run):
+    selected parent = max (blue_work, hash) among the level-0 parents; mergeset(B) = past(B) - past(SP) - {SP}; consensus order =
+    SP first, then the rest ascending by (blue_work, hash) (processes/ghostdag/ordering.rs:38-42, utxo_validation.rs:110-160).
+    Returns (by_hash, file_order, sp(h), ordered_mergeset(h))."""
+    fx = load("simpa_goref_1060.json.gz")
+    by, order = {}, []
+    for b in fx["blocks"]:
+        by[b["hash"]] = dict(b, bw=int(b["blue_work"], 16), txs=[tx_from_json(t) for t in b["transactions"]])
+        order.append(b["hash"])
+    key = lambda h: (by[h]["bw"], bytes.fromhex(h))
+    past = {}
+    for h in order:  # the file is in topological order
+        s = set()
+        for p in by[h]["parents"]:
+            s.add(p)
+            s |= past[p]
+        past[h] = s
+
+    def sp(h):
+        return max(by[h]["parents"], key=key) if by[h]["parents"] else None
+
+    def ordered_mergeset(h):
+        s = sp(h)
+        return [] if s is None else [s] + sorted(past[h] - past[s] - {s}, key=key)
+
+    return fx, by, order, sp, ordered_mergeset
