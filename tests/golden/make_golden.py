@@ -3,7 +3,8 @@
 
 Run in the build container (needs /root/reference; the GPU box does not have it):
     python tests/golden/make_golden.py
-Outputs (committed): tests/golden/{hashers,tx_hashing,sighash,check_scripts_kat,muhash}.json, simpa_goref_1060.json.gz, script_tests.json.gz
+Outputs (committed): tests/golden/{hashers,tx_hashing,sighash,check_scripts_kat,muhash}.json, simpa_goref_1060.json.gz,
+simpa_goref_pruning_5000.json.gz, script_tests.json.gz
 
 Everything is parsed out of the reference's Rust test sources / test data at run time — nothing is
 retyped by hand — and each fixture records the file:line range it came from:
@@ -158,8 +159,7 @@ def check_scripts_kat():
 
 
 # ------------------------------------------------------------------------------------ simpa DAG fixture
-def simpa_fixture():
-    rel = "testing/integration/testdata/dags_for_json_tests/goref-1060-tx-265-blocks/blocks.json.gz"
+def _simpa_fixture(rel, out_name, note_extra=""):
     with gzip.open(os.path.join(REF, rel), "rt") as f:
         lines = f.read().splitlines()
     params = json.loads(lines[0])
@@ -179,14 +179,20 @@ def simpa_fixture():
                            "accepted_id_merkle_root": h["acceptedIdMerkleRoot"], "utxo_commitment": h["utxoCommitment"],
                            "parents": h["parentsByLevel"][0] if h["parentsByLevel"] else [], "blue_work": h["blueWork"], "blue_score": h["blueScore"],
                            "transactions": [conv_tx(t) for t in b["transactions"]]})
-    dump("simpa_goref_1060.json.gz", {"source": rel, "coinbase_maturity": params.get("blockrate", {}).get("coinbase_maturity", params.get("coinbase_maturity")),
-                                   "storage_mass_parameter": params.get("storage_mass_parameter"),
-                                   "note": "simpa-generated DAG (simpa/generate-json-tests-data.sh); the reference's json_test replays it and asserts "
-                                           "every block ends UTXO-valid, so every signed input here must verify. tx ids are NOT stored: they must be "
-                                           "recomputed (hashing/tx.rs) to resolve the inputs' previous outpoints.  Header fields kept: hashMerkleRoot "
-                                           "(calc_hash_merkle_root), utxoCommitment (MuHash of the UTXO set in the block's past), acceptedIdMerkleRoot (KIP-15 "
-                                           "form), level-0 parents and blueWork (selected parent = max (blue_work, hash), processes/ghostdag/ordering.rs).",
-                                   "blocks": out_blocks})
+    dump(out_name, {"source": rel, "coinbase_maturity": params.get("blockrate", {}).get("coinbase_maturity", params.get("coinbase_maturity")),
+                    "storage_mass_parameter": params.get("storage_mass_parameter"),
+                    "note": "simpa-generated DAG (simpa/generate-json-tests-data.sh); the reference's json_test replays it and asserts "
+                            "every block ends UTXO-valid, so every signed input here must verify. tx ids are NOT stored: they must be "
+                            "recomputed (hashing/tx.rs) to resolve the inputs' previous outpoints.  Header fields kept: hashMerkleRoot "
+                            "(calc_hash_merkle_root), utxoCommitment (MuHash of the UTXO set in the block's past), acceptedIdMerkleRoot (KIP-15 "
+                            "form), level-0 parents and blueWork (selected parent = max (blue_work, hash), processes/ghostdag/ordering.rs)." + note_extra,
+                    "blocks": out_blocks})
+
+
+def simpa_fixture():
+    _simpa_fixture("testing/integration/testdata/dags_for_json_tests/goref-1060-tx-265-blocks/blocks.json.gz", "simpa_goref_1060.json.gz")
+    _simpa_fixture("testing/integration/testdata/dags_for_json_tests/goref_custom_pruning_depth/blocks.json.gz", "simpa_goref_pruning_5000.json.gz",
+                   "  5 001 blocks, 4 790 signed single-input transactions (json_test `goref_custom_pruning_depth_test`).")
 
 
 # ------------------------------------------------------------------------------------ script engine rows

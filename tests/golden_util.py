@@ -81,23 +81,23 @@ def simpa_dag_coinbase_only_chain_info():
     return by, eligible, sp
 
 
-def simpa_dag_replay_plan():
-    """The reference's own acceptance order for the simpa DAG fixture, derived from header data only (no GHOSTDAG run):
+def simpa_dag_replay_plan(fixture="simpa_goref_1060.json.gz"):
+    """The reference's own acceptance order for a simpa DAG fixture, derived from header data only (no GHOSTDAG run):
     selected parent = max (blue_work, hash) among the level-0 parents; mergeset(B) = past(B) - past(SP) - {SP}; consensus order =
     SP first, then the rest ascending by (blue_work, hash) (processes/ghostdag/ordering.rs:38-42, utxo_validation.rs:110-160).
-    Returns (by_hash, file_order, sp(h), ordered_mergeset(h))."""
-    fx = load("simpa_goref_1060.json.gz")
-    by, order = {}, []
-    for b in fx["blocks"]:
+    Returns (fixture, by_hash, file_order, sp(h), ordered_mergeset(h), virtual_chain)."""
+    fx = load(fixture)
+    by, order, idx = {}, [], {}
+    for n, b in enumerate(fx["blocks"]):
         by[b["hash"]] = dict(b, bw=int(b["blue_work"], 16), txs=[tx_from_json(t) for t in b["transactions"]])
         order.append(b["hash"])
+        idx[b["hash"]] = n
     key = lambda h: (by[h]["bw"], bytes.fromhex(h))
-    past = {}
-    for h in order:  # the file is in topological order
-        s = set()
+    past = {}  # ancestor sets as integer bitsets over the file (topological) order
+    for h in order:
+        s = 0
         for p in by[h]["parents"]:
-            s.add(p)
-            s |= past[p]
+            s |= past[p] | (1 << idx[p])
         past[h] = s
 
     def sp(h):
@@ -105,6 +105,19 @@ def simpa_dag_replay_plan():
 
     def ordered_mergeset(h):
         s = sp(h)
-        return [] if s is None else [s] + sorted(past[h] - past[s] - {s}, key=key)
+        if s is None:
+            return []
+        bits = past[h] & ~past[s] & ~(1 << idx[s])
+        rest = []
+        while bits:
+            low = bits & -bits
+            rest.append(order[low.bit_length() - 1])
+            bits ^= low
+        return [s] + sorted(rest, key=key)
 
-    return fx, by, order, sp, ordered_mergeset
+    tip = max(order, key=key)
+    chain = [tip]
+    while sp(chain[-1]) is not None:
+        chain.append(sp(chain[-1]))
+    chain.reverse()
+    return fx, by, order, sp, ordered_mergeset, chain

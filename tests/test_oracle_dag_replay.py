@@ -21,12 +21,14 @@ class OkMuHash(ctypes.Structure):
     _fields_ = [("num", ctypes.c_uint64 * 48), ("den", ctypes.c_uint64 * 48)]
 
 
-def test_every_header_commitment_of_the_simpa_dag(oracle):
-    fx, by, order, sp, ordered_mergeset = simpa_dag_replay_plan()
+def _replay(oracle, fixture, blocks_of, chain_only):
+    """blocks_of(plan) -> hashes to process in order; chain_only: one evolving state (the virtual chain) instead of one state per block"""
+    fx, by, order, sp, ordered_mergeset, chain = simpa_dag_replay_plan(fixture)
     prm = oracle_tx.params(coinbase_maturity=fx["coinbase_maturity"], storage_mass_parameter=fx["storage_mass_parameter"])
+    todo = chain if chain_only else order
     state, mh = {}, {}
-    accepted_total = spends_seen = 0
-    for h in order:
+    accepted_total = 0
+    for h in todo:
         b, s = by[h], sp(h)
         m = OkMuHash()
         if s is None:
@@ -34,7 +36,8 @@ def test_every_header_commitment_of_the_simpa_dag(oracle):
             st, accepted_ids = {}, None
         else:
             ctypes.memmove(ctypes.byref(m), ctypes.byref(mh[s]), ctypes.sizeof(m))
-            st, pov = dict(state[s]), b["daa_score"]
+            st = state[s] if chain_only else dict(state[s])
+            pov = b["daa_score"]
 
             def add(txid, i, o, coinbase):
                 st[(txid, i)] = {"amount": o["value"], "spk_version": o["spk_version"], "script": o["script"], "block_daa_score": pov, "is_coinbase": coinbase}
@@ -63,8 +66,9 @@ def test_every_header_commitment_of_the_simpa_dag(oracle):
                         add(tid, i, o, False)
                     accepted_ids.append(tid)
                     accepted_total += 1
-                    spends_seen += len(tx["inputs"])
         state[h], mh[h] = st, m
+        if chain_only and s is not None:
+            del state[s], mh[s]
         mm = OkMuHash()
         ctypes.memmove(ctypes.byref(mm), ctypes.byref(m), ctypes.sizeof(m))
         out = ctypes.create_string_buffer(32)
@@ -74,4 +78,16 @@ def test_every_header_commitment_of_the_simpa_dag(oracle):
             root = ctypes.create_string_buffer(32)
             oracle.ok_merkle_root(b"".join(accepted_ids), ctypes.c_size_t(len(accepted_ids)), root)
             assert pyref.blake2b_keyed(b"MerkleBranchHash", bytes.fromhex(by[s]["accepted_id_merkle_root"]) + root.raw).hex() == b["accepted_id_merkle_root"], h
-    assert len(order) == 266 and accepted_total > 500 and spends_seen > 500
+    return len(todo), accepted_total
+
+
+def test_every_header_commitment_of_the_simpa_dag(oracle):
+    """goref-1060-tx-265-blocks: every one of the 266 blocks from its own point of view (one UTXO state per block)"""
+    n, accepted = _replay(oracle, "simpa_goref_1060.json.gz", None, chain_only=False)
+    assert n == 266 and accepted > 500
+
+
+def test_virtual_chain_of_the_5000_block_dag(oracle):
+    """goref_custom_pruning_depth (5 001 blocks, 4 790 signed transactions): the 1 665 blocks of the virtual selected-parent chain"""
+    n, accepted = _replay(oracle, "simpa_goref_pruning_5000.json.gz", None, chain_only=True)
+    assert n > 1500 and accepted > 4500
