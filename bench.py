@@ -275,6 +275,49 @@ def measure_ecdsa(ctx, dev, stream, n, steps):
     return {"what": "kgv_ecdsa_verify, device-resident", "n": n, "verifies_per_s": n / s, "ms_per_call": s * 1e3, "generation_s": round(gen_s, 1)}
 
 
+def measure_utxo_table(ctx, dev, stream, peak_gbs):
+    """K5: the GPU UTXO table on its own: 4 Mi entries in a 16 Mi-slot (2 GiB) table; every timed call looks up a DIFFERENT random
+    1 Mi of them (occupied slots = 512 MiB, four times L2), keys and results device-resident.
+    Algorithmic bytes per lookup: 36 B key + one 128 B slot read + 32 B entry + 1 B flag written."""
+    import torch
+    from rusty_kaspa_b200 import GpuUtxoSet
+    from rusty_kaspa_b200.txbatch import ENTRY_DTYPE
+    n_ent, n = 1 << 22, 1 << 20
+    rng = np.random.default_rng(7)
+    keys = rng.integers(0, 256, size=(n_ent, 36), dtype=np.uint8)
+    ent = np.zeros(n_ent, dtype=ENTRY_DTYPE)
+    ent["amount"] = rng.integers(1, 1 << 40, size=n_ent)
+    ent["script_off"] = (np.arange(n_ent, dtype=np.uint64) * 34 % (1 << 20)).astype(np.uint32)
+    ent["script_len"] = 34
+    arena = rng.integers(0, 256, size=(1 << 20) + 64, dtype=np.uint8)
+    us = GpuUtxoSet(ctx, 4 * n_ent)
+    t0 = time.perf_counter()
+    us.apply_diff(add_keys36=keys, add_entries=ent, add_bytes=arena)
+    ctx.synchronize()
+    ins_s = time.perf_counter() - t0
+    assert us.count() == n_ent
+    reps = 5
+    dks = [torch.from_numpy(keys[rng.choice(n_ent, size=n, replace=False)]).to(dev) for _ in range(reps + 1)]
+    de = torch.empty(n * ENTRY_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+    df = torch.empty(n, dtype=torch.uint8, device=dev)
+    call = lambda dk: ctx._check(ctx._lib.kgv_utxo_lookup(ctx._h, us._h, dk.data_ptr(), n, de.data_ptr(), None, 0, df.data_ptr()))
+    call(dks[reps]); stream.synchronize()
+    assert int(df.sum().item()) == n
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for r in range(reps):
+        call(dks[r])
+    e1.record(stream)
+    stream.synchronize()
+    s = e0.elapsed_time(e1) * 1e-3 / reps
+    us.close()
+    gbs = n * (36 + 128 + 32 + 1) / s * 1e-9
+    return {"what": "k_utxo_lookup, 1 Mi random hits per call out of 4 Mi entries in a 2 GiB table (device-resident keys/results, new keys every call)",
+            "lookups_per_s": n / s, "ms_per_call": s * 1e3, "insert_4Mi_entries_host_arrays_ms": ins_s * 1e3,
+            "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak_gbs, "unit": "GB/s", "frac": gbs / peak_gbs if peak_gbs else None,
+                         "bytes_per_lookup": 197}}
+
+
 def measure_small_batches(ctx):
     """Mempool-shaped use: latency of ONE kgv_validate_txs call on small host-resident batches
     (upload + populate + context rules + scripts + verdict download), median of 20 calls."""
@@ -421,13 +464,14 @@ def run_ours(args, rank, world, local_rank):
         cpu = {"value": sample / dt, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": f"first {sample} triples of the same batch, C restatement of the reference path (oracle/), {threads} pthreads; verdicts identical to the GPU's"}
 
-    txv = txv4 = ecd = small = None
+    txv = txv4 = ecd = small = utx = None
     if world == 1 and args.tx_window > 0:
         with torch.cuda.stream(stream):
             txv = measure_tx_validation(ctx, dev, args.tx_window, max(2, min(args.steps, 5)))
             txv4 = measure_tx_validation(ctx, dev, args.tx_window, max(2, min(args.steps, 5)), mix=(0.5, 0.0, 0.25, 0.25), label="config 4 shape")
             ecd = measure_ecdsa(ctx, dev, stream, min(n, 1 << 19), 3)
             small = measure_small_batches(ctx)
+            utx = measure_utxo_table(ctx, dev, stream, peak)
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -443,7 +487,7 @@ def run_ours(args, rank, world, local_rank):
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 128 * n * world, "d2h_bytes_per_step": n * world,
                     "steps": e2e_steps, "how": "kgv_schnorr_verify through the C ABI with pinned host buffers: H2D + kernel + D2H + sync inside the timed region (host clock)"},
-            "tx_validation": txv, "tx_validation_ecdsa_multisig": txv4, "ecdsa": ecd, "small_batches": small, "gpu_launches": int(launches), "clocks": clocks}
+            "tx_validation": txv, "tx_validation_ecdsa_multisig": txv4, "ecdsa": ecd, "small_batches": small, "utxo_table": utx, "gpu_launches": int(launches), "clocks": clocks}
     emit_json_line(line)
 
 
