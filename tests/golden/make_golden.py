@@ -16,6 +16,7 @@ retyped by hand — and each fixture records the file:line range it came from:
   testing/integration/testdata/dags_for_json_tests/goref-1060-tx-265-blocks/blocks.json.gz
                                                            simpa-generated DAG: 224 signed inputs, all valid
   crypto/muhash/src/lib.rs:17-21,189-238,290-327,430-444   MuHash known answers (empty, 3 vectors, pre-computed, serialize, parse)
+  consensus/core/src/utxo/utxo_diff.rs:270-568             UtxoDiff algebra rule table (diff_from / with_diff)
 """
 import gzip
 import json
@@ -335,6 +336,37 @@ def muhash():
                          "parse_fail": {"overflow": "9b28ef" + "ff" * 381, "ok": "0028ef" + "ff" * 381, "all_ff_overflows": True}})
 
 
+# ------------------------------------------------------------------------------------ utxo diff algebra
+def utxo_diff_rules():
+    """consensus/core/src/utxo/utxo_diff.rs:270-568 test_utxo_diff_rules: the table of (this, other) -> diff_from / with_diff results.
+    One outpoint (0^32, 0), two entries: entry1 = (amount 10, daa 0, coinbase), entry2 = (amount 20, daa 1, coinbase)."""
+    src = read("consensus/core/src/utxo/utxo_diff.rs")
+    body = src[src.index("let tests = ["):src.index("// Run the tests")]
+
+    def diff(txt):
+        d = {"add": [], "remove": []}
+        for kind, ent in re.findall(r"insert_(add|remove)_point\(outpoint0, utxo_entry(\d)\.clone\(\)\)", txt):
+            d[kind].append(int(ent))
+        return d
+
+    def result(txt):
+        txt = txt.strip()
+        if txt.startswith("Ok("):
+            return {"ok": diff(txt)}
+        m = re.match(r"Err\(UtxoAlgebraError::(\w+)\(", txt)
+        return {"err": m.group(1)}
+
+    tests = []
+    for m in re.finditer(r'Test \{\s*name: "(.*?)",\s*this: (.*?),\s*other: (.*?),\s*expected_diff_from_result: (.*?),\s*expected_with_diff_result: (.*?),\s*\},', body, re.S):
+        tests.append({"name": m.group(1), "this": diff(m.group(2)), "other": diff(m.group(3)), "diff_from": result(m.group(4)), "with_diff": result(m.group(5))})
+    assert len(tests) == len(re.findall(r"Test \{", body)) and len(tests) >= 20, len(tests)
+    dump("utxo_diff_rules.json", {"source": "consensus/core/src/utxo/utxo_diff.rs:270-568 (test_utxo_diff_rules)",
+                                  "entries": {"1": {"amount": 10, "block_daa_score": 0, "is_coinbase": True}, "2": {"amount": 20, "block_daa_score": 1, "is_coinbase": True}},
+                                  "note": "errors compare by variant (and outpoint) only, utxo_error.rs:29-43; after every Ok result the reference also checks the "
+                                          "round trip this.with_diff(diff_from) == other and this.diff_from(with_diff) == other",
+                                  "tests": tests})
+
+
 if __name__ == "__main__":
     if not os.path.isdir(REF):
         sys.exit("needs /root/reference (run in the build container)")
@@ -345,3 +377,4 @@ if __name__ == "__main__":
     simpa_fixture()
     script_tests()
     muhash()
+    utxo_diff_rules()

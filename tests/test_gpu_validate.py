@@ -135,3 +135,38 @@ def test_malformed_host_batches_are_rejected_not_executed():
             with pytest.raises(KgvError):
                 ctx.tx_ids(b)
     ctx.close()
+
+
+@pytest.mark.gpu
+def test_host_utxo_diff_applied_to_the_gpu_table():
+    """a UtxoDiff composed on the host (utxo_diff.py: add_transaction + with_diff over several blocks) and written to the GPU table in one
+    write_diff_batch gives the same set as applying the blocks one by one on the GPU (count + MuHash commitment)."""
+    import rusty_kaspa_b200 as rk
+    from rusty_kaspa_b200 import simgen, MuHash
+    from rusty_kaspa_b200.txbatch import build_batch
+    from rusty_kaspa_b200.utxo_diff import UtxoDiff
+    ctx = rk.GpuContext(0)
+    dag = simgen.SimDag(seed=5, n_keys=16, n_nonces=32, coinbase_maturity=1, coinbase_outputs=4)
+    a, b = rk.GpuUtxoSet(ctx, 4096), rk.GpuUtxoSet(ctx, 4096)
+    cur, total = {}, UtxoDiff()
+    for _ in range(10):
+        txs, pov = dag.make_block(8)
+        d, acc = UtxoDiff(), []
+        for tx in txs:
+            ents = [cur.get((i["txid"], i["index"])) for i in tx["inputs"]]
+            ok = all(e is not None for e in ents)
+            acc.append(1 if ok else 0)
+            if not ok:
+                continue
+            tid, cb = simgen.tx_id(tx), tx["subnetwork_id"][0] == 1
+            d.add_transaction(tx, ents, tid, pov, is_coinbase=cb)
+            for i in tx["inputs"]:
+                del cur[(i["txid"], i["index"])]
+            for k, o in enumerate(tx["outputs"]):
+                cur[(tid, k)] = {"amount": o["value"], "spk_version": o["spk_version"], "script": o["script"], "block_daa_score": pov, "is_coinbase": cb}
+        a.add_transactions(build_batch(txs), np.array(acc, dtype=np.uint8), pov)   # block by block on the GPU
+        total.with_diff_in_place(d)
+    total.apply_to(b)                                                               # one composed diff
+    assert a.count() == b.count() == len(cur) > 20
+    assert MuHash.of_utxo_set(ctx, a).finalize() == MuHash.of_utxo_set(ctx, b).finalize()
+    a.close(); b.close(); ctx.close()
