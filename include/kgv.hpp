@@ -10,6 +10,7 @@
 //   kgv::UtxoSet (get / write_diff / add_transactions)                      consensus/src/model/stores/utxo_set.rs:107-112, consensus/core/src/utxo/utxo_diff.rs:233-247
 //   kgv::MuHash (add_element / remove_element / combine / finalize / serialize)  crypto/muhash/src/lib.rs:59-121
 //   kgv::SigVerifier (check_schnorr_signatures / check_ecdsa_signatures)    crypto/txscript/src/lib.rs:574-643, batched
+//   kgv::UtxoDiff (with_diff / diff_from / add_transaction)                 consensus/core/src/utxo/utxo_diff.rs:15-262
 //   kgv::calc_hash_merkle_roots, kgv::check_block_bodies                    consensus/core/src/merkle.rs:5-7, body_validation_in_isolation.rs:95-131
 // (* batched: one verdict per transaction.)  Verdicts are data (status codes of kgv.h); only transport failures throw.
 // There is no CPU execution path behind any of this: without libkgv.so + a CUDA device, Context's constructor throws.
@@ -17,6 +18,7 @@
 #include <array>
 #include <cstdint>
 #include <cstring>
+#include <map>
 #include <stdexcept>
 #include <string>
 #include <utility>
@@ -131,6 +133,120 @@ class TxBatch {
   std::vector<kgv_utxo_entry> entries_;
   std::vector<uint8_t> bytes_{0, 0, 0, 0, 0, 0, 0, 0};
   bool populated_ = false;
+};
+
+// ---- UTXO diff algebra (consensus/core/src/utxo/utxo_diff.rs:15-262, utxo_collection.rs): host bookkeeping, one diff per chain
+// block; the GPU table consumes diffs through UtxoSet::write_diff.  Semantics pinned by the reference's rule table
+// (tests/golden/utxo_diff_rules.json via tests/cpp/utxo_diff_test.cpp).
+struct OutpointLess {
+  bool operator()(const TransactionOutpoint& a, const TransactionOutpoint& b) const {
+    return a.transaction_id != b.transaction_id ? a.transaction_id < b.transaction_id : a.index < b.index;
+  }
+};
+inline bool operator==(const ScriptPublicKey& a, const ScriptPublicKey& b) { return a.version == b.version && a.script == b.script; }
+inline bool operator==(const UtxoEntry& a, const UtxoEntry& b) {
+  return a.amount == b.amount && a.script_public_key == b.script_public_key && a.block_daa_score == b.block_daa_score && a.is_coinbase == b.is_coinbase;
+}
+inline bool operator==(const TransactionOutpoint& a, const TransactionOutpoint& b) { return a.transaction_id == b.transaction_id && a.index == b.index; }
+using UtxoCollection = std::map<TransactionOutpoint, UtxoEntry, OutpointLess>;
+
+class UtxoAlgebraError : public std::runtime_error {
+ public:
+  enum Kind { DuplicateRemovePoint, DuplicateAddPoint, DoubleRemoveCall, DoubleAddCall, DiffIntersectionPoint, General };
+  UtxoAlgebraError(Kind k, const char* name) : std::runtime_error(name), kind(k) {}
+  Kind kind;
+};
+
+class UtxoDiff {
+ public:
+  UtxoCollection add, remove;
+  bool operator==(const UtxoDiff& o) const { return add == o.add && remove == o.remove; }
+  UtxoDiff to_reversed() const { UtxoDiff r; r.add = remove; r.remove = add; return r; }
+
+  // self, then other, applied to one base set (utxo_diff.rs:76-116)
+  UtxoDiff with_diff(const UtxoDiff& other) const { UtxoDiff c = *this; c.with_diff_in_place(other); return c; }
+  void with_diff_in_place(const UtxoDiff& other) {
+    for (const auto& kv : other.remove)
+      if (remove.count(kv.first) && !has(add, kv.first, kv.second.block_daa_score)) throw UtxoAlgebraError(UtxoAlgebraError::DuplicateRemovePoint, "DuplicateRemovePoint");
+    for (const auto& kv : other.add) {
+      auto it = add.find(kv.first);
+      if (it != add.end() && !has(other.remove, kv.first, it->second.block_daa_score)) throw UtxoAlgebraError(UtxoAlgebraError::DuplicateAddPoint, "DuplicateAddPoint");
+    }
+    std::vector<TransactionOutpoint> cancelled;
+    for (const auto& kv : other.remove) {
+      if (has(add, kv.first, kv.second.block_daa_score)) cancelled.push_back(kv.first);
+      else remove[kv.first] = kv.second;
+    }
+    for (const auto& o : cancelled) add.erase(o);
+    cancelled.clear();
+    for (const auto& kv : other.add) {
+      if (has(remove, kv.first, kv.second.block_daa_score)) cancelled.push_back(kv.first);
+      else add[kv.first] = kv.second;
+    }
+    for (const auto& o : cancelled) remove.erase(o);
+  }
+
+  // the diff that turns self into other, both taken from one base set (utxo_diff.rs:118-225)
+  UtxoDiff diff_from(const UtxoDiff& other) const {
+    for (const auto& kv : remove) {
+      auto it = other.add.find(kv.first);
+      if (it == other.add.end()) continue;
+      const uint64_t t = kv.second.block_daa_score, x = it->second.block_daa_score;
+      if (!(x != t && (has(add, kv.first, x) || has(other.remove, kv.first, t)))) throw UtxoAlgebraError(UtxoAlgebraError::DiffIntersectionPoint, "DiffIntersectionPoint");
+    }
+    for (const auto& kv : add) {
+      auto it = other.remove.find(kv.first);
+      if (it == other.remove.end()) continue;
+      const uint64_t t = kv.second.block_daa_score, x = it->second.block_daa_score;
+      if (!(x != t && (has(remove, kv.first, x) || has(other.add, kv.first, t)))) throw UtxoAlgebraError(UtxoAlgebraError::DiffIntersectionPoint, "DiffIntersectionPoint");
+    }
+    for (const auto& kv : remove) {
+      auto it = other.remove.find(kv.first);
+      if (it != other.remove.end() && it->second.block_daa_score != kv.second.block_daa_score)
+        throw UtxoAlgebraError(UtxoAlgebraError::DiffIntersectionPoint, "DiffIntersectionPoint");
+    }
+    UtxoDiff res;
+    bool both_in_my_remove = false, both_in_other_remove = false;
+    for (const auto& kv : add) {
+      if (has(other.add, kv.first, kv.second.block_daa_score)) {
+        both_in_my_remove = both_in_my_remove || remove.count(kv.first);
+        both_in_other_remove = both_in_other_remove || other.remove.count(kv.first);
+      } else {
+        res.remove[kv.first] = kv.second;
+      }
+    }
+    if (both_in_my_remove != both_in_other_remove) throw UtxoAlgebraError(UtxoAlgebraError::General, "General");
+    for (const auto& kv : other.remove) if (!has(remove, kv.first, kv.second.block_daa_score)) res.remove[kv.first] = kv.second;
+    for (const auto& kv : remove) if (!has(other.remove, kv.first, kv.second.block_daa_score)) res.add[kv.first] = kv.second;
+    for (const auto& kv : other.add) if (!has(add, kv.first, kv.second.block_daa_score)) res.add[kv.first] = kv.second;
+    return res;
+  }
+
+  // utxo_diff.rs:227-261; entries: the populated entry of every input
+  void add_transaction(const Transaction& tx, const std::vector<UtxoEntry>& entries, const Hash& tx_id, uint64_t block_daa_score) {
+    for (size_t i = 0; i < tx.inputs.size(); i++) {
+      const TransactionOutpoint& o = tx.inputs[i].previous_outpoint;
+      if (has(add, o, entries[i].block_daa_score)) add.erase(o);
+      else if (!remove.count(o)) remove[o] = entries[i];
+      else throw UtxoAlgebraError(UtxoAlgebraError::DoubleRemoveCall, "DoubleRemoveCall");
+    }
+    const bool cb = tx.subnetwork_id == subnetwork_id_coinbase();
+    for (size_t k = 0; k < tx.outputs.size(); k++) {
+      TransactionOutpoint o;
+      o.transaction_id = tx_id; o.index = (uint32_t)k;
+      UtxoEntry e;
+      e.amount = tx.outputs[k].value; e.script_public_key = tx.outputs[k].script_public_key; e.block_daa_score = block_daa_score; e.is_coinbase = cb;
+      if (has(remove, o, block_daa_score)) remove.erase(o);
+      else if (!add.count(o)) add[o] = e;
+      else throw UtxoAlgebraError(UtxoAlgebraError::DoubleAddCall, "DoubleAddCall");
+    }
+  }
+
+ private:
+  static bool has(const UtxoCollection& c, const TransactionOutpoint& o, uint64_t daa) {  // contains_with_daa_score
+    auto it = c.find(o);
+    return it != c.end() && it->second.block_daa_score == daa;
+  }
 };
 
 // ---- context ----

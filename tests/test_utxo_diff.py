@@ -78,10 +78,29 @@ def test_add_transaction_and_composition_against_a_set_model():
     assert total.add == {o: e for o, e in cur.items() if o not in base} and total.remove == {}
     assert len(total.add) > 20
     # algebra errors of add_transaction
-    tx = {"inputs": [{"txid": b"\\x01" * 32, "index": 0}], "outputs": []}
+    tx = {"inputs": [{"txid": b"\x01" * 32, "index": 0}], "outputs": []}
     e = {"amount": 1, "spk_version": 0, "script": b"", "block_daa_score": 5, "is_coinbase": False}
     d = UtxoDiff()
-    d.add_transaction(tx, [e], b"\\x02" * 32, 9)
+    d.add_transaction(tx, [e], b"\x02" * 32, 9)
     with pytest.raises(UtxoAlgebraError) as ei:
-        d.add_transaction(tx, [e], b"\\x03" * 32, 9)
+        d.add_transaction(tx, [e], b"\x03" * 32, 9)
     assert ei.value.kind == "DoubleRemoveCall"
+
+
+def test_cpp_mirror_runs_the_reference_rule_table(tmp_path):
+    """kgv::UtxoDiff (include/kgv.hpp) through tests/cpp/utxo_diff_test.cpp on the same table (pure host code, no GPU)"""
+    import subprocess
+    root = os.path.dirname(HERE)
+    src, exe = os.path.join(HERE, "cpp", "utxo_diff_test.cpp"), os.path.join(HERE, "cpp", "utxo_diff_test")
+    deps = [src, os.path.join(root, "include", "kgv.hpp")]
+    if not os.path.exists(exe) or any(os.path.getmtime(d) > os.path.getmtime(exe) for d in deps):
+        subprocess.run(["g++", "-O2", "-std=c++17", "-o", exe, src], check=True)
+    g = load("utxo_diff_rules.json")
+    f = lambda ks: "".join(str(k) for k in ks) or "-"
+    inp = "\n".join("%s %s %s %s" % (f(t["this"]["add"]), f(t["this"]["remove"]), f(t["other"]["add"]), f(t["other"]["remove"])) for t in g["tests"]) + "\n"
+    out = subprocess.run([exe], input=inp, capture_output=True, text=True, check=True).stdout.strip().splitlines()
+    assert len(out) == len(g["tests"])
+    want = lambda r: ("ok %s %s" % (f(r["ok"]["add"]), f(r["ok"]["remove"]))) if "ok" in r else "err " + r["err"]
+    for t, line in zip(g["tests"], out):
+        a, b, trips = [x.strip() for x in line.split("|")]
+        assert a == want(t["diff_from"]) and b == want(t["with_diff"]) and trips == "1", (t["name"], line)
