@@ -261,6 +261,128 @@ def measure_tx_validation(ctx, dev, n_txs, steps, mix=(1.0, 0.0, 0.0, 0.0), labe
             "generation_s": round(gen_s, 1)}
 
 
+def measure_dag_replay(ctx, dev, n_blocks, tpb, window, cpu_budget_s, mix=(1.0, 0.0, 0.0, 0.0), label="config 3", seed=0x6B61737061, frac_invalid=0.01):
+    """BASELINE.json's second headline, txs-validated/s ON A DAG (configs[2]): a generated simpa-shaped chain of n_blocks blocks
+    (<= tpb transactions each, 50 % 1-in/2-out + 50 % 2-in/2-out, coinbase maturity 200 as in simpa/src/main.rs:204, ~1 % deliberately
+    invalid transactions) replayed IN ORDER against the GPU UTXO table (2^24 slots) by kgv_replay_window, `window` blocks per call:
+    what calculate_utxo_state does block by block (utxo_validation.rs:110-173) and simpa times (simpa/src/main.rs:454-460).
+    Reported: device-resident batches (CUDA events around all calls), end to end from page-locked host arrays (H2D of every window,
+    D2H of every verdict inside the wall-clock region), and the CPU path (oracle/ok_state_replay: the restated rayon path with a
+    persistent thread pool) on a time-bounded prefix of the SAME blocks, whose verdicts must equal the GPU's."""
+    import ctypes as C
+    import torch
+    from rusty_kaspa_b200 import GpuUtxoSet, Params, simgen
+    from rusty_kaspa_b200.replay import REPLAY_BLOCK_DTYPE, ReplayStats
+    from rusty_kaspa_b200.validator import RESULT_DTYPE
+    from rusty_kaspa_b200.verifier import _KgvTxBatch
+    t0 = time.perf_counter()
+    gen = simgen.FastDag(seed=seed, n_keys=1024, n_nonces=4096, mix=mix, frac_two_inputs=0.5, frac_invalid=frac_invalid, coinbase_outputs=16)
+    wins = []
+    done = 0
+    while done < n_blocks:
+        k = min(window, n_blocks - done)
+        gen.generate(k, tpb)
+        b, first, pov = gen.take()
+        arr = np.zeros(k, dtype=REPLAY_BLOCK_DTYPE)
+        arr["first_tx"], arr["n_txs"], arr["pov_daa_score"], arr["flags"] = first[:-1], np.diff(first), pov, 1
+        wins.append((b, arr, first, pov))
+        done += k
+    cnt = gen.counts()
+    n_txs = sum(len(w[0].txs) for w in wins)
+    n_user = n_txs - n_blocks
+    n_sigs_gen = cnt["n_signatures"]
+    gen_s = time.perf_counter() - t0
+    prm = Params(coinbase_maturity=gen.maturity, storage_mass_parameter=gen.C)
+    lib, h = ctx._lib, ctx._h
+    stream = torch.cuda.current_stream(dev)
+
+    def c_batch(ptrs, b):
+        return _KgvTxBatch(ptrs[0], len(b.txs), ptrs[1], len(b.inputs), ptrs[2], len(b.outputs), None, ptrs[3], len(b.arena))
+
+    # ---- device-resident windows
+    us = GpuUtxoSet(ctx, 1 << 24)
+    dwins = []
+    for b, arr, _, _ in wins:
+        ts = [torch.from_numpy(a.view(np.uint8).reshape(-1)).to(dev) for a in (b.txs, b.inputs, b.outputs, b.arena)]
+        dres = torch.empty(len(b.txs) * 16, dtype=torch.uint8, device=dev)
+        dwins.append((ts, dres, c_batch([t.data_ptr() for t in ts], b)))
+    stream.synchronize()
+    l0 = ctx.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for (b, arr, _, _), (ts, dres, cb) in zip(wins, dwins):
+        ctx._check(lib.kgv_replay_window(h, us._h, C.byref(cb), arr.ctypes.data, len(arr), C.byref(prm), dres.data_ptr(), None, None))
+    e1.record(stream)
+    stream.synchronize()
+    dev_s = e0.elapsed_time(e1) * 1e-3
+    launches = ctx.launch_count - l0
+    dev_status = [np.frombuffer(d[1].cpu().numpy().tobytes(), dtype=RESULT_DTYPE)["status"].copy() for d in dwins]
+    n_table = us.count()
+    assert n_table == cnt["n_utxos"], (n_table, cnt["n_utxos"])
+    us.close()
+    del dwins
+    # ---- end to end from page-locked host arrays
+    cudart = torch.cuda.cudart()
+    pinned = []
+    for b, arr, _, _ in wins:
+        for a in (b.txs, b.inputs, b.outputs, b.arena):
+            if a.nbytes and int(cudart.cudaHostRegister(a.ctypes.data, a.nbytes, 0)) == 0:
+                pinned.append(a)
+    us = GpuUtxoSet(ctx, 1 << 24)
+    hres = [np.zeros(len(w[0].txs), dtype=RESULT_DTYPE) for w in wins]
+    for r in hres:
+        if int(cudart.cudaHostRegister(r.ctypes.data, r.nbytes, 0)) == 0:
+            pinned.append(r)
+    st = ReplayStats()
+    n_acc = n_sig = 0
+    h2d = 0
+    t0 = time.perf_counter()
+    for (b, arr, _, _), r in zip(wins, hres):
+        cb = c_batch([a.ctypes.data for a in (b.txs, b.inputs, b.outputs, b.arena)], b)
+        ctx._check(lib.kgv_replay_window(h, us._h, C.byref(cb), arr.ctypes.data, len(arr), C.byref(prm), r.ctypes.data, None, C.byref(st)))
+        n_acc += int(st.n_accepted); n_sig += int(st.n_sig_checks)
+        h2d += b.txs.nbytes + b.inputs.nbytes + b.outputs.nbytes + b.arena.nbytes
+    e2e_s = time.perf_counter() - t0
+    for a in pinned:
+        cudart.cudaHostUnregister(a.ctypes.data)
+    assert n_acc == n_user - cnt["n_invalid"], (n_acc, n_user, cnt["n_invalid"])
+    assert us.count() == cnt["n_utxos"]
+    for a, r in zip(dev_status, hres):
+        assert (a == r["status"]).all()
+    us.close()
+    # ---- the CPU path beside it: same blocks, time-bounded prefix, verdicts must be identical
+    cpu = None
+    if cpu_budget_s > 0:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_tx
+        ora = load_oracle()
+        threads = host_threads()
+        ost = oracle_tx.State(ora)
+        op = oracle_tx.params(coinbase_maturity=gen.maturity, storage_mass_parameter=gen.C)
+        c_txs = c_blocks = 0
+        c_s = 0.0
+        for (b, arr, first, pov), r in zip(wins, hres):
+            t0 = time.perf_counter()
+            cres, _ = oracle_tx.state_replay(ost, b, first, pov, op, threads=threads)
+            c_s += time.perf_counter() - t0
+            assert (cres["status"] == r["status"]).all() and (cres["script_err"] == r["script_err"]).all(), "CPU path and GPU replay disagree"
+            c_txs += len(b.txs) - len(pov); c_blocks += len(pov)
+            if c_s > cpu_budget_s:
+                break
+        ost.close()
+        cpu = {"value": c_txs / c_s, "unit": "txs/s", "cores": threads, "kind": "port",
+               "sample": f"first {c_blocks} blocks ({c_txs} non-coinbase txs) of the same chain, oracle/ok_state_replay (validate in parallel on a persistent pool of {threads} "
+                         f"pthreads, accept, commit, block after block); verdicts identical to the GPU's", "seconds": round(c_s, 2)}
+    gen.close()
+    return {"workload": f"{label}: generated chain of {n_blocks} blocks, <= {tpb} txs/block (50% 1-in/2-out, 50% 2-in/2-out), spent-output mix (P2PK Schnorr, P2PK ECDSA, "
+                        f"P2SH 2-of-3 Schnorr, P2SH 2-of-3 ECDSA) = {tuple(mix)}, ~{frac_invalid:.0%} invalid, replayed in order against a 2^24-slot GPU UTXO table, "
+                        f"kgv_replay_window over {window} blocks per call",
+            "n_blocks": n_blocks, "n_txs": n_user, "n_sig_checks": n_sig, "n_accepted": n_acc, "window_blocks": window,
+            "txs_per_s": n_user / dev_s, "blocks_per_s": n_blocks / dev_s, "sig_checks_per_s": n_sig / dev_s, "ms_total": dev_s * 1e3, "gpu_launches": int(launches),
+            "e2e_txs_per_s": n_user / e2e_s, "e2e_sig_checks_per_s": n_sig / e2e_s, "e2e_h2d_bytes": int(h2d), "e2e_d2h_bytes": int(16 * n_txs),
+            "cpu_baseline": cpu, "generation_s": round(gen_s, 1), "generator_signatures": n_sigs_gen}
+
+
 def measure_ecdsa(ctx, dev, stream, n, steps):
     """Secondary: kgv_ecdsa_verify (33-byte compressed keys, low-S rule, tri-state verdicts), device-resident triples."""
     import torch
@@ -474,7 +596,10 @@ def run_ours(args, rank, world, local_rank):
         cpu = {"value": sample / dt, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": f"first {sample} triples of the same batch, C restatement of the reference path (oracle/), {threads} pthreads; verdicts identical to the GPU's"}
 
-    txv = txv4 = ecd = small = utx = None
+    txv = txv4 = ecd = small = utx = rep = None
+    if world == 1 and args.replay_blocks > 0:
+        with torch.cuda.stream(stream):
+            rep = measure_dag_replay(ctx, dev, args.replay_blocks, 150, args.replay_window, 0 if args.no_cpu_baseline else 12.0)
     if world == 1 and args.tx_window > 0:
         with torch.cuda.stream(stream):
             txv = measure_tx_validation(ctx, dev, args.tx_window, max(2, min(args.steps, 5)))
@@ -497,7 +622,7 @@ def run_ours(args, rank, world, local_rank):
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 128 * n * world, "d2h_bytes_per_step": n * world,
                     "steps": e2e_steps, "how": "kgv_schnorr_verify through the C ABI with pinned host buffers: H2D + kernel + D2H + sync inside the timed region (host clock)"},
-            "tx_validation": txv, "tx_validation_ecdsa_multisig": txv4, "ecdsa": ecd, "small_batches": small, "utxo_table": utx, "gpu_launches": int(launches), "clocks": clocks}
+            "dag_replay": rep, "tx_validation": txv, "tx_validation_ecdsa_multisig": txv4, "ecdsa": ecd, "small_batches": small, "utxo_table": utx, "gpu_launches": int(launches), "clocks": clocks}
     emit_json_line(line)
 
 
@@ -531,6 +656,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=N_DEFAULT, help="triples per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--replay-blocks", type=int, default=10000, help="blocks of the DAG-replay leg (BASELINE configs[2]: 10k blocks; 0 = skip)")
+    ap.add_argument("--replay-window", type=int, default=256, help="blocks per kgv_replay_window call")
     ap.add_argument("--tx-window", type=int, default=32768, help="transactions in the secondary txs-validated/s measurement (0 = skip)")
     args = ap.parse_args()
     _quiet_stdout()

@@ -230,13 +230,49 @@ int kgv_utxo_count(kgv_ctx* ctx, kgv_utxo_table* t, uint64_t* count);
 int kgv_utxo_digest(kgv_ctx* ctx, kgv_utxo_table* t, uint8_t out32[32]);
 
 /* validate_transactions_in_parallel (utxo_validation.rs:262-278) against the table: populate every input
- * by table lookup (:319-327), then as kgv_validate_populated.  batch->entries is ignored. */
+ * by table lookup (:319-327), then as kgv_validate_populated.  batch->entries is ignored.
+ * Unlike kgv_validate_populated this call never reports KGV_TX_NEEDS_HOST_VM: transactions with non-standard scripts are
+ * decided inside the call by the host script engine on the entries the table returned (the reference accepts ANY
+ * transaction whose scripts execute successfully, utxo_validation.rs:282-309). */
 int kgv_validate_txs(kgv_ctx* ctx, kgv_utxo_table* t, const kgv_tx_batch* batch, uint64_t pov_daa_score, uint32_t flags, const kgv_params* params,
                      kgv_tx_result* results);
 /* UtxoDiff::add_transaction (utxo_diff.rs:233-247) applied directly to the table for every tx with
  * accept[i] != 0: spent outpoints are erased, outputs inserted with block_daa_score = pov_daa_score and
  * is_coinbase of the tx (tx ids are computed on the device). */
 int kgv_utxo_apply_accepted(kgv_ctx* ctx, kgv_utxo_table* t, const kgv_tx_batch* batch, const uint8_t* accept, uint64_t pov_daa_score);
+
+/* ------------------------------------------------------------------------------------------------
+ * DAG replay: calculate_utxo_state / verify_expected_utxo_state (utxo_validation.rs:110-173,182-228) for a WINDOW of
+ * blocks as one device-resident call; the loop simpa times (simpa/src/main.rs:454-460).
+ *
+ * The batch holds the transactions of all blocks of the window, block after block; blocks[] (a HOST array) tiles it.
+ * Transaction 0 of every block is its coinbase and is skipped by position (utxo_validation.rs:273).  Semantics are those
+ * of processing the blocks one by one, in order, against the table:
+ *     validate_transactions_in_parallel(block txs, table, pov_daa_score, Full | SkipScriptChecks)
+ *     UtxoDiff::add_transaction for every accepted transaction (and for the coinbase when ACCEPT_COINBASE is set)
+ * but every signature of the window is verified in one batch up front (signatures are context free given the spent
+ * output) and the in-order pass is a single persistent kernel.
+ * All merged blocks of one chain block carry that chain block's pov_daa_score (:124-151).
+ * ------------------------------------------------------------------------------------------------ */
+#define KGV_REPLAY_ACCEPT_COINBASE 1u /* the block is the selected parent of its chain block: its coinbase is accepted (:116-121) */
+#define KGV_REPLAY_SKIP_SCRIPTS 2u    /* TxValidationFlags::SkipScriptChecks for this block (selected parent, :138-140) */
+#define KGV_REPLAY_VERIFY_ONLY 4u     /* validate against the current view, apply nothing (verify_expected_utxo_state, :219-225) */
+typedef struct {
+  uint32_t first_tx, n_txs; /* range of batch->txs; tx first_tx is the block's coinbase */
+  uint64_t pov_daa_score;
+  uint32_t flags;           /* KGV_REPLAY_* */
+  uint32_t pad_;
+} kgv_replay_block; /* 24 bytes */
+typedef struct {
+  uint64_t n_accepted;   /* accepted non-coinbase transactions */
+  uint64_t n_sig_checks; /* candidate (signature, key) pairs verified in the pre-check */
+  uint64_t n_host_vm;    /* transactions decided by the host script engine */
+} kgv_replay_stats;
+/* results: n_txs records (host or device memory): the UTXO-context verdict when the context rules fail, else the script
+ * verdict (KGV_TX_SKIPPED_COINBASE for coinbases).  accept (may be NULL): n_txs bytes, 1 = folded into the table.
+ * stats may be NULL. */
+int kgv_replay_window(kgv_ctx* ctx, kgv_utxo_table* t, const kgv_tx_batch* batch, const kgv_replay_block* blocks, size_t n_blocks,
+                      const kgv_params* params, kgv_tx_result* results, uint8_t* accept, kgv_replay_stats* stats);
 
 /* ------------------------------------------------------------------------------------------------
  * Merkle roots: crypto/merkle/src/lib.rs:3-30 calc_merkle_root / merkle_hash.

@@ -155,6 +155,12 @@ void ok_state_free(ok_state* s);
 void ok_state_validate(ok_state* s, const ok_batch* b, uint64_t pov_daa_score, int flags, const ok_params* p, ok_tx_result* results, int nthreads);
 /* mergeset_diff.add_transaction for every tx with accept[i] != 0 (utxo_diff.rs:233-247). returns 0, or -1 on a UtxoAlgebraError */
 int ok_state_accept(ok_state* s, const ok_batch* b, const uint8_t* accept, uint64_t pov_daa_score);
+/* calculate_utxo_state over a window of blocks in one call (utxo_validation.rs:110-173): per block validate in parallel on a
+ * persistent pool of nthreads workers (tx 0 = coinbase, skipped by position), accept, commit.  block_flags (may be NULL = 1):
+ * bit 0 accept the coinbase, bit 1 SkipScriptChecks, bit 2 validate only.  accept_out may be NULL.  Returns 0, or -1 on a
+ * UtxoAlgebraError. */
+int ok_state_replay(ok_state* s, const ok_batch* b, const uint32_t* block_first_tx, const uint64_t* block_pov, const uint32_t* block_flags, size_t n_blocks,
+                    const ok_params* p, ok_tx_result* results, uint8_t* accept_out, int nthreads);
 /* write_diff_batch: fold the diff into the base (utxo_set.rs:107-112) */
 void ok_state_commit(ok_state* s);
 /* composed get: returns 1 if found (entry header + script bytes copied, script_cap bytes max) */

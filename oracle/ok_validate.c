@@ -373,8 +373,10 @@ void ok_state_validate(ok_state* s, const ok_batch* b, uint64_t pov, int flags, 
 }
 
 /* UtxoDiff::add_transaction (utxo_diff.rs:233-269) */
-int ok_state_accept(ok_state* s, const ok_batch* b, const uint8_t* accept, uint64_t pov) {
-  for (size_t ti = 0; ti < b->n_txs; ti++) {
+static int accept_range(ok_state* s, const ok_batch* b, size_t t0, size_t t1, const uint8_t* accept, uint64_t pov);
+int ok_state_accept(ok_state* s, const ok_batch* b, const uint8_t* accept, uint64_t pov) { return accept_range(s, b, 0, b->n_txs, accept, pov); }
+static int accept_range(ok_state* s, const ok_batch* b, size_t t0, size_t t1, const uint8_t* accept, uint64_t pov) {
+  for (size_t ti = t0; ti < t1; ti++) {
     if (!accept[ti]) continue;
     const ok_tx* t = &b->txs[ti];
     for (uint32_t i = 0; i < t->n_inputs; i++) { /* remove_entry */
@@ -405,6 +407,113 @@ int ok_state_accept(ok_state* s, const ok_batch* b, const uint8_t* accept, uint6
     }
   }
   return 0;
+}
+
+/* --------------------------------------------------------------------------------------------------------------
+ * calculate_utxo_state as ONE call over a window of blocks (utxo_validation.rs:110-173): for every block in order
+ *   validate_transactions_in_parallel (tx 0 = coinbase, skipped by position :273) on a pool of worker threads,
+ *   UtxoDiff::add_transaction for the accepted ones (+ the coinbase when block_flags bit 0 is set; NULL = always), commit.
+ * Block b = transactions [block_first_tx[b], block_first_tx[b+1]).  block_flags bit 1 = SkipScriptChecks, bit 2 = verify only.
+ * This is the CPU baseline of the DAG-replay benchmark and the checker of kgv_replay_window.
+ * Workers split a block's transactions into static contiguous chunks (rayon par_iter over a Vec); the pool lives for the
+ * whole call.  Entries are populated by the calling thread before the fan-out (HashMap probes are noise next to the
+ * signature checks) into ONE shadow arena = window bytes ++ spent scripts.
+ * -------------------------------------------------------------------------------------------------------------- */
+typedef struct {
+  pthread_mutex_t mu; pthread_cond_t go, done;
+  int nthreads, generation, remaining, quit;
+  /* current job */
+  const ok_batch* sb; const ok_utxo_entry* ents; const uint8_t* missing; uint64_t pov; int flags; const ok_params* p; ok_tx_result* res; size_t t0, t1;
+} rpool;
+typedef struct { rpool* pool; int id; } rworker_arg;
+static void replay_chunk(rpool* q, int id) {
+  size_t n = q->t1 - q->t0, lo = q->t0 + n * (size_t)id / (size_t)q->nthreads, hi = q->t0 + n * ((size_t)id + 1) / (size_t)q->nthreads;
+  for (size_t ti = lo; ti < hi; ti++) {
+    ok_tx_result* r = &q->res[ti];
+    memset(r, 0, sizeof *r);
+    if (ti == q->t0 || tx_is_coinbase(&q->sb->txs[ti])) { r->status = OK_TX_SKIPPED_COINBASE; continue; }
+    if (q->missing[ti]) { r->status = OK_TX_MISSING_OUTPOINTS; continue; }
+    ok_validate_populated(q->sb, q->ents, ti, q->pov, q->flags, q->p, r);
+  }
+}
+static void* rworker(void* a) {
+  rworker_arg* w = (rworker_arg*)a;
+  rpool* q = w->pool;
+  int seen = 0;
+  for (;;) {
+    pthread_mutex_lock(&q->mu);
+    while (q->generation == seen && !q->quit) pthread_cond_wait(&q->go, &q->mu);
+    if (q->quit) { pthread_mutex_unlock(&q->mu); return NULL; }
+    seen = q->generation;
+    pthread_mutex_unlock(&q->mu);
+    replay_chunk(q, w->id);
+    pthread_mutex_lock(&q->mu);
+    if (--q->remaining == 0) pthread_cond_signal(&q->done);
+    pthread_mutex_unlock(&q->mu);
+  }
+}
+static int accept_range(ok_state* s, const ok_batch* b, size_t t0, size_t t1, const uint8_t* accept, uint64_t pov);
+
+int ok_state_replay(ok_state* s, const ok_batch* b, const uint32_t* block_first_tx, const uint64_t* block_pov, const uint32_t* block_flags, size_t n_blocks,
+                    const ok_params* p, ok_tx_result* results, uint8_t* accept_out, int nthreads) {
+  ok_secp_init();
+  if (nthreads < 1) nthreads = 1;
+  rpool q;
+  memset(&q, 0, sizeof q);
+  pthread_mutex_init(&q.mu, NULL); pthread_cond_init(&q.go, NULL); pthread_cond_init(&q.done, NULL);
+  q.nthreads = nthreads; q.p = p; q.res = results;
+  pthread_t* th = malloc(sizeof(pthread_t) * (size_t)nthreads);
+  rworker_arg* wa = malloc(sizeof(rworker_arg) * (size_t)nthreads);
+  for (int t = 1; t < nthreads; t++) { wa[t].pool = &q; wa[t].id = t; pthread_create(&th[t], NULL, rworker, &wa[t]); }
+  size_t cap = b->n_bytes + 64 * b->n_inputs + 4096, off = b->n_bytes;
+  uint8_t* shadow = malloc(cap);
+  memcpy(shadow, b->bytes, b->n_bytes);
+  ok_utxo_entry* ents = calloc(b->n_inputs ? b->n_inputs : 1, sizeof(ok_utxo_entry));
+  uint8_t* missing = calloc(b->n_txs ? b->n_txs : 1, 1);
+  uint8_t* acc = accept_out ? accept_out : calloc(b->n_txs ? b->n_txs : 1, 1);
+  int rc = 0;
+  for (size_t bi = 0; bi < n_blocks && rc == 0; bi++) {
+    size_t t0 = block_first_tx[bi], t1 = block_first_tx[bi + 1];
+    uint32_t bf = block_flags ? block_flags[bi] : 1u;
+    if (t1 <= t0) continue;
+    for (size_t ti = t0 + 1; ti < t1; ti++) { /* populate: utxo_validation.rs:319-327 */
+      const ok_tx* t = &b->txs[ti];
+      missing[ti] = 0;
+      for (uint32_t i = 0; i < t->n_inputs; i++) {
+        const ok_input* in = &b->inputs[t->first_input + i];
+        uint8_t k[36];
+        make_key(k, in->prev_txid, in->prev_index);
+        const slot_t* f = state_get(s, k);
+        if (!f) { missing[ti] = 1; break; }
+        if (off + f->e.script_len > cap) { cap = 2 * cap + f->e.script_len; shadow = realloc(shadow, cap); }
+        ents[t->first_input + i] = f->e;
+        ents[t->first_input + i].script_off = (uint32_t)off;
+        memcpy(shadow + off, f->script, f->e.script_len);
+        off += f->e.script_len;
+      }
+    }
+    ok_batch sb = *b;
+    sb.bytes = shadow; sb.n_bytes = off;
+    pthread_mutex_lock(&q.mu);
+    q.sb = &sb; q.ents = ents; q.missing = missing; q.pov = block_pov[bi]; q.flags = (bf & 2u) ? OK_FLAGS_SKIP_SCRIPT_CHECKS : OK_FLAGS_FULL; q.t0 = t0; q.t1 = t1;
+    q.remaining = nthreads - 1; q.generation++;
+    pthread_cond_broadcast(&q.go);
+    pthread_mutex_unlock(&q.mu);
+    replay_chunk(&q, 0);
+    pthread_mutex_lock(&q.mu);
+    while (q.remaining) pthread_cond_wait(&q.done, &q.mu);
+    pthread_mutex_unlock(&q.mu);
+    for (size_t ti = t0; ti < t1; ti++) acc[ti] = (uint8_t)(!(bf & 4u) && (ti == t0 ? (bf & 1u) != 0 : results[ti].status == OK_TX_OK));
+    if (accept_range(s, b, t0, t1, acc, block_pov[bi]) != 0) rc = -1;
+    ok_state_commit(s);
+    off = b->n_bytes; /* the spent scripts of this block are no longer needed */
+  }
+  pthread_mutex_lock(&q.mu); q.quit = 1; pthread_cond_broadcast(&q.go); pthread_mutex_unlock(&q.mu);
+  for (int t = 1; t < nthreads; t++) pthread_join(th[t], NULL);
+  free(th); free(wa); free(shadow); free(ents); free(missing);
+  if (!accept_out) free(acc);
+  pthread_mutex_destroy(&q.mu); pthread_cond_destroy(&q.go); pthread_cond_destroy(&q.done);
+  return rc;
 }
 
 void ok_state_commit(ok_state* s) { /* write_diff_batch: delete removed, then put added */

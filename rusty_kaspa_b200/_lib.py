@@ -39,6 +39,7 @@ SYMBOLS = [
     ("kgv_utxo_digest", _c.c_int, [_c.c_void_p, _c.c_void_p, _u8p]),
     ("kgv_validate_txs", _c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_uint64, _c.c_uint32, _c.c_void_p, _u8p]),
     ("kgv_utxo_apply_accepted", _c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _u8p, _c.c_uint64]),
+    ("kgv_replay_window", _c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _u8p, _c.c_size_t, _c.c_void_p, _u8p, _u8p, _c.c_void_p]),
     ("kgv_merkle_roots", _c.c_int, [_c.c_void_p, _u8p, _u8p, _c.c_uint32, _u8p]),
     ("kgv_block_hash_merkle_roots", _c.c_int, [_c.c_void_p, _c.c_void_p, _u8p, _c.c_uint32, _u8p]),
     ("kgv_block_set_checks", _c.c_int, [_c.c_void_p, _c.c_void_p, _u8p, _c.c_uint32, _u8p]),

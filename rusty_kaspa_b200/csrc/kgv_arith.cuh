@@ -634,6 +634,19 @@ KGV_HD void fe_sqr2(fe& r1, const fe& a1, fe& r2, const fe& a2) { fe x, y; fe_sq
 KGV_HD void fe_mulsqr(fe& r1, const fe& a1, const fe& b1, fe& r2, const fe& a2) { fe x, y; fe_mul(x, a1, b1); fe_sqr(y, a2); r1 = x; r2 = y; }
 #endif
 
+// always-inlined forms: used INSIDE the (non-inlined) point operations when KGV_INLINE_MUL_IN_POINT is set, so that no
+// by-value call ABI (16-24 register moves per product) sits between the products of one group-law formula
+KGV_HD void fe_mul_inl(fe& r, const fe& a, const fe& b) {
+  uint32_t t[16];
+  mul_wide(t, a.v, b.v);
+  fe_reduce_wide(r, t);
+}
+KGV_HD void fe_sqr_inl(fe& r, const fe& a) {
+  uint32_t t[16];
+  sqr_wide(t, a.v);
+  fe_reduce_wide(r, t);
+}
+
 KGV_HD void fe_sqr_n(fe& r, const fe& a, int n) {
   r = a;
   for (int i = 0; i < n; i++) fe_sqr(r, r);

@@ -46,6 +46,20 @@ int kgv_batch_to_device(kgv_ctx* ctx, const kgv_tx_batch* b, kgv_dev_batch* out,
       return KGV_ERR_ARG;
     }
   }
+  // the per-transaction ranges must tile inputs[] and outputs[] exactly, in order: the kernels derive the input -> transaction and
+  // output -> transaction maps from them (an input no range covers would index verdict arrays with an uninitialised number)
+  {
+    uint64_t at_in = 0, at_out = 0;
+    for (size_t i = 0; i < b->n_txs; i++) {
+      const kgv_tx& t = b->txs[i];
+      if (t.first_input != at_in || t.first_output != at_out) {
+        ctx->err = "malformed batch: transaction " + std::to_string(i) + " does not continue the input / output ranges of its predecessor";
+        return KGV_ERR_ARG;
+      }
+      at_in += t.n_inputs; at_out += t.n_outputs;
+    }
+    if (at_in != b->n_inputs || at_out != b->n_outputs) { ctx->err = "malformed batch: the transactions do not cover the input / output arrays"; return KGV_ERR_ARG; }
+  }
   for (size_t i = 0; i < b->n_inputs; i++)
     if ((uint64_t)b->inputs[i].sigscript_off + b->inputs[i].sigscript_len > b->n_bytes) {
       ctx->err = "malformed batch: signature script of input " + std::to_string(i) + " lies outside the byte arena";
@@ -134,7 +148,7 @@ k_sighash_items(BatchView b, const SigHashReused* __restrict__ reused, const kgv
 // ---------------------------------------------------------------------------------------------
 static int digest_common(kgv_ctx* ctx, const kgv_tx_batch* batch, uint8_t* out32, bool hash) {
   if (!ctx) return KGV_ERR_ARG;
-  std::lock_guard<std::mutex> g(ctx->mu);
+  std::lock_guard<std::recursive_mutex> g(ctx->mu);
   if (!batch || (batch->n_txs && !out32)) { ctx->err = "null argument"; return KGV_ERR_ARG; }
   if (batch->n_txs == 0) return KGV_OK;
   CK(cudaSetDevice(ctx->device));
@@ -165,7 +179,7 @@ extern "C" int kgv_tx_hashes(kgv_ctx* ctx, const kgv_tx_batch* batch, uint8_t* o
 
 extern "C" int kgv_sighash(kgv_ctx* ctx, const kgv_tx_batch* batch, const kgv_sighash_item* items, size_t n_items, uint8_t* out32) {
   if (!ctx) return KGV_ERR_ARG;
-  std::lock_guard<std::mutex> g(ctx->mu);
+  std::lock_guard<std::recursive_mutex> g(ctx->mu);
   if (!batch || (n_items && (!items || !out32))) { ctx->err = "null argument"; return KGV_ERR_ARG; }
   if (n_items == 0) return KGV_OK;
   CK(cudaSetDevice(ctx->device));
@@ -257,6 +271,7 @@ __global__ void k_merkle_collect(const uint64_t* __restrict__ cur, const uint32_
 // dh: device array of n_total hashes (modified: used as one of the two ping-pong buffers); first_host: n_groups + 1 offsets on the HOST
 static int merkle_core(kgv_ctx* ctx, uint64_t* dh, size_t n_total, const uint32_t* first_host, uint32_t n_groups, uint64_t* droots) {
   uint32_t max_n = 0;
+  if (n_groups && (first_host[0] != 0 || first_host[n_groups] != n_total)) { ctx->err = "merkle group offsets must start at 0 and end at the number of hashes"; return KGV_ERR_ARG; }
   for (uint32_t g = 0; g < n_groups; g++) {
     if (first_host[g + 1] < first_host[g] || first_host[g + 1] > n_total) { ctx->err = "merkle group offsets not monotone / out of range"; return KGV_ERR_ARG; }
     uint32_t n = first_host[g + 1] - first_host[g];
@@ -292,7 +307,7 @@ static int merkle_core(kgv_ctx* ctx, uint64_t* dh, size_t n_total, const uint32_
 
 extern "C" int kgv_merkle_roots(kgv_ctx* ctx, const uint8_t* hashes32, const uint32_t* first, uint32_t n_groups, uint8_t* roots32) {
   if (!ctx) return KGV_ERR_ARG;
-  std::lock_guard<std::mutex> g(ctx->mu);
+  std::lock_guard<std::recursive_mutex> g(ctx->mu);
   if (n_groups == 0) return KGV_OK;
   if (!first || !roots32) { ctx->err = "null argument"; return KGV_ERR_ARG; }
   if (kgv_ptr_is_device(first)) { ctx->err = "merkle group offsets must be a host array"; return KGV_ERR_ARG; }
@@ -318,7 +333,7 @@ extern "C" int kgv_merkle_roots(kgv_ctx* ctx, const uint8_t* hashes32, const uin
 // [block_first_tx[b], block_first_tx[b+1]) (host array); tx hashes never leave the device.
 extern "C" int kgv_block_hash_merkle_roots(kgv_ctx* ctx, const kgv_tx_batch* batch, const uint32_t* block_first_tx, uint32_t n_blocks, uint8_t* roots32) {
   if (!ctx) return KGV_ERR_ARG;
-  std::lock_guard<std::mutex> g(ctx->mu);
+  std::lock_guard<std::recursive_mutex> g(ctx->mu);
   if (n_blocks == 0) return KGV_OK;
   if (!batch || !block_first_tx || !roots32) { ctx->err = "null argument"; return KGV_ERR_ARG; }
   if (kgv_ptr_is_device(block_first_tx)) { ctx->err = "block offsets must be a host array"; return KGV_ERR_ARG; }
@@ -408,7 +423,7 @@ __global__ void k_block_set_checks_final(const BlockCheckAcc* __restrict__ acc, 
 
 extern "C" int kgv_block_set_checks(kgv_ctx* ctx, const kgv_tx_batch* batch, const uint32_t* block_first_tx, uint32_t n_blocks, kgv_block_check* out) {
   if (!ctx) return KGV_ERR_ARG;
-  std::lock_guard<std::mutex> g(ctx->mu);
+  std::lock_guard<std::recursive_mutex> g(ctx->mu);
   if (n_blocks == 0) return KGV_OK;
   if (n_blocks > 65535) { ctx->err = "at most 65535 blocks per call"; return KGV_ERR_ARG; }
   if (!batch || !block_first_tx || !out) { ctx->err = "null argument"; return KGV_ERR_ARG; }

@@ -32,11 +32,15 @@ struct kgv_ctx {
   size_t d_batch_cap = 0;
   uint8_t* d_scratch = nullptr; // per-call device scratch (sub-hashes, sig items, ...)
   size_t d_scratch_cap = 0;
+  uint8_t* d_work = nullptr;    // per-call populated entries / input->tx index / verdicts of the validation calls
+  size_t d_work_cap = 0;
+  uint8_t* d_replay = nullptr;  // kgv_replay_window: window-wide state (tx ids, window map, script verdicts, accept mask)
+  size_t d_replay_cap = 0;
   uint8_t* d_mu = nullptr;      // MuHash element arrays, product-tree levels and wide-product scratch rows
   size_t d_mu_cap = 0;
   uint64_t launches = 0;
   int resident_blocks = 148 * KGV_BLOCKS_PER_SM;  // verification kernels: blocks that fit the device at once (persistent grid)
-  std::mutex mu;
+  std::recursive_mutex mu;  // recursive: the host-VM resolution inside a validation call re-enters the ABI (kgv_sighash, kgv_*_verify)
   std::string err;
 };
 
@@ -68,3 +72,6 @@ int kgv_mu_reserve(kgv_ctx* ctx, size_t n_den, size_t n_num, uint32_t** e_den, u
 // Multiply each tree down to one value (denominator on ctx->stream, numerator on the side stream) and write the two
 // canonical residues (384 little-endian bytes each) to host or device memory.
 int kgv_mu_reduce(kgv_ctx* ctx, size_t n_den, size_t n_num, uint8_t* out_num384, uint8_t* out_den384);
+
+// ---- shared pieces of the validation path (kgv_validate.cu) ----
+struct kgv_utxo_table;

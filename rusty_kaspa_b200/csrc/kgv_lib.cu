@@ -360,6 +360,8 @@ extern "C" void kgv_destroy(kgv_ctx* ctx) {
   if (ctx->d_batch) cudaFree(ctx->d_batch);
   if (ctx->d_scratch) cudaFree(ctx->d_scratch);
   if (ctx->d_mu) cudaFree(ctx->d_mu);
+  if (ctx->d_work) cudaFree(ctx->d_work);
+  if (ctx->d_replay) cudaFree(ctx->d_replay);
   for (cudaEvent_t e : ctx->ev_chunk) if (e) cudaEventDestroy(e);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
@@ -370,21 +372,21 @@ extern "C" void kgv_destroy(kgv_ctx* ctx) {
 
 extern "C" int kgv_set_stream(kgv_ctx* ctx, void* cuda_stream) {
   if (!ctx) return KGV_ERR_ARG;
-  std::lock_guard<std::mutex> g(ctx->mu);
+  std::lock_guard<std::recursive_mutex> g(ctx->mu);
   ctx->stream = (cudaStream_t)cuda_stream;  // NULL is CUDA's default stream, exactly as in cudaStream_t
   return KGV_OK;
 }
 
 extern "C" int kgv_reset_stream(kgv_ctx* ctx) {
   if (!ctx) return KGV_ERR_ARG;
-  std::lock_guard<std::mutex> g(ctx->mu);
+  std::lock_guard<std::recursive_mutex> g(ctx->mu);
   ctx->stream = ctx->own_stream;
   return KGV_OK;
 }
 
 extern "C" int kgv_synchronize(kgv_ctx* ctx) {
   if (!ctx) return KGV_ERR_ARG;
-  std::lock_guard<std::mutex> g(ctx->mu);
+  std::lock_guard<std::recursive_mutex> g(ctx->mu);
   CK(cudaSetDevice(ctx->device));
   CK(cudaStreamSynchronize(ctx->stream));
   return KGV_OK;
@@ -421,7 +423,7 @@ int kgv_launch_verify(kgv_ctx* ctx, const uint8_t* dpk, const uint8_t* dmsg, con
 static int verify_common(kgv_ctx* ctx, const uint8_t* pk, size_t pk_stride, const uint8_t* msg, const uint8_t* sig, size_t n,
                          uint8_t* status, bool ecdsa) {
   if (!ctx) return KGV_ERR_ARG;
-  std::lock_guard<std::mutex> g(ctx->mu);
+  std::lock_guard<std::recursive_mutex> g(ctx->mu);
   if (n == 0) return KGV_OK;
   if (!pk || !msg || !sig || !status) return fail_arg(ctx, "null buffer");
   CK(cudaSetDevice(ctx->device));
@@ -484,7 +486,7 @@ extern "C" int kgv_ecdsa_verify(kgv_ctx* ctx, const uint8_t* pk33, const uint8_t
 
 extern "C" int kgv_status_to_bitmap(kgv_ctx* ctx, const uint8_t* status, size_t n, uint8_t* bitmap) {
   if (!ctx) return KGV_ERR_ARG;
-  std::lock_guard<std::mutex> g(ctx->mu);
+  std::lock_guard<std::recursive_mutex> g(ctx->mu);
   if (n == 0) return KGV_OK;
   if (!status || !bitmap) return fail_arg(ctx, "null buffer");
   CK(cudaSetDevice(ctx->device));
@@ -514,7 +516,7 @@ extern "C" int kgv_status_to_bitmap(kgv_ctx* ctx, const uint8_t* status, size_t 
 extern "C" int kgv_debug_schnorr_trace(kgv_ctx* ctx, const uint8_t* pk32, const uint8_t* msg32, const uint8_t* sig64, uint32_t* trace_words,
                                        uint8_t* status) {
   if (!ctx) return KGV_ERR_ARG;
-  std::lock_guard<std::mutex> g(ctx->mu);
+  std::lock_guard<std::recursive_mutex> g(ctx->mu);
   if (!pk32 || !msg32 || !sig64 || !trace_words || !status) return fail_arg(ctx, "null buffer");
   CK(cudaSetDevice(ctx->device));
   const size_t tw = KGV_TRACE_STAGES * 16 * sizeof(uint32_t);
@@ -539,7 +541,7 @@ extern "C" int kgv_debug_schnorr_trace(kgv_ctx* ctx, const uint8_t* pk32, const 
 
 extern "C" int kgv_debug_selftest(kgv_ctx* ctx, int op, const uint32_t* in_words, uint32_t* out_words, size_t n) {
   if (!ctx) return KGV_ERR_ARG;
-  std::lock_guard<std::mutex> g(ctx->mu);
+  std::lock_guard<std::recursive_mutex> g(ctx->mu);
   if (!in_words || !out_words || n == 0 || n > (1u << 20)) return fail_arg(ctx, "bad selftest arguments");
   CK(cudaSetDevice(ctx->device));
   int rc = kgv_reserve(ctx, &ctx->d_in, &ctx->d_in_cap, n * 64);
@@ -557,7 +559,7 @@ extern "C" int kgv_debug_selftest(kgv_ctx* ctx, int op, const uint32_t* in_words
 
 extern "C" int kgv_gtable_entry(kgv_ctx* ctx, int which, uint32_t v, uint8_t out_xy[64]) {
   if (!ctx) return KGV_ERR_ARG;
-  std::lock_guard<std::mutex> g(ctx->mu);
+  std::lock_guard<std::recursive_mutex> g(ctx->mu);
   if ((which != 0 && which != 1) || v == 0 || v > 65535 || !out_xy) return fail_arg(ctx, "bad table index");
   CK(cudaSetDevice(ctx->device));
   uint32_t w[16];

@@ -159,7 +159,7 @@ int kgv_mu_reduce(kgv_ctx* ctx, size_t n_den, size_t n_num, uint8_t* out_num384,
 extern "C" int kgv_muhash_elements(kgv_ctx* ctx, const uint8_t* data, const uint64_t* offsets, const uint8_t* remove, size_t n, uint8_t* numerator384,
                                    uint8_t* denominator384) {
   if (!ctx) return KGV_ERR_ARG;
-  std::lock_guard<std::mutex> g(ctx->mu);
+  std::lock_guard<std::recursive_mutex> g(ctx->mu);
   if (!numerator384 || !denominator384 || (n && (!offsets || !data))) { ctx->err = "null argument"; return KGV_ERR_ARG; }
   if (kgv_ptr_is_device(numerator384) != kgv_ptr_is_device(denominator384)) { ctx->err = "outputs must both be host or both be device pointers"; return KGV_ERR_ARG; }
   CK(cudaSetDevice(ctx->device));
@@ -202,7 +202,7 @@ __global__ void k_muhash_combine(uint32_t* __restrict__ w) {  // w: [a_num | a_d
 }
 extern "C" int kgv_muhash_combine(kgv_ctx* ctx, uint8_t* num_a, uint8_t* den_a, const uint8_t* num_b, const uint8_t* den_b) {
   if (!ctx) return KGV_ERR_ARG;
-  std::lock_guard<std::mutex> g(ctx->mu);
+  std::lock_guard<std::recursive_mutex> g(ctx->mu);
   if (!num_a || !den_a || !num_b || !den_b) { ctx->err = "null argument"; return KGV_ERR_ARG; }
   CK(cudaSetDevice(ctx->device));
   int rc = kgv_reserve(ctx, &ctx->d_mu, &ctx->d_mu_cap, 4096);
@@ -269,7 +269,7 @@ __global__ void k_muhash_finalize(uint32_t* __restrict__ w, uint32_t* __restrict
 }
 extern "C" int kgv_muhash_finalize(kgv_ctx* ctx, const uint8_t* numerator384, const uint8_t* denominator384, uint8_t* serialized384, uint8_t* hash32) {
   if (!ctx) return KGV_ERR_ARG;
-  std::lock_guard<std::mutex> g(ctx->mu);
+  std::lock_guard<std::recursive_mutex> g(ctx->mu);
   if (!numerator384 || !denominator384 || !hash32) { ctx->err = "null argument"; return KGV_ERR_ARG; }
   CK(cudaSetDevice(ctx->device));
   int rc = kgv_reserve(ctx, &ctx->d_mu, &ctx->d_mu_cap, 8192);

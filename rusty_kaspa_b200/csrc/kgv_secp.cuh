@@ -290,6 +290,16 @@ KGV_HD void recoded_digit(const uint32_t* h, int i, uint32_t& idx, bool& neg) {
 // group law, Jacobian coordinates on y^2 = x^3 + b (a = 0; b never appears in the formulas,
 // so the same code runs on the isomorphic curves used for the per-thread tables)
 // ------------------------------------------------------------------------------------------
+#ifndef KGV_INLINE_MUL_IN_POINT
+#define KGV_INLINE_MUL_IN_POINT 0  // 1: the field products inside gej_double / gej_add_ge are inlined into those (non-inlined) functions
+#endif
+#if defined(__CUDACC__) && KGV_INLINE_MUL_IN_POINT
+#define FE_PMUL fe_mul_inl
+#define FE_PSQR fe_sqr_inl
+#else
+#define FE_PMUL fe_mul
+#define FE_PSQR fe_sqr
+#endif
 KGV_HD void gej_double_body(gej& r) {
   if (r.inf) return;
   fe A, B, C, D, E, F, t, yz;
@@ -306,26 +316,26 @@ KGV_HD void gej_double_body(gej& r) {
   fe_sub(t, F, D);
   fe_sub(r.x, t, D);             // X3 = E^2 - 2D
   fe_sub(t, D, r.x);
-  fe_mul(t, E, t);
+  FE_PMUL(t, E, t);
   fe_mul8(C, C);
   fe_sub(r.y, t, C);             // Y3 = E (D - X3) - 8 Y^4
 #else
-  fe_sqr(A, r.x);
-  fe_sqr(B, r.y);
-  fe_sqr(C, B);
+  FE_PSQR(A, r.x);
+  FE_PSQR(B, r.y);
+  FE_PSQR(C, B);
   fe_add(t, r.x, B);
-  fe_sqr(t, t);
+  FE_PSQR(t, t);
   fe_sub(t, t, A);
   fe_sub(t, t, C);
   fe_dbl(D, t);        // D = 2((X+B)^2 - A - C) = 4 X Y^2
   fe_mul3(E, A);       // E = 3 X^2
-  fe_mul(r.z, r.y, r.z);
+  FE_PMUL(r.z, r.y, r.z);
   fe_dbl(r.z, r.z);    // Z3 = 2 Y Z
-  fe_sqr(t, E);
+  FE_PSQR(t, E);
   fe_sub(t, t, D);
   fe_sub(r.x, t, D);   // X3 = E^2 - 2D
   fe_sub(t, D, r.x);
-  fe_mul(t, E, t);
+  FE_PMUL(t, E, t);
   fe_mul8(C, C);
   fe_sub(r.y, t, C);   // Y3 = E (D - X3) - 8 Y^4
   (void)F; (void)yz;
@@ -355,20 +365,20 @@ KGV_HD void gej_add_ge_body(gej& r, const fe& bx, const fe& by, fe* hout) {
     return;
   }
   fe z1z1, u2, s2, h, rr, t;
-  fe_sqr(z1z1, r.z);
+  FE_PSQR(z1z1, r.z);
 #if KGV_PAIRED_MUL
   fe_mul2(u2, bx, z1z1, t, r.z, z1z1);
 #else
-  fe_mul(u2, bx, z1z1);
-  fe_mul(t, r.z, z1z1);
+  FE_PMUL(u2, bx, z1z1);
+  FE_PMUL(t, r.z, z1z1);
 #endif
-  fe_mul(s2, by, t);
+  FE_PMUL(s2, by, t);
   fe_sub(h, u2, r.x);
   fe_sub(rr, s2, r.y);
   if (fe_is_zero(h)) {
     if (hout) fe_set_u32(*hout, 1);
     if (fe_is_zero(rr)) {
-      gej_double_body(r);
+      gej_double(r);                 // rare path: through the (non-inlined) doubling, not a second inlined copy
       if (hout) fe_dbl(*hout, r.y);  // not used by the table builder (cannot happen there)
     } else {
       r.inf = true;
@@ -386,28 +396,36 @@ KGV_HD void gej_add_ge_body(gej& r, const fe& bx, const fe& by, fe* hout) {
   fe_sub(t, t, v);
   fe_sub(r.x, t, v);                      // X3 = R^2 - H^3 - 2V
   fe_sub(t, v, r.x);
-  fe_mul(t, rr, t);
+  FE_PMUL(t, rr, t);
   fe_sub(r.y, t, y1h3);                   // Y3 = R (V - X3) - Y1 H^3
 #else
-  fe_sqr(hh, h);
-  fe_mul(hhh, hh, h);
-  fe_mul(v, r.x, hh);
-  fe_mul(r.z, r.z, h);
-  fe_sqr(t, rr);
+  FE_PSQR(hh, h);
+  FE_PMUL(hhh, hh, h);
+  FE_PMUL(v, r.x, hh);
+  FE_PMUL(r.z, r.z, h);
+  FE_PSQR(t, rr);
   fe_sub(t, t, hhh);
   fe_sub(t, t, v);
   fe_sub(r.x, t, v);      // X3 = R^2 - H^3 - 2V
   fe_sub(t, v, r.x);
-  fe_mul(t, rr, t);
-  fe_mul(hhh, r.y, hhh);
+  FE_PMUL(t, rr, t);
+  FE_PMUL(hhh, r.y, hhh);
   fe_sub(r.y, t, hhh);    // Y3 = R (V - X3) - Y1 H^3
 #endif
 }
 
 #if defined(__CUDACC__) && KGV_NOINLINE_POINT
 static __device__ __noinline__ gej gej_add_ge_call(gej r, fe bx, fe by) { gej_add_ge_body(r, bx, by, nullptr); return r; }
+#if KGV_INLINE_MUL_IN_POINT
+struct gej_h { gej r; fe h; };
+static __device__ __noinline__ gej_h gej_add_ge_h_call(gej r, fe bx, fe by) { gej_h o; gej_add_ge_body(r, bx, by, &o.h); o.r = r; return o; }
+#endif
 KGV_HD void gej_add_ge(gej& r, const fe& bx, const fe& by, fe* hout = nullptr) {
+#if KGV_INLINE_MUL_IN_POINT
+  if (hout) { gej_h o = gej_add_ge_h_call(r, bx, by); r = o.r; *hout = o.h; }
+#else
   if (hout) gej_add_ge_body(r, bx, by, hout);
+#endif
   else r = gej_add_ge_call(r, bx, by);
 }
 #else

@@ -15,6 +15,8 @@
 #include "kgv_internal.h"
 #include "kgv_muhash.cuh"
 #include "kgv_txhash.cuh"
+#include "kgv_utxo.cuh"
+#include "kgv_context.cuh"
 
 #include <cstdio>
 #include <vector>
@@ -47,142 +49,12 @@ static bool kgv_debug_on() { static int v = -1; if (v < 0) v = getenv("KGV_DEBUG
   } while (0)
 
 // ---------------------------------------------------------------------------------------------
-// UTXO table
+// UTXO table kernels (device functions: kgv_utxo.cuh)
 // ---------------------------------------------------------------------------------------------
-#define SLOT_EMPTY 0u
-#define SLOT_FULL 1u
-#define SLOT_TOMB 2u
-#define SLOT_BUSY 3u
-#define INLINE_SCRIPT 68u
-
-struct __align__(128) UtxoSlot {
-  uint32_t state;
-  uint32_t key[9];       // txid (8 words) + index
-  uint64_t amount;       // word 10,11
-  uint64_t daa;          // word 12,13
-  uint32_t meta;         // spk_version | is_coinbase << 16 | script_len << 17
-  uint8_t script[INLINE_SCRIPT];  // inline bytes, or (len > 68) a u64 offset into the overflow arena
-};
-static_assert(sizeof(UtxoSlot) == 128, "slot must be one 128-byte line");
-
-struct kgv_utxo_table {
-  UtxoSlot* slots = nullptr;
-  uint64_t mask = 0;             // capacity - 1
-  uint8_t* overflow = nullptr;   // long scripts
-  uint64_t overflow_cap = 0;
-  unsigned long long* counters = nullptr;  // [0] live entries, [1] tombstones, [2] overflow bytes used, [3] insert failures
-};
-
-struct TableView {
-  UtxoSlot* slots;
-  uint64_t mask;
-  uint8_t* overflow;
-  uint64_t overflow_cap;
-  unsigned long long* counters;
-};
-
-__device__ __forceinline__ void load_key(uint32_t* k, const uint8_t* p) {
-#pragma unroll
-  for (int i = 0; i < 9; i++) k[i] = (uint32_t)p[4 * i] | ((uint32_t)p[4 * i + 1] << 8) | ((uint32_t)p[4 * i + 2] << 16) | ((uint32_t)p[4 * i + 3] << 24);
-}
-__device__ __forceinline__ uint64_t key_hash(const uint32_t* k) {
-  uint64_t h = ((uint64_t)k[1] << 32 | k[0]) ^ ((uint64_t)k[3] << 32 | k[2]) * 0x9E3779B97F4A7C15ull;
-  h ^= (uint64_t)k[8] * 0xD6E8FEB86659FD93ull;
-  h ^= h >> 29;
-  h *= 0xBF58476D1CE4E5B9ull;
-  h ^= h >> 32;
-  return h;
-}
-__device__ __forceinline__ bool key_eq(const UtxoSlot* s, const uint32_t* k) {
-  bool eq = true;
-#pragma unroll
-  for (int i = 0; i < 9; i++) eq = eq && (s->key[i] == k[i]);
-  return eq;
-}
-// returns the slot holding key k, or nullptr (table is not being modified concurrently)
-__device__ __forceinline__ UtxoSlot* table_find(const TableView& t, const uint32_t* k) {
-  uint64_t i = key_hash(k) & t.mask;
-  for (uint64_t probes = 0; probes <= t.mask; probes++) {
-    UtxoSlot* s = &t.slots[i];
-    uint32_t st = s->state;
-    if (st == SLOT_EMPTY) return nullptr;
-    if (st == SLOT_FULL && key_eq(s, k)) return s;
-    i = (i + 1) & t.mask;
-  }
-  return nullptr;
-}
-__device__ __forceinline__ const uint8_t* slot_script(const TableView& t, const UtxoSlot* s, uint32_t len) {
-  if (len <= INLINE_SCRIPT) return s->script;
-  uint64_t off;
-  memcpy(&off, s->script, 8);
-  return t.overflow + off;
-}
 __device__ __forceinline__ void slot_to_entry(DevEntry& e, const TableView& t, const UtxoSlot* s) {
-  e.amount = s->amount;
-  e.block_daa_score = s->daa;
-  e.spk_version = (uint16_t)(s->meta & 0xFFFFu);
-  e.is_coinbase = (uint8_t)((s->meta >> 16) & 1u);
-  e.script_len = s->meta >> 17;
-  e.script = slot_script(t, s, e.script_len);
-  e.found = 1;
-}
-
-// upsert; returns 1 inserted, 2 replaced, 0 failed (table or overflow arena full).
-// Keys inserted concurrently by one kernel must be distinct (API contract), so a slot another thread is
-// filling (BUSY) always belongs to a different key and is simply skipped: no thread ever waits on another.
-__device__ uint32_t table_put(const TableView& t, const uint32_t* k, uint64_t amount, uint64_t daa, uint32_t spk_version, uint32_t is_coinbase,
-                              const uint8_t* script, uint32_t script_len) {
-  uint64_t i = key_hash(k) & t.mask;
-  UtxoSlot* target = nullptr;
-  UtxoSlot* tomb = nullptr;
-  bool replace = false;
-  for (uint64_t probes = 0; probes <= t.mask; probes++, i = (i + 1) & t.mask) {
-    UtxoSlot* s = &t.slots[i];
-    uint32_t st = *(volatile uint32_t*)&s->state;
-    if (st == SLOT_FULL) {
-      if (key_eq(s, k)) { target = s; replace = true; break; }
-      continue;
-    }
-    if (st == SLOT_TOMB) { if (!tomb) tomb = s; continue; }
-    if (st == SLOT_BUSY) continue;
-    // EMPTY: the key is not in the table. Prefer the first tombstone seen, else this slot.
-    if (tomb) {
-      if (atomicCAS(&tomb->state, SLOT_TOMB, SLOT_BUSY) == SLOT_TOMB) { target = tomb; atomicAdd(&t.counters[1], (unsigned long long)-1); break; }
-      tomb = nullptr;
-    }
-    if (atomicCAS(&s->state, SLOT_EMPTY, SLOT_BUSY) == SLOT_EMPTY) { target = s; break; }
-    // lost the race for this slot (it now holds another key): keep probing
-  }
-  if (!target && tomb && atomicCAS(&tomb->state, SLOT_TOMB, SLOT_BUSY) == SLOT_TOMB) { target = tomb; atomicAdd(&t.counters[1], (unsigned long long)-1); }
-  if (!target) { atomicAdd(&t.counters[3], 1ull); return 0; }
-#pragma unroll
-  for (int w = 0; w < 9; w++) target->key[w] = k[w];
-  target->amount = amount;
-  target->daa = daa;
-  target->meta = (spk_version & 0xFFFFu) | ((is_coinbase & 1u) << 16) | (script_len << 17);
-  if (script_len <= INLINE_SCRIPT) {
-    for (uint32_t b = 0; b < script_len; b++) target->script[b] = script[b];
-  } else {
-    uint64_t need = (script_len + 7u) & ~7ull;
-    uint64_t off = atomicAdd(&t.counters[2], (unsigned long long)need);
-    if (off + need > t.overflow_cap) { atomicAdd(&t.counters[3], 1ull); if (!replace) { __threadfence(); target->state = SLOT_TOMB; atomicAdd(&t.counters[1], 1ull); } return 0; }
-    for (uint32_t b = 0; b < script_len; b++) t.overflow[off + b] = script[b];
-    memcpy(target->script, &off, 8);
-  }
-  if (!replace) {
-    __threadfence();
-    target->state = SLOT_FULL;
-    atomicAdd(&t.counters[0], 1ull);
-  }
-  return replace ? 2u : 1u;
-}
-__device__ uint32_t table_erase(const TableView& t, const uint32_t* k) {
-  UtxoSlot* s = table_find(t, k);
-  if (!s) return 0;
-  s->state = SLOT_TOMB;
-  atomicAdd(&t.counters[0], (unsigned long long)-1);
-  atomicAdd(&t.counters[1], 1ull);
-  return 1;
+  SlotHead h;
+  slot_load_head(h, s);
+  head_to_entry(e, t, s, h);
 }
 
 __global__ void k_utxo_lookup(TableView t, const uint8_t* __restrict__ keys, size_t n, kgv_utxo_entry* __restrict__ entries,
@@ -191,17 +63,25 @@ __global__ void k_utxo_lookup(TableView t, const uint8_t* __restrict__ keys, siz
   if (i >= n) return;
   uint32_t k[9];
   load_key(k, keys + 36 * i);
-  UtxoSlot* s = table_find(t, k);
-  kgv_utxo_entry e;
-  memset(&e, 0, sizeof e);
-  e.script_off = (uint32_t)(i * stride);
+  SlotHead h;
+  UtxoSlot* s = table_find(t, k, h);
+  // the 32-byte entry record is written with one 256-bit store
+  uint32_t e[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  e[4] = (uint32_t)(i * stride);  // script_off
   if (s) {
     DevEntry d;
-    slot_to_entry(d, t, s);
-    e.amount = d.amount; e.block_daa_score = d.block_daa_score; e.script_len = d.script_len; e.spk_version = d.spk_version; e.is_coinbase = d.is_coinbase;
+    head_to_entry(d, t, s, h);
+    e[0] = h.w[10]; e[1] = h.w[11]; e[2] = h.w[12]; e[3] = h.w[13];
+    e[5] = d.script_len;
+    e[6] = (uint32_t)d.spk_version | ((uint32_t)d.is_coinbase << 16);
     for (uint32_t b = 0; b < d.script_len && b < stride; b++) scripts[i * stride + b] = d.script[b];
   }
-  entries[i] = e;
+  if ((((uintptr_t)entries) & 31) == 0) st256(entries + i, e);
+  else {
+    uint32_t* o = (uint32_t*)(entries + i);
+#pragma unroll
+    for (int j = 0; j < 8; j++) o[j] = e[j];
+  }
   found[i] = s ? 1 : 0;
 }
 __global__ void k_utxo_erase(TableView t, const uint8_t* __restrict__ keys, size_t n, uint8_t* __restrict__ status) {
@@ -266,55 +146,19 @@ __global__ void k_populate(TableView t, const kgv_input* __restrict__ inputs, si
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   uint32_t k[9];
-  const kgv_input& in = inputs[i];
-#pragma unroll
-  for (int w = 0; w < 8; w++) k[w] = (uint32_t)in.prev_txid[4 * w] | ((uint32_t)in.prev_txid[4 * w + 1] << 8) | ((uint32_t)in.prev_txid[4 * w + 2] << 16) | ((uint32_t)in.prev_txid[4 * w + 3] << 24);
-  k[8] = in.prev_index;
-  UtxoSlot* s = table_find(t, k);
+  input_key(k, inputs[i]);
+  SlotHead h;
+  UtxoSlot* s = table_find(t, k, h);
   DevEntry d;
-  if (s) slot_to_entry(d, t, s);
-  else { d.amount = 0; d.block_daa_score = 0; d.script = nullptr; d.script_len = 0; d.spk_version = 0; d.is_coinbase = 0; d.found = 0; }
+  if (s) head_to_entry(d, t, s, h);
+  else entry_absent(d);
   out[i] = d;
 }
 
 __global__ void k_tx_context(BatchView b, uint32_t n_txs, uint64_t pov, uint32_t flags, kgv_params prm, kgv_tx_result* __restrict__ res) {
   uint32_t ti = blockIdx.x * blockDim.x + threadIdx.x;
   if (ti >= n_txs) return;
-  const kgv_tx& t = b.txs[ti];
-  kgv_tx_result r;
-  r.fee = 0; r.fail_input = 0; r.status = KGV_TX_OK; r.script_err = 0; r.pad_[0] = r.pad_[1] = 0;
-  const DevEntry* ent = b.entries + t.first_input;
-  bool cb = tx_is_coinbase(t);
-  if (cb) { r.status = KGV_TX_SKIPPED_COINBASE; res[ti] = r; return; }
-  for (uint32_t i = 0; i < t.n_inputs; i++)
-    if (!ent[i].found) { r.status = KGV_TX_MISSING_OUTPOINTS; res[ti] = r; return; }  // utxo_validation.rs:319-327
-  if (flags == KGV_FLAGS_SCRIPTS_ONLY) { res[ti] = r; return; }
-  for (uint32_t i = 0; i < t.n_inputs; i++)
-    if (ent[i].is_coinbase && ent[i].block_daa_score + prm.coinbase_maturity > pov) { r.status = KGV_TX_IMMATURE_COINBASE; r.fail_input = i; res[ti] = r; return; }
-  uint64_t total_in = 0;
-  for (uint32_t i = 0; i < t.n_inputs; i++) {
-    if (ck_add(total_in, ent[i].amount, total_in)) { r.status = KGV_TX_INPUT_AMOUNT_OVERFLOW; res[ti] = r; return; }
-    if (total_in > prm.max_sompi) { r.status = KGV_TX_INPUT_AMOUNT_TOO_HIGH; res[ti] = r; return; }
-  }
-  uint64_t total_out = 0;
-  for (uint32_t i = 0; i < t.n_outputs; i++) total_out += b.outputs[t.first_output + i].value;
-  if (total_in < total_out) { r.status = KGV_TX_SPEND_TOO_HIGH; res[ti] = r; return; }
-  r.fee = total_in - total_out;
-  if (flags != KGV_FLAGS_SKIP_MASS_CHECK) {
-    uint64_t mass;
-    const kgv_output* outs = b.outputs + t.first_output;
-    bool ok = storage_mass(mass, false, t.n_inputs, t.n_outputs, [&](uint32_t i) -> const DevEntry& { return ent[i]; },
-                           [&](uint32_t i, uint64_t& v, uint32_t& l) { v = outs[i].value; l = outs[i].script_len; }, prm.storage_mass_parameter);
-    if (!ok) { r.status = KGV_TX_MASS_INCOMPUTABLE; res[ti] = r; return; }
-    if (mass != t.mass) { r.status = KGV_TX_WRONG_MASS; res[ti] = r; return; }
-  }
-  for (uint32_t i = 0; i < t.n_inputs; i++) {
-    uint64_t seq = b.inputs[t.first_input + i].sequence;
-    if (seq & (1ull << 63)) continue;
-    long long lock = (long long)ent[i].block_daa_score + (long long)(seq & 0xFFFFFFFFull) - 1;
-    if (lock >= (long long)pov) { r.status = KGV_TX_SEQUENCE_LOCK; res[ti] = r; return; }
-  }
-  res[ti] = r;
+  res[ti] = tx_context_rules(b, ti, pov, flags, prm, tx_is_coinbase(b.txs[ti]));
 }
 
 // plan: one thread per input. counts[0][i] = Schnorr items, counts[1][i] = ECDSA items (0 when the tx already failed).
@@ -476,10 +320,7 @@ __global__ void k_apply_erase(TableView t, const kgv_tx* __restrict__ txs, const
   if (i >= n_inputs) return;
   if (!accept[input_tx[i]]) return;
   uint32_t k[9];
-  const kgv_input& in = inputs[i];
-#pragma unroll
-  for (int w = 0; w < 8; w++) k[w] = (uint32_t)in.prev_txid[4 * w] | ((uint32_t)in.prev_txid[4 * w + 1] << 8) | ((uint32_t)in.prev_txid[4 * w + 2] << 16) | ((uint32_t)in.prev_txid[4 * w + 3] << 24);
-  k[8] = in.prev_index;
+  input_key(k, inputs[i]);
   table_erase(t, k);
 }
 __global__ void k_output_tx_index(const kgv_tx* __restrict__ txs, uint32_t n_txs, uint32_t* __restrict__ output_tx) {
@@ -573,12 +414,11 @@ __global__ void k_u3072_scatter(const uint32_t* __restrict__ values, size_t n, u
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-static TableView view_of(const kgv_utxo_table* t) { return TableView{t->slots, t->mask, t->overflow, t->overflow_cap, t->counters}; }
 static inline unsigned nblk(size_t n, unsigned b) { return (unsigned)((n + b - 1) / b); }
 
 extern "C" int kgv_utxo_create(kgv_ctx* ctx, uint64_t capacity_slots, kgv_utxo_table** out) {
   if (!ctx || !out) return KGV_ERR_ARG;
-  std::lock_guard<std::mutex> g(ctx->mu);
+  std::lock_guard<std::recursive_mutex> g(ctx->mu);
   *out = nullptr;
   CK(cudaSetDevice(ctx->device));
   uint64_t cap = 1024;
@@ -620,7 +460,7 @@ struct Stager {
 extern "C" int kgv_utxo_lookup(kgv_ctx* ctx, kgv_utxo_table* t, const uint8_t* keys36, size_t n, kgv_utxo_entry* entries, uint8_t* scripts_out,
                                uint32_t script_stride, uint8_t* found) {
   if (!ctx || !t) return KGV_ERR_ARG;
-  std::lock_guard<std::mutex> g(ctx->mu);
+  std::lock_guard<std::recursive_mutex> g(ctx->mu);
   if (n == 0) return KGV_OK;
   if (!keys36 || !entries || !found || (script_stride && !scripts_out)) { ctx->err = "null buffer"; return KGV_ERR_ARG; }
   CK(cudaSetDevice(ctx->device));
@@ -653,7 +493,7 @@ extern "C" int kgv_utxo_apply_diff(kgv_ctx* ctx, kgv_utxo_table* t, const uint8_
                                    const uint8_t* add_keys36, const kgv_utxo_entry* add_entries, const uint8_t* add_bytes, size_t n_add_bytes, size_t n_add,
                                    uint8_t* add_status) {
   if (!ctx || !t) return KGV_ERR_ARG;
-  std::lock_guard<std::mutex> g(ctx->mu);
+  std::lock_guard<std::recursive_mutex> g(ctx->mu);
   if ((n_rem && !rem_keys36) || (n_add && (!add_keys36 || !add_entries || (n_add_bytes && !add_bytes)))) { ctx->err = "null buffer"; return KGV_ERR_ARG; }
   CK(cudaSetDevice(ctx->device));
   const void* probe = n_rem ? (const void*)rem_keys36 : (const void*)add_keys36;
@@ -690,7 +530,7 @@ extern "C" int kgv_utxo_apply_diff(kgv_ctx* ctx, kgv_utxo_table* t, const uint8_
 
 extern "C" int kgv_utxo_count(kgv_ctx* ctx, kgv_utxo_table* t, uint64_t* count) {
   if (!ctx || !t || !count) return KGV_ERR_ARG;
-  std::lock_guard<std::mutex> g(ctx->mu);
+  std::lock_guard<std::recursive_mutex> g(ctx->mu);
   CK(cudaSetDevice(ctx->device));
   unsigned long long c[4];
   CK(cudaMemcpyAsync(c, t->counters, sizeof c, cudaMemcpyDeviceToHost, ctx->stream));
@@ -702,7 +542,7 @@ extern "C" int kgv_utxo_count(kgv_ctx* ctx, kgv_utxo_table* t, uint64_t* count) 
 
 extern "C" int kgv_utxo_digest(kgv_ctx* ctx, kgv_utxo_table* t, uint8_t out32[32]) {
   if (!ctx || !t || !out32) return KGV_ERR_ARG;
-  std::lock_guard<std::mutex> g(ctx->mu);
+  std::lock_guard<std::recursive_mutex> g(ctx->mu);
   CK(cudaSetDevice(ctx->device));
   unsigned long long* acc = t->counters + 8;
   CK(cudaMemsetAsync(acc, 0, 8 * sizeof(unsigned long long), ctx->stream));
@@ -722,6 +562,207 @@ extern "C" int kgv_utxo_digest(kgv_ctx* ctx, kgv_utxo_table* t, uint8_t out32[32
   return KGV_OK;
 }
 
+// The script phase of check_scripts (tx_validation_in_utxo_context.rs:162-200) for every transaction whose dres[].status is
+// KGV_TX_OK: plan -> scan -> emit -> sighash -> verify -> resolve -> finalize, all enqueued on ctx->stream (the ECDSA items on
+// the side stream).  v.entries must be populated.  Uses ctx->d_scratch (plans, counts, offsets, sub-hashes) and ctx->d_in
+// (item arrays); one host synchronisation (the two item totals).
+int kgv_scripts_phase(kgv_ctx* ctx, const BatchView& v, size_t nt, size_t ni, const uint32_t* itx, kgv_tx_result* dres, uint64_t* n_items_out) {
+  if (n_items_out) *n_items_out = 0;
+  if (ni == 0) return KGV_OK;
+  size_t o_plan = 0;
+  size_t o_cs = al256(o_plan + ni * sizeof(InputPlan));
+  size_t o_ce = al256(o_cs + ni * 4);
+  size_t o_os = al256(o_ce + ni * 4);
+  size_t o_oe = al256(o_os + ni * 4);
+  size_t o_tot = al256(o_oe + ni * 4);
+  size_t o_err = al256(o_tot + 64);
+  size_t o_reu = al256(o_err + ni);
+  size_t total = al256(o_reu + nt * sizeof(SigHashReused));
+  int rc = kgv_reserve(ctx, &ctx->d_scratch, &ctx->d_scratch_cap, total);
+  if (rc) return rc;
+  uint8_t* S = ctx->d_scratch;
+  InputPlan* plans = (InputPlan*)(S + o_plan);
+  uint32_t *cs = (uint32_t*)(S + o_cs), *ce = (uint32_t*)(S + o_ce), *os = (uint32_t*)(S + o_os), *oe = (uint32_t*)(S + o_oe), *tot = (uint32_t*)(S + o_tot);
+  uint8_t* ierr = S + o_err;
+  SigHashReused* reu = (SigHashReused*)(S + o_reu);
+  cudaStream_t st = ctx->stream;
+  k_plan<<<nblk(ni, 128), 128, 0, st>>>(v, ni, itx, dres, plans, cs, ce);
+  CK(cudaGetLastError());
+  STAGE("plan");
+  k_exclusive_scan2<<<2, 1024, 0, st>>>(cs, os, ce, oe, ni, tot);
+  CK(cudaGetLastError());
+  ctx->launches += 2;
+  uint32_t totals[2];
+  CK(cudaMemcpyAsync(totals, tot, sizeof totals, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  size_t ns = totals[0], ne = totals[1];
+  if (n_items_out) *n_items_out = ns + ne;
+  if (kgv_debug_on()) fprintf(stderr, "[kgv] items: schnorr %zu ecdsa %zu\n", ns, ne);
+  // item arrays live in d_in (pk/sig/msg, status, refs)
+  size_t i_pks = 0, i_sigs = al256(i_pks + ns * 32), i_msgs = al256(i_sigs + ns * 64), i_refs = al256(i_msgs + ns * 32), i_sts = al256(i_refs + ns * sizeof(ItemRef));
+  size_t i_pke = al256(i_sts + ns), i_sige = al256(i_pke + ne * 33), i_msge = al256(i_sige + ne * 64), i_refe = al256(i_msge + ne * 32), i_ste = al256(i_refe + ne * sizeof(ItemRef));
+  size_t total2 = al256(i_ste + ne + 64);
+  rc = kgv_reserve(ctx, &ctx->d_in, &ctx->d_in_cap, total2);
+  if (rc) return rc;
+  uint8_t* I = ctx->d_in;
+  if (ns + ne) {
+    k_emit_items<<<nblk(ni, 128), 128, 0, st>>>(v, ni, plans, os, oe, I + i_pks, I + i_sigs, (ItemRef*)(I + i_refs), I + i_pke, I + i_sige, (ItemRef*)(I + i_refe));
+    CK(cudaGetLastError());
+    k_sighash_reused_v<<<nblk(nt, 128), 128, 0, st>>>(v, (uint32_t)nt, dres, reu);
+    CK(cudaGetLastError());
+    ctx->launches += 2;
+    STAGE("emit+reused");
+  }
+  if (ns && ne) CK(cudaEventRecord(ctx->ev_fork, st));  // fork point: everything both item kinds depend on is queued
+  if (ns) {
+    k_item_msgs<<<nblk(ns, 128), 128, 0, st>>>(v, reu, itx, plans, (const ItemRef*)(I + i_refs), ns, false, (uint32_t*)(I + i_msgs));
+    CK(cudaGetLastError());
+    ctx->launches++;
+    STAGE("msgs schnorr");
+    rc = kgv_launch_verify(ctx, I + i_pks, I + i_msgs, I + i_sigs, ns, I + i_sts, false);
+    if (rc) return rc;
+    STAGE("verify schnorr");
+  }
+  if (ne) {
+    // with both kinds present the ECDSA items run on the side stream so the two (often sub-wave) verify
+    // launches share the SMs instead of queueing behind each other
+    const bool fork = ns != 0 && !kgv_debug_on();
+    cudaStream_t se = fork ? ctx->aux_stream : st;
+    if (fork) CK(cudaStreamWaitEvent(se, ctx->ev_fork, 0));
+    k_item_msgs<<<nblk(ne, 128), 128, 0, se>>>(v, reu, itx, plans, (const ItemRef*)(I + i_refe), ne, true, (uint32_t*)(I + i_msge));
+    CK(cudaGetLastError());
+    ctx->launches++;
+    STAGE("msgs ecdsa");
+    rc = kgv_launch_verify(ctx, I + i_pke, I + i_msge, I + i_sige, ne, I + i_ste, true, se, true);
+    if (rc) return rc;
+    if (fork) {
+      CK(cudaEventRecord(ctx->ev_join, se));
+      CK(cudaStreamWaitEvent(st, ctx->ev_join, 0));
+    }
+    STAGE("verify ecdsa");
+  }
+  k_resolve<<<nblk(ni, 128), 128, 0, st>>>(v, ni, itx, dres, plans, I + i_sts, I + i_ste, ierr);
+  CK(cudaGetLastError());
+  STAGE("resolve");
+  k_tx_finalize<<<nblk(nt, 128), 128, 0, st>>>(v, (uint32_t)nt, ierr, dres);
+  CK(cudaGetLastError());
+  ctx->launches += 2;
+  return KGV_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Non-standard scripts behind the table: the host script engine needs the populated entries, which only the library can
+// see.  For every transaction reported KGV_TX_NEEDS_HOST_VM the entries the device populated (dent) are gathered at their
+// TRUE script length (no stride, no truncation), a host-resident populated batch is assembled and kgv_check_scripts_host
+// decides (its signature checks go back to the GPU in batches).  `dres` is patched in place (device array of n_txs).
+// Rare path: a few synchronous copies.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_gather_entry_meta(const DevEntry* __restrict__ dent, const uint32_t* __restrict__ list, uint32_t n, kgv_utxo_entry* __restrict__ out) {
+  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  DevEntry d = dent[list[j]];
+  kgv_utxo_entry e;
+  memset(&e, 0, sizeof e);
+  e.amount = d.amount; e.block_daa_score = d.block_daa_score; e.script_len = d.found ? d.script_len : 0; e.spk_version = d.spk_version; e.is_coinbase = d.is_coinbase;
+  e.pad_[0] = d.found ? 0 : 1;
+  out[j] = e;
+}
+__global__ void k_gather_entry_scripts(const DevEntry* __restrict__ dent, const uint32_t* __restrict__ list, uint32_t n, const uint64_t* __restrict__ off,
+                                       uint8_t* __restrict__ out) {
+  uint32_t j = blockIdx.x;
+  if (j >= n) return;
+  DevEntry d = dent[list[j]];
+  if (!d.found) return;
+  for (uint32_t b = threadIdx.x; b < d.script_len; b += blockDim.x) out[off[j] + b] = d.script[b];
+}
+
+int kgv_host_vm_resolve(kgv_ctx* ctx, const kgv_tx_batch* batch, const kgv_dev_batch& d, const DevEntry* dent, kgv_tx_result* dres) {
+  const size_t nt = d.n_txs, ni = d.n_inputs;
+  cudaStream_t st = ctx->stream;
+  std::vector<kgv_tx_result> hres(nt);
+  CK(cudaMemcpyAsync(hres.data(), dres, nt * sizeof(kgv_tx_result), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  std::vector<uint32_t> idx;
+  for (size_t i = 0; i < nt; i++) if (hres[i].status == KGV_TX_NEEDS_HOST_VM) idx.push_back((uint32_t)i);
+  if (idx.empty()) return KGV_OK;
+  // host copy of the batch
+  std::vector<kgv_tx> htx; std::vector<kgv_input> hin; std::vector<kgv_output> hout; std::vector<uint8_t> hby;
+  const kgv_tx* txs = batch->txs; const kgv_input* ins = batch->inputs; const kgv_output* outs = batch->outputs; const uint8_t* by = batch->bytes;
+  const void* probe = batch->n_txs ? (const void*)batch->txs : (const void*)batch->bytes;
+  if (probe && kgv_ptr_is_device(probe)) {
+    htx.resize(nt); hin.resize(ni); hout.resize(d.n_outputs); hby.resize(d.n_bytes);
+    CK(cudaMemcpyAsync(htx.data(), d.txs, nt * sizeof(kgv_tx), cudaMemcpyDeviceToHost, st));
+    if (ni) CK(cudaMemcpyAsync(hin.data(), d.inputs, ni * sizeof(kgv_input), cudaMemcpyDeviceToHost, st));
+    if (d.n_outputs) CK(cudaMemcpyAsync(hout.data(), d.outputs, d.n_outputs * sizeof(kgv_output), cudaMemcpyDeviceToHost, st));
+    if (d.n_bytes) CK(cudaMemcpyAsync(hby.data(), d.bytes, d.n_bytes, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    txs = htx.data(); ins = hin.data(); outs = hout.data(); by = hby.data();
+  }
+  std::vector<uint32_t> list;
+  for (uint32_t ti : idx)
+    for (uint32_t k = 0; k < txs[ti].n_inputs; k++) list.push_back(txs[ti].first_input + k);
+  const size_t nl = list.size();
+  std::vector<kgv_utxo_entry> ents(ni);
+  for (auto& e : ents) { memset(&e, 0, sizeof e); e.pad_[0] = 1; }
+  std::vector<uint8_t> arena(by, by + d.n_bytes);
+  if (nl) {
+    size_t o_list = 0, o_meta = al256(nl * 4), o_off = al256(o_meta + nl * sizeof(kgv_utxo_entry));
+    int rc = kgv_reserve(ctx, &ctx->d_out, &ctx->d_out_cap, al256(o_off + nl * 8));
+    if (rc) return rc;
+    uint8_t* O = ctx->d_out;
+    CK(cudaMemcpyAsync(O + o_list, list.data(), nl * 4, cudaMemcpyHostToDevice, st));
+    k_gather_entry_meta<<<nblk(nl, 128), 128, 0, st>>>(dent, (const uint32_t*)(O + o_list), (uint32_t)nl, (kgv_utxo_entry*)(O + o_meta));
+    CK(cudaGetLastError());
+    ctx->launches++;
+    std::vector<kgv_utxo_entry> meta(nl);
+    CK(cudaMemcpyAsync(meta.data(), O + o_meta, nl * sizeof(kgv_utxo_entry), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    std::vector<uint64_t> off(nl);
+    uint64_t run = 0;
+    for (size_t j = 0; j < nl; j++) { off[j] = run; run += (meta[j].script_len + 7u) & ~7u; }
+    if (d.n_bytes + run > 0xFFFFFFF0ull) { ctx->err = "populated scripts do not fit a 32-bit arena offset"; return KGV_ERR_ARG; }
+    std::vector<uint8_t> scripts(run + 8);
+    if (run) {
+      // d_scratch is free again at this point (the script phase of this call has completed)
+      rc = kgv_reserve(ctx, &ctx->d_scratch, &ctx->d_scratch_cap, run + 256);
+      if (rc) return rc;
+      CK(cudaMemcpyAsync(O + o_off, off.data(), nl * 8, cudaMemcpyHostToDevice, st));
+      k_gather_entry_scripts<<<(unsigned)nl, 64, 0, st>>>(dent, (const uint32_t*)(O + o_list), (uint32_t)nl, (const uint64_t*)(O + o_off), ctx->d_scratch);
+      CK(cudaGetLastError());
+      ctx->launches++;
+      CK(cudaMemcpyAsync(scripts.data(), ctx->d_scratch, run, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+    }
+    const size_t base = arena.size();
+    arena.insert(arena.end(), scripts.begin(), scripts.end());
+    for (size_t j = 0; j < nl; j++) {
+      kgv_utxo_entry e = meta[j];
+      e.script_off = (uint32_t)(base + off[j]);
+      ents[list[j]] = e;
+    }
+  }
+  // a transaction with an absent entry never reaches the script phase (MissingTxOutpoints comes first), so every listed entry is present
+  kgv_tx_batch hb;
+  hb.txs = txs; hb.n_txs = nt; hb.inputs = ins; hb.n_inputs = ni; hb.outputs = outs; hb.n_outputs = d.n_outputs; hb.entries = ents.data();
+  hb.bytes = arena.data(); hb.n_bytes = arena.size();
+  std::vector<kgv_tx_result> out(idx.size());
+  int rc = kgv_check_scripts_host(ctx, &hb, idx.data(), idx.size(), out.data());
+  if (rc) return rc;
+  for (size_t j = 0; j < idx.size(); j++) {
+    kgv_tx_result& r = hres[idx[j]];
+    r.status = out[j].status; r.script_err = out[j].script_err; r.fail_input = out[j].fail_input;
+  }
+  CK(cudaMemcpyAsync(dres, hres.data(), nt * sizeof(kgv_tx_result), cudaMemcpyHostToDevice, st));
+  CK(cudaStreamSynchronize(st));
+  return KGV_OK;
+}
+__global__ void k_count_status(const kgv_tx_result* __restrict__ res, uint32_t n, uint8_t what, unsigned long long* __restrict__ out) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  bool hit = i < n && res[i].status == what;
+  unsigned m = __ballot_sync(0xFFFFFFFFu, hit);
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(out, (unsigned long long)__popc(m));
+}
+
 // shared core of kgv_validate_populated / kgv_validate_txs
 static int validate_core(kgv_ctx* ctx, kgv_utxo_table* table, const kgv_tx_batch* batch, uint64_t pov, uint32_t flags, const kgv_params* prm,
                          kgv_tx_result* results) {
@@ -733,31 +774,15 @@ static int validate_core(kgv_ctx* ctx, kgv_utxo_table* table, const kgv_tx_batch
   int rc = kgv_batch_to_device(ctx, batch, &d, table == nullptr);
   if (rc) return rc;
   const size_t nt = d.n_txs, ni = d.n_inputs;
-  const size_t max_items = ni * 110 < ((size_t)1 << 26) ? 0 : 0;  // (sized after the scan)
-  (void)max_items;
-  // scratch layout (phase 1)
   size_t o_ent = 0;
   size_t o_itx = al256(o_ent + ni * sizeof(DevEntry));
   size_t o_res = al256(o_itx + ni * 4);
-  size_t o_plan = al256(o_res + nt * sizeof(kgv_tx_result));
-  size_t o_cs = al256(o_plan + ni * sizeof(InputPlan));
-  size_t o_ce = al256(o_cs + ni * 4);
-  size_t o_os = al256(o_ce + ni * 4);
-  size_t o_oe = al256(o_os + ni * 4);
-  size_t o_tot = al256(o_oe + ni * 4);
-  size_t o_err = al256(o_tot + 64);
-  size_t o_reu = al256(o_err + ni);
-  size_t phase1 = al256(o_reu + nt * sizeof(SigHashReused));
-  rc = kgv_reserve(ctx, &ctx->d_scratch, &ctx->d_scratch_cap, phase1);
+  rc = kgv_reserve(ctx, &ctx->d_work, &ctx->d_work_cap, al256(o_res + nt * sizeof(kgv_tx_result)));
   if (rc) return rc;
-  uint8_t* S = ctx->d_scratch;
+  uint8_t* S = ctx->d_work;
   DevEntry* dent = (DevEntry*)(S + o_ent);
   uint32_t* itx = (uint32_t*)(S + o_itx);
   kgv_tx_result* dres = (kgv_tx_result*)(S + o_res);
-  InputPlan* plans = (InputPlan*)(S + o_plan);
-  uint32_t *cs = (uint32_t*)(S + o_cs), *ce = (uint32_t*)(S + o_ce), *os = (uint32_t*)(S + o_os), *oe = (uint32_t*)(S + o_oe), *tot = (uint32_t*)(S + o_tot);
-  uint8_t* ierr = S + o_err;
-  SigHashReused* reu = (SigHashReused*)(S + o_reu);
   cudaStream_t st = ctx->stream;
 
   if (ni) {
@@ -775,66 +800,24 @@ static int validate_core(kgv_ctx* ctx, kgv_utxo_table* table, const kgv_tx_batch
   ctx->launches++;
   STAGE("tx_context");
   if (flags != KGV_FLAGS_SKIP_SCRIPT_CHECKS && ni) {
-    k_plan<<<nblk(ni, 128), 128, 0, st>>>(v, ni, itx, dres, plans, cs, ce);
-    CK(cudaGetLastError());
-    STAGE("plan");
-    k_exclusive_scan2<<<2, 1024, 0, st>>>(cs, os, ce, oe, ni, tot);
-    CK(cudaGetLastError());
-    ctx->launches += 2;
-    uint32_t totals[2];
-    CK(cudaMemcpyAsync(totals, tot, sizeof totals, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    size_t ns = totals[0], ne = totals[1];
-    if (kgv_debug_on()) fprintf(stderr, "[kgv] items: schnorr %zu ecdsa %zu\n", ns, ne);
-    // item arrays (phase 2) live in d_in (pk/sig/msg) and d_out (status/refs): both unused by this call so far unless the batch was host-resident
-    size_t i_pks = 0, i_sigs = al256(i_pks + ns * 32), i_msgs = al256(i_sigs + ns * 64), i_refs = al256(i_msgs + ns * 32), i_sts = al256(i_refs + ns * sizeof(ItemRef));
-    size_t i_pke = al256(i_sts + ns), i_sige = al256(i_pke + ne * 33), i_msge = al256(i_sige + ne * 64), i_refe = al256(i_msge + ne * 32), i_ste = al256(i_refe + ne * sizeof(ItemRef));
-    size_t total2 = al256(i_ste + ne + 64);
-    rc = kgv_reserve(ctx, &ctx->d_in, &ctx->d_in_cap, total2);
+    rc = kgv_scripts_phase(ctx, v, nt, ni, itx, dres, nullptr);
     if (rc) return rc;
-    uint8_t* I = ctx->d_in;
-    if (ns + ne) {
-      k_emit_items<<<nblk(ni, 128), 128, 0, st>>>(v, ni, plans, os, oe, I + i_pks, I + i_sigs, (ItemRef*)(I + i_refs), I + i_pke, I + i_sige, (ItemRef*)(I + i_refe));
-      CK(cudaGetLastError());
-      k_sighash_reused_v<<<nblk(nt, 128), 128, 0, st>>>(v, (uint32_t)nt, dres, reu);
-      CK(cudaGetLastError());
-      ctx->launches += 2;
-      STAGE("emit+reused");
-    }
-    if (ns && ne) CK(cudaEventRecord(ctx->ev_fork, st));  // fork point: everything both item kinds depend on is queued
-    if (ns) {
-      k_item_msgs<<<nblk(ns, 128), 128, 0, st>>>(v, reu, itx, plans, (const ItemRef*)(I + i_refs), ns, false, (uint32_t*)(I + i_msgs));
+    if (table) {
+      // utxo_validation.rs:282-309 accepts ANY transaction whose scripts execute successfully: a non-standard spend must not
+      // leave this call undecided, and only the library can read the entries it was populated with
+      unsigned long long* cnt = table->counters + 4;
+      unsigned long long n_vm = 0;
+      CK(cudaMemsetAsync(cnt, 0, 8, st));
+      k_count_status<<<nblk(nt, 256), 256, 0, st>>>(dres, (uint32_t)nt, KGV_TX_NEEDS_HOST_VM, cnt);
       CK(cudaGetLastError());
       ctx->launches++;
-      STAGE("msgs schnorr");
-      rc = kgv_launch_verify(ctx, I + i_pks, I + i_msgs, I + i_sigs, ns, I + i_sts, false);
-      if (rc) return rc;
-      STAGE("verify schnorr");
-    }
-    if (ne) {
-      // with both kinds present the ECDSA items run on the side stream so the two (often sub-wave) verify
-      // launches share the SMs instead of queueing behind each other
-      const bool fork = ns != 0 && !kgv_debug_on();
-      cudaStream_t se = fork ? ctx->aux_stream : st;
-      if (fork) CK(cudaStreamWaitEvent(se, ctx->ev_fork, 0));
-      k_item_msgs<<<nblk(ne, 128), 128, 0, se>>>(v, reu, itx, plans, (const ItemRef*)(I + i_refe), ne, true, (uint32_t*)(I + i_msge));
-      CK(cudaGetLastError());
-      ctx->launches++;
-      STAGE("msgs ecdsa");
-      rc = kgv_launch_verify(ctx, I + i_pke, I + i_msge, I + i_sige, ne, I + i_ste, true, se, true);
-      if (rc) return rc;
-      if (fork) {
-        CK(cudaEventRecord(ctx->ev_join, se));
-        CK(cudaStreamWaitEvent(st, ctx->ev_join, 0));
+      CK(cudaMemcpyAsync(&n_vm, cnt, 8, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      if (n_vm) {
+        rc = kgv_host_vm_resolve(ctx, batch, d, dent, dres);
+        if (rc) return rc;
       }
-      STAGE("verify ecdsa");
     }
-    k_resolve<<<nblk(ni, 128), 128, 0, st>>>(v, ni, itx, dres, plans, I + i_sts, I + i_ste, ierr);
-    CK(cudaGetLastError());
-    STAGE("resolve");
-    k_tx_finalize<<<nblk(nt, 128), 128, 0, st>>>(v, (uint32_t)nt, ierr, dres);
-    CK(cudaGetLastError());
-    ctx->launches += 2;
   }
   if (kgv_ptr_is_device(results)) {
     CK(cudaMemcpyAsync(results, dres, nt * sizeof(kgv_tx_result), cudaMemcpyDeviceToDevice, st));
@@ -848,19 +831,19 @@ static int validate_core(kgv_ctx* ctx, kgv_utxo_table* table, const kgv_tx_batch
 extern "C" int kgv_validate_populated(kgv_ctx* ctx, const kgv_tx_batch* batch, uint64_t pov_daa_score, uint32_t flags, const kgv_params* params,
                                       kgv_tx_result* results) {
   if (!ctx) return KGV_ERR_ARG;
-  std::lock_guard<std::mutex> g(ctx->mu);
+  std::lock_guard<std::recursive_mutex> g(ctx->mu);
   return validate_core(ctx, nullptr, batch, pov_daa_score, flags, params, results);
 }
 extern "C" int kgv_validate_txs(kgv_ctx* ctx, kgv_utxo_table* t, const kgv_tx_batch* batch, uint64_t pov_daa_score, uint32_t flags, const kgv_params* params,
                                 kgv_tx_result* results) {
   if (!ctx || !t) return KGV_ERR_ARG;
-  std::lock_guard<std::mutex> g(ctx->mu);
+  std::lock_guard<std::recursive_mutex> g(ctx->mu);
   return validate_core(ctx, t, batch, pov_daa_score, flags, params, results);
 }
 
 extern "C" int kgv_utxo_apply_accepted(kgv_ctx* ctx, kgv_utxo_table* t, const kgv_tx_batch* batch, const uint8_t* accept, uint64_t pov_daa_score) {
   if (!ctx || !t) return KGV_ERR_ARG;
-  std::lock_guard<std::mutex> g(ctx->mu);
+  std::lock_guard<std::recursive_mutex> g(ctx->mu);
   if (!batch || (batch->n_txs && !accept)) { ctx->err = "null argument"; return KGV_ERR_ARG; }
   if (batch->n_txs == 0) return KGV_OK;
   CK(cudaSetDevice(ctx->device));
@@ -898,7 +881,7 @@ extern "C" int kgv_utxo_apply_accepted(kgv_ctx* ctx, kgv_utxo_table* t, const kg
 extern "C" int kgv_muhash_txs(kgv_ctx* ctx, kgv_utxo_table* table, const kgv_tx_batch* batch, const uint8_t* accept, uint64_t pov_daa_score,
                               uint8_t* numerator384, uint8_t* denominator384) {
   if (!ctx) return KGV_ERR_ARG;
-  std::lock_guard<std::mutex> g(ctx->mu);
+  std::lock_guard<std::recursive_mutex> g(ctx->mu);
   if (!batch || !numerator384 || !denominator384 || (batch->n_txs && !accept)) { ctx->err = "null argument"; return KGV_ERR_ARG; }
   if (kgv_ptr_is_device(numerator384) != kgv_ptr_is_device(denominator384)) { ctx->err = "outputs must both be host or both be device pointers"; return KGV_ERR_ARG; }
   CK(cudaSetDevice(ctx->device));
@@ -951,7 +934,7 @@ extern "C" int kgv_muhash_txs(kgv_ctx* ctx, kgv_utxo_table* table, const kgv_tx_
 // consensus/core/src/muhash.rs:28-33).  The table is walked in chunks; chunk products are multiplied in a last tree.
 extern "C" int kgv_utxo_muhash(kgv_ctx* ctx, kgv_utxo_table* t, uint8_t* numerator384) {
   if (!ctx || !t) return KGV_ERR_ARG;
-  std::lock_guard<std::mutex> g(ctx->mu);
+  std::lock_guard<std::recursive_mutex> g(ctx->mu);
   if (!numerator384) { ctx->err = "null argument"; return KGV_ERR_ARG; }
   CK(cudaSetDevice(ctx->device));
   const uint64_t slots = t->mask + 1;
@@ -989,3 +972,5 @@ extern "C" int kgv_utxo_muhash(kgv_ctx* ctx, kgv_utxo_table* t, uint8_t* numerat
   uint8_t den_host[384];
   return kgv_mu_reduce(ctx, 0, n_chunks, numerator384, den_host);
 }
+
+#include "kgv_replay_impl.cuh"

@@ -308,3 +308,68 @@ def entries_to_arrays(entries):
         arr[i]["script_off"], arr[i]["script_len"] = len(arena), len(e["script"])
         arena.extend(e["script"])
     return arr, np.frombuffer(bytes(arena) + bytes(8), dtype=np.uint8).copy()
+
+
+# ----------------------------------------------------------------------------------------------------
+# fast generator (tools/simgen/kgv_simgen.cpp): the same shapes, ~100x faster, emitted directly in the flat batch layout
+# ----------------------------------------------------------------------------------------------------
+class FastDag:
+    """Seeded C++ generator of a linearised chain of blocks of signed transactions (configs 1, 3, 4, 5 of BASELINE.json at
+    their stated sizes).  generate(n_blocks, tpb) appends blocks; take() returns everything emitted since the last take()
+    as (TxBatch, block_first_tx (n+1,), pov (n,)) and starts a new batch (spendable outputs carry over)."""
+
+    def __init__(self, seed=0x6B61737061, n_keys=1024, n_nonces=4096, storage_mass_parameter=DEFAULT_STORAGE_MASS_PARAMETER,
+                 coinbase_maturity=DEFAULT_COINBASE_MATURITY, mix=(1.0, 0.0, 0.0, 0.0), frac_two_inputs=0.5, frac_invalid=0.0,
+                 coinbase_outputs=8, subsidy=50_000_000_000):
+        import ctypes
+        import os
+        import subprocess
+        here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        src = os.path.join(here, "tools", "simgen", "kgv_simgen.cpp")
+        lib = os.path.join(here, "tools", "simgen", "libkgv_simgen.so")
+        if not os.path.exists(lib) or os.path.getmtime(lib) < os.path.getmtime(src):
+            subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", lib, src], check=True, capture_output=True)
+        self._ct = ctypes
+        self._lib = ctypes.CDLL(lib)
+        self._lib.sg_create.restype = ctypes.c_void_p
+        keys = W.ScalarPointPool(n_keys, seed, b"sim-keys")
+        nonces = W.ScalarPointPool(n_nonces, seed, b"sim-nonces")
+        self.keys, self.nonces = keys, nonces
+        self.C, self.maturity = storage_mass_parameter, coinbase_maturity
+
+        class Cfg(ctypes.Structure):
+            _fields_ = [("seed", ctypes.c_uint64), ("n_keys", ctypes.c_uint32), ("n_nonces", ctypes.c_uint32), ("smp", ctypes.c_uint64), ("maturity", ctypes.c_uint64),
+                        ("mix", ctypes.c_double * 4), ("f2", ctypes.c_double), ("finv", ctypes.c_double), ("cbo", ctypes.c_uint32), ("pad_", ctypes.c_uint32),
+                        ("subsidy", ctypes.c_uint64)]
+        cfg = Cfg(seed, n_keys, n_nonces, storage_mass_parameter, coinbase_maturity, (ctypes.c_double * 4)(*[float(m) for m in mix]), frac_two_inputs, frac_invalid,
+                  coinbase_outputs, 0, subsidy)
+        be = lambda ints: b"".join(int(x).to_bytes(32, "big") for x in ints)
+        self._h = ctypes.c_void_p(self._lib.sg_create(ctypes.byref(cfg), be(keys.scalars), b"".join(keys.xs), be(nonces.scalars),
+                                                      be(pow(k, -1, N) for k in nonces.scalars), b"".join(nonces.xs)))
+
+    def close(self):
+        if self._h:
+            self._lib.sg_destroy(self._h)
+            self._h = None
+
+    def generate(self, n_blocks, txs_per_block):
+        self._lib.sg_generate(self._h, int(n_blocks), int(txs_per_block))
+
+    def counts(self):
+        c = (self._ct.c_uint64 * 8)()
+        self._lib.sg_counts(self._h, c)
+        return dict(zip(("n_txs", "n_inputs", "n_outputs", "n_bytes", "n_blocks", "n_signatures", "n_invalid", "n_utxos"), (int(x) for x in c)))
+
+    def take(self):
+        from .txbatch import INPUT_DTYPE, OUTPUT_DTYPE, TX_DTYPE, TxBatch
+        c = self.counts()
+        txs = np.zeros(c["n_txs"], dtype=TX_DTYPE)
+        ins = np.zeros(c["n_inputs"], dtype=INPUT_DTYPE)
+        outs = np.zeros(c["n_outputs"], dtype=OUTPUT_DTYPE)
+        arena = np.zeros(c["n_bytes"] + 16, dtype=np.uint8)
+        first = np.zeros(c["n_blocks"] + 1, dtype=np.uint32)
+        pov = np.zeros(c["n_blocks"], dtype=np.uint64)
+        p = lambda a: a.ctypes.data_as(self._ct.c_void_p)
+        self._lib.sg_copy(self._h, p(txs), p(ins), p(outs), p(arena), p(first), p(pov))
+        self._lib.sg_reset_output(self._h)
+        return TxBatch(txs, ins, outs, None, arena), first, pov

@@ -117,3 +117,18 @@ class State:
         if self.h:
             self.lib.ok_state_free(self.h)
             self.h = None
+
+
+def state_replay(state, b, block_first_tx, block_pov, p, block_flags=None, threads=4):
+    """ok_state_replay: the whole window in one call. Returns (results, accept)."""
+    ob = ok_batch(b)
+    res = np.zeros(len(b.txs), dtype=RESULT_DTYPE)
+    acc = np.zeros(len(b.txs), dtype=np.uint8)
+    first = np.ascontiguousarray(block_first_tx, dtype=np.uint32)
+    pov = np.ascontiguousarray(block_pov, dtype=np.uint64)
+    fl = None if block_flags is None else np.ascontiguousarray(block_flags, dtype=np.uint32)
+    vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    rc = state.lib.ok_state_replay(state.h, ctypes.byref(ob), vp(first), vp(pov), None if fl is None else vp(fl), ctypes.c_size_t(len(pov)), ctypes.byref(p), vp(res), vp(acc),
+                                   int(threads))
+    assert rc == 0, "UtxoAlgebraError in the oracle replay"
+    return res, acc

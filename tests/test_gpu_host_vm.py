@@ -88,3 +88,62 @@ def test_nonstandard_scripts_via_host_engine(gpu_ctx, oracle):
         assert res[i]["status"] in (0, 9)
         names.add(SCRIPT_ERR_NAMES[got])
     assert {"Ok", "EvalFalse", "VerifyError", "NullFail", "UnsatisfiedLockTime"} <= names, names
+
+
+def _load_entries(us, txs, ents):
+    """puts the entries spent by `txs` into the GPU UTXO set"""
+    from rusty_kaspa_b200.simgen import entries_to_arrays
+    keys = np.frombuffer(b"".join(i["txid"] + int(i["index"]).to_bytes(4, "little") for t in txs for i in t["inputs"]), dtype=np.uint8).reshape(-1, 36)
+    arr, arena = entries_to_arrays([e for es in ents for e in es])
+    us.apply_diff(add_keys36=keys, add_entries=arr, add_bytes=arena)
+
+
+def test_nonstandard_spends_through_the_table_path(gpu_ctx, oracle):
+    """utxo_validation.rs:282-309 accepts any transaction whose scripts execute successfully: kgv_validate_txs (table-backed) must
+    decide non-standard spends itself (never KGV_TX_NEEDS_HOST_VM), including script public keys far longer than a slot's inline
+    68 bytes (kept in the overflow arena; the old stride-limited lookup truncated them), and
+    validate_transactions_with_muhash_in_parallel must fold the valid ones into the MuHash.  Same through kgv_replay_window."""
+    from rusty_kaspa_b200 import GpuUtxoSet, MuHash
+    from rusty_kaspa_b200.replay import DagReplayer, REPLAY_ACCEPT_COINBASE
+    from rusty_kaspa_b200.simgen import SUBNET_COINBASE
+    txs, ents = _custom_spends(96, seed=9)
+    # a 400-byte script public key: <pk> CHECKSIGVERIFY, 30 x (push 10 bytes, DROP), OP_1
+    dag = SimDag(seed=77, n_keys=8, n_nonces=16)
+    for j in range(6):
+        pk = dag.keys.xs[j]
+        spk = bytes([0x20]) + pk + bytes([0xAD]) + b"".join(bytes([0x0A]) + bytes([j + 1] * 10) + bytes([0x75]) for _ in range(30)) + bytes([0x51])
+        assert len(spk) > 300
+        entry = {"amount": 10**9, "spk_version": 0, "script": spk, "block_daa_score": 5, "is_coinbase": False}
+        tx = {"version": 0, "inputs": [{"txid": bytes([0xC0 + j]) * 32, "index": j, "sigscript": b"", "sequence": 0, "sig_op_count": 1}],
+              "outputs": [{"value": 10**9 - 1, "spk_version": 0, "script": bytes([0x20]) + pk + bytes([0xAC])}], "lock_time": 0,
+              "subnetwork_id": SUBNET_NATIVE, "gas": 0, "payload": b"", "mass": 0}
+        msg = sighash_all(tx, [entry], 0, False)
+        sig = dag._sign(j, msg if j != 3 else bytes(32), False)  # one of them carries a wrong signature
+        tx["inputs"][0]["sigscript"] = bytes([0x41]) + sig + bytes([0x01])
+        txs.append(tx); ents.append([entry])
+    pb = build_batch(txs, ents)
+    exp = [script_execute(pb, i, 0, oracle_verdicts(oracle, pb)) for i in range(len(txs))]
+    assert exp[-6:] == [0, 0, 0, 25, 0, 0] and 0 in exp[:96] and any(e != 0 for e in exp[:96])
+    tv = TransactionValidator(gpu_ctx, Params(coinbase_maturity=0, storage_mass_parameter=0))
+    us = GpuUtxoSet(gpu_ctx, 1 << 12)
+    _load_entries(us, txs, ents)
+    b = build_batch(txs)
+    res, mu = tv.validate_transactions_with_muhash_in_parallel(us, b, 1000, flags=2)
+    assert not (res["status"] == 11).any()
+    got = [0 if r["status"] == 0 else int(r["script_err"]) for r in res]
+    assert got == exp
+    acc = (res["status"] == 0).astype(np.uint8)
+    assert mu.numerator == MuHash.from_transactions(gpu_ctx, pb, acc, 1000).numerator and acc[-1] == 1 and acc[-3] == 0
+    us.close()
+    # the same spends as one block of a replay window (tx 0 = coinbase)
+    cb = {"version": 0, "inputs": [], "outputs": [{"value": 5, "spk_version": 0, "script": bytes([0x51])}], "lock_time": 0, "subnetwork_id": SUBNET_COINBASE,
+          "gas": 0, "payload": b"x", "mass": 0}
+    r = DagReplayer(gpu_ctx, Params(coinbase_maturity=0, storage_mass_parameter=0), 1 << 12)
+    _load_entries(r.us, txs, ents)
+    for t in txs:  # mass check is on in the replay: commit the storage mass the context rules expect (C = 0 -> 0)
+        t["mass"] = 0
+    out = r.replay_windowed([([cb] + txs, 1000, REPLAY_ACCEPT_COINBASE)])[0]
+    assert r.last_stats["n_host_vm"] == len(txs)
+    assert [0 if x["status"] == 0 else int(x["script_err"]) for x in out[1:]] == exp and out[0]["status"] == 12
+    assert r.us.count() == 1 + int(acc.sum()) + (len(txs) - int(acc.sum()))  # coinbase output + one output per accepted tx + unspent entries of rejected txs
+    r.close()

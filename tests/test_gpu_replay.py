@@ -114,3 +114,70 @@ def test_virtual_chain_of_the_simpa_dag_reproduces_the_reference_headers(gpu_ctx
     if "5000" in fixture:
         assert len(chain) > 1500 and n_txs > 4500
     us.close()
+
+
+def _fast_windows(n_blocks, tpb, window, **kw):
+    from rusty_kaspa_b200 import simgen
+    g = simgen.FastDag(**kw)
+    out, done = [], 0
+    while done < n_blocks:
+        k = min(window, n_blocks - done)
+        g.generate(k, tpb)
+        out.append(g.take())
+        done += k
+    return g, out
+
+
+def test_replay_of_150k_generated_transactions_matches_the_cpu_path(gpu_ctx, oracle):
+    """BASELINE's "bit-exact on a 100k-tx simpa DAG" at its stated size: a generated simpa-shaped chain (C++ generator, 1000 blocks, mixed
+    1-/2-input P2PK Schnorr transactions, ~2 % invalid of every class) is replayed in order by kgv_replay_window (128-block windows) and by
+    the oracle's restated CPU path (ok_state_replay); every per-transaction verdict, the accepted set and the final UTXO-set digest agree."""
+    from rusty_kaspa_b200.replay import DagReplayer, REPLAY_BLOCK_DTYPE
+    g, wins = _fast_windows(1000, 170, 128, seed=99, n_keys=512, n_nonces=2048, coinbase_maturity=30, frac_invalid=0.02, coinbase_outputs=16)
+    prm = Params(coinbase_maturity=30, storage_mass_parameter=g.C)
+    op = oracle_tx.params(coinbase_maturity=30, storage_mass_parameter=g.C)
+    r = DagReplayer(gpu_ctx, prm, 1 << 20)
+    ost = oracle_tx.State(oracle)
+    n_tx = n_acc = 0
+    seen = set()
+    for b, first, pov in wins:
+        arr = np.zeros(len(pov), dtype=REPLAY_BLOCK_DTYPE)
+        arr["first_tx"], arr["n_txs"], arr["pov_daa_score"], arr["flags"] = first[:-1], np.diff(first), pov, 1
+        got, acc = r.replay_window(b, arr, want_accept=True)
+        exp, eacc = oracle_tx.state_replay(ost, b, first, pov, op, threads=16)
+        for f in ("status", "script_err"):
+            assert (got[f] == exp[f]).all(), f
+        ok = exp["status"] == 0
+        assert (got["fee"][ok] == exp["fee"][ok]).all() and (acc == eacc).all()
+        n_tx += len(b.txs) - len(pov); n_acc += int(acc.sum()) - len(pov)
+        seen |= {(int(s), int(e)) for s, e in zip(got["status"], got["script_err"])}
+    c = g.counts()
+    assert n_tx >= 100_000 and n_acc == n_tx - c["n_invalid"], (n_tx, n_acc, c)
+    assert r.us.count() == ost.count() == c["n_utxos"] and r.us.digest() == ost.digest()
+    assert len(seen) >= 6, seen
+    r.close(); ost.close(); g.close()
+
+
+def test_replay_block_flags_follow_the_reference_semantics(gpu_ctx, oracle):
+    """Per-block flags of kgv_replay_window against the oracle: merged blocks whose coinbase is NOT accepted (only the selected parent's is,
+    utxo_validation.rs:116-121), SkipScriptChecks blocks (:138-140: a bad signature is accepted there), validate-only blocks (:219-225: verdicts
+    but no state change), on a mixed-class chain whose later blocks then miss the outputs that were never created."""
+    from rusty_kaspa_b200.replay import DagReplayer, REPLAY_BLOCK_DTYPE
+    g, wins = _fast_windows(160, 40, 40, seed=7, n_keys=64, n_nonces=256, coinbase_maturity=3, mix=(0.4, 0.2, 0.2, 0.2), frac_invalid=0.1, coinbase_outputs=12)
+    prm = Params(coinbase_maturity=3, storage_mass_parameter=g.C)
+    op = oracle_tx.params(coinbase_maturity=3, storage_mass_parameter=g.C)
+    r = DagReplayer(gpu_ctx, prm, 1 << 16)
+    ost = oracle_tx.State(oracle)
+    rng = np.random.default_rng(5)
+    seen_flags, skipped_bad_sig = set(), 0
+    for b, first, pov in wins:
+        flags = rng.choice([1, 1, 1, 0, 3, 4, 5, 2], size=len(pov)).astype(np.uint32)
+        arr = np.zeros(len(pov), dtype=REPLAY_BLOCK_DTYPE)
+        arr["first_tx"], arr["n_txs"], arr["pov_daa_score"], arr["flags"] = first[:-1], np.diff(first), pov, flags
+        got, acc = r.replay_window(b, arr, want_accept=True)
+        exp, eacc = oracle_tx.state_replay(ost, b, first, pov, op, block_flags=flags, threads=8)
+        assert (got["status"] == exp["status"]).all() and (got["script_err"] == exp["script_err"]).all() and (acc == eacc).all()
+        seen_flags |= set(int(f) for f in flags)
+        assert r.us.count() == ost.count()
+    assert r.us.digest() == ost.digest() and seen_flags >= {0, 1, 2, 3, 4, 5}
+    r.close(); ost.close(); g.close()
