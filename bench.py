@@ -657,7 +657,7 @@ def main():
     ap.add_argument("--n", type=int, default=N_DEFAULT, help="triples per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--replay-blocks", type=int, default=10000, help="blocks of the DAG-replay leg (BASELINE configs[2]: 10k blocks; 0 = skip)")
-    ap.add_argument("--replay-window", type=int, default=256, help="blocks per kgv_replay_window call")
+    ap.add_argument("--replay-window", type=int, default=1024, help="blocks per kgv_replay_window call")
     ap.add_argument("--tx-window", type=int, default=32768, help="transactions in the secondary txs-validated/s measurement (0 = skip)")
     args = ap.parse_args()
     _quiet_stdout()

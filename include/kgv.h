@@ -242,6 +242,46 @@ int kgv_validate_txs(kgv_ctx* ctx, kgv_utxo_table* t, const kgv_tx_batch* batch,
 int kgv_utxo_apply_accepted(kgv_ctx* ctx, kgv_utxo_table* t, const kgv_tx_batch* batch, const uint8_t* accept, uint64_t pov_daa_score);
 
 /* ------------------------------------------------------------------------------------------------
+ * Multi-GPU (SURVEY.md §8b kgv_shard_allgather, §8e): signature batches shard across GPUs as contiguous ranges, one context (and
+ * normally one process) per GPU; the only exchange step of the path is "every rank ends up with every shard's verdicts".
+ * The reference has no counterpart (rayon on one host, utxo_validation.rs:269-277).
+ *
+ * A communicator binds a context to its place among n_ranks and offers two transports:
+ *   NCCL  (id != NULL): kgv_shard_allgather = ncclAllGather on the context's stream.  libnccl.so.2 is resolved at run time;
+ *         KGV_ERR_NCCL if it is missing.  The 128-byte id comes from kgv_comm_unique_id on rank 0 and reaches the other ranks
+ *         through whatever the host uses (MPI, TCP, torch.distributed).
+ *   peer  (slice_capacity_bytes != 0): every rank owns receive buffers its peers map (kgv_comm_export -> host exchanges the
+ *         handles -> kgv_comm_import; or kgv_comm_connect_local for several contexts of ONE process).  kgv_shard_publish_* is the
+ *         PRODUCING kernel writing its shard straight into every peer over NVLink and raising an epoch flag there;
+ *         kgv_shard_wait waits on local flags.  No collective, no host rendezvous.  Every rank must publish the same sequence
+ *         of epochs and wait for epoch e before publishing e + 1.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct kgv_comm kgv_comm;
+#define KGV_COMM_ID_BYTES 128
+#define KGV_COMM_HANDLE_BYTES 64
+int kgv_comm_unique_id(uint8_t id[KGV_COMM_ID_BYTES]);
+int kgv_comm_create(kgv_ctx* ctx, int n_ranks, int rank, const uint8_t* id /* NULL: no NCCL */, size_t slice_capacity_bytes /* 0: no peer buffers */,
+                    kgv_comm** out);
+void kgv_comm_destroy(kgv_comm* comm);
+int kgv_comm_export(kgv_comm* comm, uint8_t handle[KGV_COMM_HANDLE_BYTES]);
+int kgv_comm_import(kgv_comm* comm, const uint8_t* handles /* n_ranks * KGV_COMM_HANDLE_BYTES, indexed by rank */);
+int kgv_comm_connect_local(kgv_comm* const* comms, int n /* comms[i] has rank i */);
+/* all_shards[r * nbytes_per_rank ..) = rank r's local_shard, on every rank (device pointers; in place allowed as in NCCL). */
+int kgv_shard_allgather(kgv_ctx* ctx, kgv_comm* comm, const uint8_t* local_shard, size_t nbytes_per_rank, uint8_t* all_shards);
+/* peer transport.  publish_bitmap: kgv_status_to_bitmap fused with the transfer (status: n device bytes; the shard is 4*ceil(n/32) bytes);
+ * publish_bytes: a raw device array.  *epoch_out names the exchange.  wait: enqueue the wait for `epoch` and (all_shards != NULL)
+ * copy the n_ranks received shards, nbytes_per_rank each, into one contiguous device array. */
+int kgv_shard_publish_bitmap(kgv_ctx* ctx, kgv_comm* comm, const uint8_t* status, size_t n, uint64_t* epoch_out);
+int kgv_shard_publish_bytes(kgv_ctx* ctx, kgv_comm* comm, const uint8_t* src, size_t nbytes, uint64_t* epoch_out);
+int kgv_shard_wait(kgv_ctx* ctx, kgv_comm* comm, uint64_t epoch, size_t nbytes_per_rank, uint8_t* all_shards);
+/* Shard the signature checks of this context's validation calls (kgv_replay_window, kgv_validate_*) over the communicator's
+ * ranks (BASELINE configs[4]): every rank runs the same call on the same batch against its own replica of the UTXO table;
+ * the candidate (signature, key) pairs are split into n_ranks contiguous ranges, each rank verifies one range and the verdicts
+ * are exchanged (peer transport if connected, else NCCL) before the scripts are resolved - identically on every rank.
+ * comm == NULL switches sharding off. */
+int kgv_set_sharding(kgv_ctx* ctx, kgv_comm* comm);
+
+/* ------------------------------------------------------------------------------------------------
  * DAG replay: calculate_utxo_state / verify_expected_utxo_state (utxo_validation.rs:110-173,182-228) for a WINDOW of
  * blocks as one device-resident call; the loop simpa times (simpa/src/main.rs:454-460).
  *
@@ -267,6 +307,8 @@ typedef struct {
   uint64_t n_accepted;   /* accepted non-coinbase transactions */
   uint64_t n_sig_checks; /* candidate (signature, key) pairs verified in the pre-check */
   uint64_t n_host_vm;    /* transactions decided by the host script engine */
+  float pre_check_ms;    /* device time of the batched script pre-check (tx ids, window map, populate, sighash, verify, resolve) */
+  float in_order_ms;     /* device time of the in-order pass */
 } kgv_replay_stats;
 /* results: n_txs records (host or device memory): the UTXO-context verdict when the context rules fail, else the script
  * verdict (KGV_TX_SKIPPED_COINBASE for coinbases).  accept (may be NULL): n_txs bytes, 1 = folded into the table.

@@ -39,6 +39,17 @@ SYMBOLS = [
     ("kgv_utxo_digest", _c.c_int, [_c.c_void_p, _c.c_void_p, _u8p]),
     ("kgv_validate_txs", _c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_uint64, _c.c_uint32, _c.c_void_p, _u8p]),
     ("kgv_utxo_apply_accepted", _c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _u8p, _c.c_uint64]),
+    ("kgv_comm_unique_id", _c.c_int, [_u8p]),
+    ("kgv_comm_create", _c.c_int, [_c.c_void_p, _c.c_int, _c.c_int, _u8p, _c.c_size_t, _c.POINTER(_c.c_void_p)]),
+    ("kgv_comm_destroy", None, [_c.c_void_p]),
+    ("kgv_comm_export", _c.c_int, [_c.c_void_p, _u8p]),
+    ("kgv_comm_import", _c.c_int, [_c.c_void_p, _u8p]),
+    ("kgv_comm_connect_local", _c.c_int, [_c.POINTER(_c.c_void_p), _c.c_int]),
+    ("kgv_shard_allgather", _c.c_int, [_c.c_void_p, _c.c_void_p, _u8p, _c.c_size_t, _u8p]),
+    ("kgv_shard_publish_bitmap", _c.c_int, [_c.c_void_p, _c.c_void_p, _u8p, _c.c_size_t, _c.POINTER(_c.c_uint64)]),
+    ("kgv_shard_publish_bytes", _c.c_int, [_c.c_void_p, _c.c_void_p, _u8p, _c.c_size_t, _c.POINTER(_c.c_uint64)]),
+    ("kgv_shard_wait", _c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_uint64, _c.c_size_t, _u8p]),
+    ("kgv_set_sharding", _c.c_int, [_c.c_void_p, _c.c_void_p]),
     ("kgv_replay_window", _c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _u8p, _c.c_size_t, _c.c_void_p, _u8p, _u8p, _c.c_void_p]),
     ("kgv_merkle_roots", _c.c_int, [_c.c_void_p, _u8p, _u8p, _c.c_uint32, _u8p]),
     ("kgv_block_hash_merkle_roots", _c.c_int, [_c.c_void_p, _c.c_void_p, _u8p, _c.c_uint32, _u8p]),

@@ -21,6 +21,7 @@ struct kgv_ctx {
   cudaStream_t own_stream = nullptr;
   cudaStream_t aux_stream = nullptr;              // fork/join side stream: ECDSA items verify beside the Schnorr items
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_time[3] = {};                    // kgv_replay_window: phase timing for kgv_replay_stats
   cudaEvent_t ev_chunk[32] = {};                  // upload-complete events of the chunked host-pointer verify path
   cudaStream_t stream = nullptr;
   uint32_t* gtab = nullptr;     // [2][65536][16] u32: v*G and v*2^128*G, affine
@@ -38,6 +39,7 @@ struct kgv_ctx {
   size_t d_replay_cap = 0;
   uint8_t* d_mu = nullptr;      // MuHash element arrays, product-tree levels and wide-product scratch rows
   size_t d_mu_cap = 0;
+  struct kgv_comm* shard_comm = nullptr;  // kgv_set_sharding: signature checks of the validation calls are split over its ranks
   uint64_t launches = 0;
   int resident_blocks = 148 * KGV_BLOCKS_PER_SM;  // verification kernels: blocks that fit the device at once (persistent grid)
   std::recursive_mutex mu;  // recursive: the host-VM resolution inside a validation call re-enters the ABI (kgv_sighash, kgv_*_verify)
@@ -75,3 +77,9 @@ int kgv_mu_reduce(kgv_ctx* ctx, size_t n_den, size_t n_num, uint8_t* out_num384,
 
 // ---- shared pieces of the validation path (kgv_validate.cu) ----
 struct kgv_utxo_table;
+
+// ---- multi-GPU exchange used by the sharded script phase (kgv_comm.cu) ----
+// Every rank contributes `per` bytes at buf + rank * per (device memory, n_ranks * per bytes in all); on return (stream order)
+// buf holds all ranks' contributions.  Peer transport if the communicator is connected, else NCCL (in place).
+int kgv_comm_exchange_slices(kgv_ctx* ctx, struct kgv_comm* c, uint8_t* buf, size_t per);
+int kgv_comm_ranks(const struct kgv_comm* c, int* rank);

@@ -296,12 +296,21 @@ int kgv_ptr_is_device(const void* p) {
   return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
 
+// Per-call device buffers grow through the stream-ordered allocator (cudaMallocAsync / cudaFreeAsync on the context's stream):
+// cudaFree would synchronise the WHOLE device, which deadlocks a process that drives several contexts of one device whose
+// kernels wait for each other (the peer-exchange wait kernels of kgv_comm.cu), and stalls unrelated streams everywhere else.
 int kgv_reserve(kgv_ctx* ctx, uint8_t** buf, size_t* cap, size_t need) {
   if (*cap >= need) return KGV_OK;
-  if (*buf) { CK(cudaStreamSynchronize(ctx->stream)); CK(cudaFree(*buf)); *buf = nullptr; *cap = 0; }
+  if (*buf) {
+    // work of this call already queued on the side stream may still read the old buffer
+    CK(cudaEventRecord(ctx->ev_join, ctx->aux_stream));
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+    CK(cudaFreeAsync(*buf, ctx->stream));
+    *buf = nullptr; *cap = 0;
+  }
   size_t want = need + need / 4 + 4096;
-  cudaError_t e = cudaMalloc((void**)buf, want);
-  if (e != cudaSuccess) { ctx->err = std::string("cudaMalloc failed: ") + cudaGetErrorString(e); (void)cudaGetLastError(); return KGV_ERR_NOMEM; }
+  cudaError_t e = cudaMallocAsync((void**)buf, want, ctx->stream);
+  if (e != cudaSuccess) { ctx->err = std::string("cudaMallocAsync failed: ") + cudaGetErrorString(e); (void)cudaGetLastError(); *buf = nullptr; return KGV_ERR_NOMEM; }
   *cap = want;
   return KGV_OK;
 }
@@ -355,14 +364,11 @@ extern "C" void kgv_destroy(kgv_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   if (ctx->gtab) cudaFree(ctx->gtab);
-  if (ctx->d_in) cudaFree(ctx->d_in);
-  if (ctx->d_out) cudaFree(ctx->d_out);
-  if (ctx->d_batch) cudaFree(ctx->d_batch);
-  if (ctx->d_scratch) cudaFree(ctx->d_scratch);
-  if (ctx->d_mu) cudaFree(ctx->d_mu);
-  if (ctx->d_work) cudaFree(ctx->d_work);
-  if (ctx->d_replay) cudaFree(ctx->d_replay);
+  for (uint8_t* b : {ctx->d_in, ctx->d_out, ctx->d_batch, ctx->d_scratch, ctx->d_mu, ctx->d_work, ctx->d_replay})
+    if (b) cudaFreeAsync(b, ctx->own_stream);
+  cudaStreamSynchronize(ctx->own_stream);
   for (cudaEvent_t e : ctx->ev_chunk) if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : ctx->ev_time) if (e) cudaEventDestroy(e);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);

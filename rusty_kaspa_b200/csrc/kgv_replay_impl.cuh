@@ -109,6 +109,26 @@ __global__ void k_replay_pre_status(BatchView b, uint32_t n_txs, const kgv_repla
 // ---------------------------------------------------------------------------------------------
 // the in-order pass: ONE CTA, blocks in sequence
 // ---------------------------------------------------------------------------------------------
+// per-block ranges, computed in parallel before the walk so that the in-order kernel never chases tx records to find them
+struct ReplayRange {
+  uint32_t t0, t1, i0, i1, o0, o1, flags, pad_;
+  uint64_t pov;
+};
+__global__ void k_replay_ranges(const kgv_replay_block* __restrict__ blocks, uint32_t n_blocks, const kgv_tx* __restrict__ txs, ReplayRange* __restrict__ out) {
+  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n_blocks) return;
+  kgv_replay_block bl = blocks[b];
+  ReplayRange r;
+  r.t0 = bl.first_tx; r.t1 = bl.first_tx + bl.n_txs; r.flags = bl.flags; r.pad_ = 0; r.pov = bl.pov_daa_score;
+  r.i0 = r.i1 = r.o0 = r.o1 = 0;
+  if (bl.n_txs) {
+    const kgv_tx& tf = txs[r.t0];
+    const kgv_tx& tl = txs[r.t1 - 1];
+    r.i0 = tf.first_input; r.i1 = tl.first_input + tl.n_inputs; r.o0 = tf.first_output; r.o1 = tl.first_output + tl.n_outputs;
+  }
+  out[b] = r;
+}
+
 struct ReplayArgs {
   TableView t;
   BatchView b;              // b.entries = dent (written here: the entry every input finds AT ITS BLOCK'S POSITION)
@@ -118,7 +138,7 @@ struct ReplayArgs {
   const uint64_t* ids;
   const uint32_t* itx;
   const uint32_t* otx;
-  const kgv_replay_block* blocks;
+  const ReplayRange* ranges;
   uint32_t n_blocks;
   kgv_params prm;
   const kgv_tx_result* pre; // script verdicts of the pre-check
@@ -127,17 +147,63 @@ struct ReplayArgs {
   unsigned long long* stats; // [0] accepted transactions
 };
 
+// L2 prefetch of the 128-byte lines covering [p, p + bytes), dealt to the threads from the TOP of the CTA downwards (the low
+// threads carry the per-input / per-transaction work of the current block)
+__device__ __forceinline__ void prefetch_range(const void* p, size_t bytes, uint32_t rtid, uint32_t nth) {
+  if (!bytes) return;
+  const uintptr_t lo = (uintptr_t)p & ~(uintptr_t)127, hi = (uintptr_t)p + bytes;
+  for (uintptr_t q = lo + 128 * (uintptr_t)rtid; q < hi; q += 128 * (uintptr_t)nth) prefetch_l2((const void*)q);
+}
+
+// The walk is a chain of dependent memory accesses per block (record -> key -> slot -> entry -> verdict -> slot update); left to
+// itself every link is a DRAM miss (~1 us) and a block costs ~20 us.  So the kernel runs a two-block look-ahead entirely with
+// L2 prefetches: while block b is decided, the records of block b+2 (transactions, inputs, outputs, ids, script verdicts) are
+// prefetched by address range, and for block b+1 - whose records are L2 hits by then - the table slots its inputs will probe,
+// the slots its outputs will be inserted into and the script bytes those inserts copy.  The walk itself then only meets L2 hits.
 __global__ void __launch_bounds__(1024, 1) k_replay_inorder(ReplayArgs a) {
-  const uint32_t tid = threadIdx.x, nth = blockDim.x;
+  const uint32_t tid = threadIdx.x, nth = blockDim.x, rtid = nth - 1 - tid;
   __shared__ unsigned long long s_acc;
-  if (tid == 0) s_acc = 0;
+  __shared__ int s_live, s_tomb;  // table counter deltas of this launch (one global atomic at the end instead of one per entry)
+  if (tid == 0) { s_acc = 0; s_live = 0; s_tomb = 0; }
+  auto prefetch_records = [&](uint32_t bi) {
+    if (bi >= a.n_blocks) return;
+    const ReplayRange r = a.ranges[bi];
+    prefetch_range(a.b.txs + r.t0, (size_t)(r.t1 - r.t0) * sizeof(kgv_tx), rtid, nth);
+    prefetch_range(a.b.inputs + r.i0, (size_t)(r.i1 - r.i0) * sizeof(kgv_input), rtid, nth);
+    prefetch_range(a.b.outputs + r.o0, (size_t)(r.o1 - r.o0) * sizeof(kgv_output), rtid, nth);
+    prefetch_range(a.ids + 4 * (size_t)r.t0, (size_t)(r.t1 - r.t0) * 32, rtid, nth);
+    prefetch_range(a.pre + r.t0, (size_t)(r.t1 - r.t0) * sizeof(kgv_tx_result), rtid, nth);
+    prefetch_range(a.itx + r.i0, (size_t)(r.i1 - r.i0) * 4, rtid, nth);
+    prefetch_range(a.otx + r.o0, (size_t)(r.o1 - r.o0) * 4, rtid, nth);
+  };
+  auto prefetch_slots = [&](uint32_t bi) {
+    if (bi >= a.n_blocks) return;
+    const ReplayRange r = a.ranges[bi];
+    for (uint32_t i = r.i0 + rtid; i < r.i1; i += nth) {
+      uint32_t k[9];
+      input_key(k, a.b.inputs[i]);
+      prefetch_l2(&a.t.slots[key_hash(k) & a.t.mask]);
+    }
+    if (!(r.flags & KGV_REPLAY_VERIFY_ONLY))
+      for (uint32_t o = r.o0 + rtid; o < r.o1; o += nth) {
+        const uint32_t ti = a.otx[o];
+        uint32_t k[9];
+#pragma unroll
+        for (int w = 0; w < 4; w++) { uint64_t q = a.ids[4 * (size_t)ti + w]; k[2 * w] = (uint32_t)q; k[2 * w + 1] = (uint32_t)(q >> 32); }
+        k[8] = o - a.b.txs[ti].first_output;
+        prefetch_l2(&a.t.slots[key_hash(k) & a.t.mask]);
+        prefetch_l2(a.b.bytes + a.b.outputs[o].script_off);
+      }
+  };
+  prefetch_records(0);
+  prefetch_records(1);
+  __syncthreads();
+  prefetch_slots(0);
   for (uint32_t bi = 0; bi < a.n_blocks; bi++) {
-    const kgv_replay_block bl = a.blocks[bi];
-    if (bl.n_txs == 0) continue;
-    const kgv_tx& tf = a.b.txs[bl.first_tx];
-    const kgv_tx& tl = a.b.txs[bl.first_tx + bl.n_txs - 1];
-    const uint32_t i0 = tf.first_input, i1 = tl.first_input + tl.n_inputs;
-    const uint32_t o0 = tf.first_output, o1 = tl.first_output + tl.n_outputs;
+    const ReplayRange bl = a.ranges[bi];
+    prefetch_records(bi + 2);
+    if (bl.t1 == bl.t0) { prefetch_slots(bi + 1); continue; }
+    const uint32_t i0 = bl.i0, i1 = bl.i1, o0 = bl.o0, o1 = bl.o1;
     // ---- A: populate from the table as it stands after the previous block (utxo_validation.rs:319-327)
     for (uint32_t i = i0 + tid; i < i1; i += nth) {
       uint32_t k[9];
@@ -159,35 +225,14 @@ __global__ void __launch_bounds__(1024, 1) k_replay_inorder(ReplayArgs a) {
       a.dent[i] = d;
       a.slotp[i] = s;
     }
-    // prefetch what the NEXT block will probe (home slots of its inputs) and what THIS block will insert into
-    if (bi + 1 < a.n_blocks) {
-      const kgv_replay_block nb = a.blocks[bi + 1];
-      if (nb.n_txs) {
-        const kgv_tx& nf = a.b.txs[nb.first_tx];
-        const kgv_tx& nl = a.b.txs[nb.first_tx + nb.n_txs - 1];
-        for (uint32_t i = nf.first_input + tid; i < nl.first_input + nl.n_inputs; i += nth) {
-          uint32_t k[9];
-          input_key(k, a.b.inputs[i]);
-          prefetch_l2(&a.t.slots[key_hash(k) & a.t.mask]);
-        }
-      }
-    }
-    if (!(bl.flags & KGV_REPLAY_VERIFY_ONLY))
-      for (uint32_t o = o0 + tid; o < o1; o += nth) {
-        const uint32_t ti = a.otx[o];
-        uint32_t k[9];
-#pragma unroll
-        for (int w = 0; w < 4; w++) { uint64_t q = a.ids[4 * (size_t)ti + w]; k[2 * w] = (uint32_t)q; k[2 * w + 1] = (uint32_t)(q >> 32); }
-        k[8] = o - a.b.txs[ti].first_output;
-        prefetch_l2(&a.t.slots[key_hash(k) & a.t.mask]);
-      }
+    prefetch_slots(bi + 1);
     __syncthreads();
     // ---- B: context rules and the acceptance decision
-    for (uint32_t ti = bl.first_tx + tid; ti < bl.first_tx + bl.n_txs; ti += nth) {
-      const bool cb = ti == bl.first_tx || tx_is_coinbase(a.b.txs[ti]);
-      kgv_tx_result r = tx_context_rules(a.b, ti, bl.pov_daa_score, KGV_FLAGS_SKIP_SCRIPT_CHECKS, a.prm, cb);
+    for (uint32_t ti = bl.t0 + tid; ti < bl.t1; ti += nth) {
+      const bool cb = ti == bl.t0 || tx_is_coinbase(a.b.txs[ti]);
+      kgv_tx_result r = tx_context_rules(a.b, ti, bl.pov, KGV_FLAGS_SKIP_SCRIPT_CHECKS, a.prm, cb);
       bool acc;
-      if (cb) acc = (ti == bl.first_tx) && (bl.flags & KGV_REPLAY_ACCEPT_COINBASE);
+      if (cb) acc = (ti == bl.t0) && (bl.flags & KGV_REPLAY_ACCEPT_COINBASE);
       else {
         acc = r.status == KGV_TX_OK;
         if (acc && !(bl.flags & KGV_REPLAY_SKIP_SCRIPTS)) {
@@ -195,20 +240,21 @@ __global__ void __launch_bounds__(1024, 1) k_replay_inorder(ReplayArgs a) {
           if (p.status != KGV_TX_OK) { r.status = p.status; r.script_err = p.script_err; r.fail_input = p.fail_input; acc = false; }
         }
       }
-      if (bl.flags & KGV_REPLAY_VERIFY_ONLY) acc = acc && false;
+      if (bl.flags & KGV_REPLAY_VERIFY_ONLY) acc = false;
       a.res[ti] = r;
       a.accept[ti] = acc ? 1 : 0;
       if (acc && !cb) atomicAdd(&s_acc, 1ull);
     }
     __syncthreads();
-    // ---- C: UtxoDiff::add_transaction straight into the table (utxo_diff.rs:233-247)
+    // ---- C: UtxoDiff::add_transaction straight into the table (utxo_diff.rs:233-247).  One CTA: the barrier orders these writes
+    // before the next block's probes, no device-wide fence is needed inside the walk.
     if (!(bl.flags & KGV_REPLAY_VERIFY_ONLY)) {
       for (uint32_t i = i0 + tid; i < i1; i += nth) {
         if (!a.accept[a.itx[i]]) continue;
         UtxoSlot* s = a.slotp[i];
         *(volatile uint32_t*)&s->state = SLOT_TOMB;
-        atomicAdd(&a.t.counters[0], (unsigned long long)-1);
-        atomicAdd(&a.t.counters[1], 1ull);
+        atomicSub(&s_live, 1);
+        atomicAdd(&s_tomb, 1);
       }
       for (uint32_t o = o0 + tid; o < o1; o += nth) {
         const uint32_t ti = a.otx[o];
@@ -219,14 +265,18 @@ __global__ void __launch_bounds__(1024, 1) k_replay_inorder(ReplayArgs a) {
 #pragma unroll
         for (int w = 0; w < 4; w++) { uint64_t q = a.ids[4 * (size_t)ti + w]; k[2 * w] = (uint32_t)q; k[2 * w + 1] = (uint32_t)(q >> 32); }
         k[8] = o - tx.first_output;
-        table_put(a.t, k, out.value, bl.pov_daa_score, out.spk_version, (ti == bl.first_tx || tx_is_coinbase(tx)) ? 1u : 0u, a.b.bytes + out.script_off, out.script_len);
+        table_put<false>(a.t, k, out.value, bl.pov, out.spk_version, (ti == bl.t0 || tx_is_coinbase(tx)) ? 1u : 0u, a.b.bytes + out.script_off, out.script_len, &s_live, &s_tomb);
       }
-      __threadfence();
       __syncthreads();
     }
   }
+  __threadfence();
   __syncthreads();
-  if (tid == 0) a.stats[0] = s_acc;
+  if (tid == 0) {
+    a.stats[0] = s_acc;
+    atomicAdd(&a.t.counters[0], (unsigned long long)(long long)s_live);
+    atomicAdd(&a.t.counters[1], (unsigned long long)(long long)s_tomb);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -237,7 +287,7 @@ extern "C" int kgv_replay_window(kgv_ctx* ctx, kgv_utxo_table* table, const kgv_
   if (!ctx || !table) return KGV_ERR_ARG;
   std::lock_guard<std::recursive_mutex> g(ctx->mu);
   if (!batch || !prm || (n_blocks && !blocks) || (batch->n_txs && !results)) { ctx->err = "null argument"; return KGV_ERR_ARG; }
-  if (stats) { stats->n_accepted = 0; stats->n_sig_checks = 0; stats->n_host_vm = 0; }
+  if (stats) { stats->n_accepted = 0; stats->n_sig_checks = 0; stats->n_host_vm = 0; stats->pre_check_ms = 0; stats->in_order_ms = 0; }
   if (batch->n_txs == 0 || n_blocks == 0) return KGV_OK;
   if (n_blocks > 0xFFFFFFFFull) { ctx->err = "too many blocks"; return KGV_ERR_ARG; }
   // the blocks must tile the batch in order (block b = transactions [first_tx, first_tx + n_txs))
@@ -269,7 +319,8 @@ extern "C" int kgv_replay_window(kgv_ctx* ctx, kgv_utxo_table* table, const kgv_
   size_t o_acc = al256(o_res + nt * sizeof(kgv_tx_result));
   size_t o_scr = al256(o_acc + nt);
   size_t o_slp = al256(o_scr + ni * 72);
-  size_t o_cnt = al256(o_slp + ni * sizeof(UtxoSlot*));
+  size_t o_rng = al256(o_slp + ni * sizeof(UtxoSlot*));
+  size_t o_cnt = al256(o_rng + n_blocks * sizeof(ReplayRange));
   size_t total = al256(o_cnt + 64);
   rc = kgv_reserve(ctx, &ctx->d_replay, &ctx->d_replay_cap, total);
   if (rc) return rc;
@@ -283,6 +334,10 @@ extern "C" int kgv_replay_window(kgv_ctx* ctx, kgv_utxo_table* table, const kgv_
   uint8_t* dacc = R + o_acc;
   unsigned long long* cnt = (unsigned long long*)(R + o_cnt);
   cudaStream_t st = ctx->stream;
+  if (stats) {
+    for (cudaEvent_t& e : ctx->ev_time) if (!e) CK(cudaEventCreate(&e));
+    CK(cudaEventRecord(ctx->ev_time[0], st));
+  }
   CK(cudaMemcpyAsync(dblk, blocks, n_blocks * sizeof(kgv_replay_block), cudaMemcpyHostToDevice, st));
   CK(cudaMemsetAsync(wm, 0, wm_cap * 4, st));
   CK(cudaMemsetAsync(cnt, 0, 64, st));
@@ -297,7 +352,9 @@ extern "C" int kgv_replay_window(kgv_ctx* ctx, kgv_utxo_table* table, const kgv_
   CK(cudaGetLastError());
   k_replay_tx_block<<<(unsigned)n_blocks, 128, 0, st>>>(dblk, (uint32_t)n_blocks, txb);
   CK(cudaGetLastError());
-  ctx->launches += 5;
+  k_replay_ranges<<<nblk(n_blocks, 128), 128, 0, st>>>(dblk, (uint32_t)n_blocks, d.txs, (ReplayRange*)(R + o_rng));
+  CK(cudaGetLastError());
+  ctx->launches += 6;
   // ---- pre-check of every script of the window
   BatchView v{d.txs, d.inputs, d.outputs, dent, d.bytes};
   if (ni) {
@@ -335,12 +392,14 @@ extern "C" int kgv_replay_window(kgv_ctx* ctx, kgv_utxo_table* table, const kgv_
   a.spent_scripts = R + o_scr;
   a.slotp = (UtxoSlot**)(R + o_slp);
   a.ids = ids; a.itx = itx; a.otx = otx;
-  a.blocks = dblk; a.n_blocks = (uint32_t)n_blocks;
+  a.ranges = (const ReplayRange*)(R + o_rng); a.n_blocks = (uint32_t)n_blocks;
   a.prm = *prm;
   a.pre = pre; a.res = res; a.accept = dacc; a.stats = cnt;
+  if (stats) CK(cudaEventRecord(ctx->ev_time[1], st));
   k_replay_inorder<<<1, 1024, 0, st>>>(a);
   CK(cudaGetLastError());
   ctx->launches++;
+  if (stats) CK(cudaEventRecord(ctx->ev_time[2], st));
   STAGE("replay in-order");
   const bool dev_out = kgv_ptr_is_device(results);
   CK(cudaMemcpyAsync(results, res, nt * sizeof(kgv_tx_result), dev_out ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
@@ -350,6 +409,10 @@ extern "C" int kgv_replay_window(kgv_ctx* ctx, kgv_utxo_table* table, const kgv_
     CK(cudaMemcpyAsync(&n_acc, cnt, 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
   }
-  if (stats) { stats->n_accepted = n_acc; stats->n_sig_checks = n_items; stats->n_host_vm = n_vm; }
+  if (stats) {
+    stats->n_accepted = n_acc; stats->n_sig_checks = n_items; stats->n_host_vm = n_vm;
+    CK(cudaEventElapsedTime(&stats->pre_check_ms, ctx->ev_time[0], ctx->ev_time[1]));
+    CK(cudaEventElapsedTime(&stats->in_order_ms, ctx->ev_time[1], ctx->ev_time[2]));
+  }
   return KGV_OK;
 }

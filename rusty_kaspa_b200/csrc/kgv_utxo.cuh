@@ -165,8 +165,11 @@ __device__ __forceinline__ void load_script_words(uint32_t* w, const uint8_t* p,
 // upsert; returns 1 inserted, 2 replaced, 0 failed (table or overflow arena full).
 // Keys inserted concurrently by one kernel must be distinct (API contract), so a slot another thread is
 // filling (BUSY) always belongs to a different key and is simply skipped: no thread ever waits on another.
+// FENCE = false: the caller is a single CTA whose barriers order the slot contents before the state word for every reader.
+template <bool FENCE = true>
 __device__ __forceinline__ uint32_t table_put(const TableView& t, const uint32_t* k, uint64_t amount, uint64_t daa, uint32_t spk_version, uint32_t is_coinbase,
-                                              const uint8_t* script, uint32_t script_len) {
+                                              const uint8_t* script, uint32_t script_len, int* s_live = nullptr, int* s_tomb = nullptr) {
+  // s_live / s_tomb: optional shared-memory accumulators for the live / tombstone counters (a single-CTA caller flushes them once)
   uint64_t i = key_hash(k) & t.mask;
   UtxoSlot* target = nullptr;
   UtxoSlot* tomb = nullptr;
@@ -184,13 +187,20 @@ __device__ __forceinline__ uint32_t table_put(const TableView& t, const uint32_t
     if (st == SLOT_BUSY) continue;
     // EMPTY: the key is not in the table. Prefer the first tombstone seen, else this slot.
     if (tomb) {
-      if (atomicCAS(&tomb->state, SLOT_TOMB, SLOT_BUSY) == SLOT_TOMB) { target = tomb; atomicAdd(&t.counters[1], (unsigned long long)-1); break; }
+      if (atomicCAS(&tomb->state, SLOT_TOMB, SLOT_BUSY) == SLOT_TOMB) {
+        target = tomb;
+        if (s_tomb) atomicSub(s_tomb, 1); else atomicAdd(&t.counters[1], (unsigned long long)-1);
+        break;
+      }
       tomb = nullptr;
     }
     if (atomicCAS(&s->state, SLOT_EMPTY, SLOT_BUSY) == SLOT_EMPTY) { target = s; break; }
     // lost the race for this slot (it now holds another key): keep probing
   }
-  if (!target && tomb && atomicCAS(&tomb->state, SLOT_TOMB, SLOT_BUSY) == SLOT_TOMB) { target = tomb; atomicAdd(&t.counters[1], (unsigned long long)-1); }
+  if (!target && tomb && atomicCAS(&tomb->state, SLOT_TOMB, SLOT_BUSY) == SLOT_TOMB) {
+    target = tomb;
+    if (s_tomb) atomicSub(s_tomb, 1); else atomicAdd(&t.counters[1], (unsigned long long)-1);
+  }
   if (!target) { atomicAdd(&t.counters[3], 1ull); return 0; }
   uint32_t w[32];
   w[0] = replace ? SLOT_FULL : SLOT_BUSY;
@@ -219,9 +229,9 @@ __device__ __forceinline__ uint32_t table_put(const TableView& t, const uint32_t
   st256((uint8_t*)target + 96, w + 24);
   st256(target, w);
   if (!replace) {
-    __threadfence();
+    if (FENCE) __threadfence();
     *(volatile uint32_t*)&target->state = SLOT_FULL;
-    atomicAdd(&t.counters[0], 1ull);
+    if (s_live) atomicAdd(s_live, 1); else atomicAdd(&t.counters[0], 1ull);
   }
   return replace ? 2u : 1u;
 }

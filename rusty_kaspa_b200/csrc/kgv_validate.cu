@@ -598,10 +598,19 @@ int kgv_scripts_phase(kgv_ctx* ctx, const BatchView& v, size_t nt, size_t ni, co
   size_t ns = totals[0], ne = totals[1];
   if (n_items_out) *n_items_out = ns + ne;
   if (kgv_debug_on()) fprintf(stderr, "[kgv] items: schnorr %zu ecdsa %zu\n", ns, ne);
+  // multi-GPU (kgv_set_sharding): the candidate pairs are split into n_ranks contiguous ranges; this rank verifies one and the
+  // status bytes are exchanged before the scripts are resolved.  per_* = range length (the status arrays are padded to nr * per)
+  int nr = 1, rk = 0;
+  if (ctx->shard_comm) nr = kgv_comm_ranks(ctx->shard_comm, &rk);
+  auto per_of = [&](size_t n) { size_t p = (n + nr - 1) / nr; return (p + 255) & ~(size_t)255; };
+  const size_t per_s = nr > 1 ? per_of(ns) : ns, per_e = nr > 1 ? per_of(ne) : ne;
+  const size_t s_lo = nr > 1 ? (rk * per_s < ns ? rk * per_s : ns) : 0, s_hi = nr > 1 ? ((rk + 1) * per_s < ns ? (rk + 1) * per_s : ns) : ns;
+  const size_t e_lo = nr > 1 ? (rk * per_e < ne ? rk * per_e : ne) : 0, e_hi = nr > 1 ? ((rk + 1) * per_e < ne ? (rk + 1) * per_e : ne) : ne;
   // item arrays live in d_in (pk/sig/msg, status, refs)
   size_t i_pks = 0, i_sigs = al256(i_pks + ns * 32), i_msgs = al256(i_sigs + ns * 64), i_refs = al256(i_msgs + ns * 32), i_sts = al256(i_refs + ns * sizeof(ItemRef));
-  size_t i_pke = al256(i_sts + ns), i_sige = al256(i_pke + ne * 33), i_msge = al256(i_sige + ne * 64), i_refe = al256(i_msge + ne * 32), i_ste = al256(i_refe + ne * sizeof(ItemRef));
-  size_t total2 = al256(i_ste + ne + 64);
+  size_t i_pke = al256(i_sts + (nr > 1 ? nr * per_s : ns)), i_sige = al256(i_pke + ne * 33), i_msge = al256(i_sige + ne * 64), i_refe = al256(i_msge + ne * 32),
+         i_ste = al256(i_refe + ne * sizeof(ItemRef));
+  size_t total2 = al256(i_ste + (nr > 1 ? nr * per_e : ne) + 64);
   rc = kgv_reserve(ctx, &ctx->d_in, &ctx->d_in_cap, total2);
   if (rc) return rc;
   uint8_t* I = ctx->d_in;
@@ -615,13 +624,15 @@ int kgv_scripts_phase(kgv_ctx* ctx, const BatchView& v, size_t nt, size_t ni, co
   }
   if (ns && ne) CK(cudaEventRecord(ctx->ev_fork, st));  // fork point: everything both item kinds depend on is queued
   if (ns) {
-    k_item_msgs<<<nblk(ns, 128), 128, 0, st>>>(v, reu, itx, plans, (const ItemRef*)(I + i_refs), ns, false, (uint32_t*)(I + i_msgs));
-    CK(cudaGetLastError());
-    ctx->launches++;
-    STAGE("msgs schnorr");
-    rc = kgv_launch_verify(ctx, I + i_pks, I + i_msgs, I + i_sigs, ns, I + i_sts, false);
-    if (rc) return rc;
-    STAGE("verify schnorr");
+    if (s_hi > s_lo) {
+      k_item_msgs<<<nblk(s_hi - s_lo, 128), 128, 0, st>>>(v, reu, itx, plans, (const ItemRef*)(I + i_refs) + s_lo, s_hi - s_lo, false, (uint32_t*)(I + i_msgs) + 8 * s_lo);
+      CK(cudaGetLastError());
+      ctx->launches++;
+      STAGE("msgs schnorr");
+      rc = kgv_launch_verify(ctx, I + i_pks + 32 * s_lo, I + i_msgs + 32 * s_lo, I + i_sigs + 64 * s_lo, s_hi - s_lo, I + i_sts + s_lo, false);
+      if (rc) return rc;
+      STAGE("verify schnorr");
+    }
   }
   if (ne) {
     // with both kinds present the ECDSA items run on the side stream so the two (often sub-wave) verify
@@ -629,17 +640,24 @@ int kgv_scripts_phase(kgv_ctx* ctx, const BatchView& v, size_t nt, size_t ni, co
     const bool fork = ns != 0 && !kgv_debug_on();
     cudaStream_t se = fork ? ctx->aux_stream : st;
     if (fork) CK(cudaStreamWaitEvent(se, ctx->ev_fork, 0));
-    k_item_msgs<<<nblk(ne, 128), 128, 0, se>>>(v, reu, itx, plans, (const ItemRef*)(I + i_refe), ne, true, (uint32_t*)(I + i_msge));
-    CK(cudaGetLastError());
-    ctx->launches++;
-    STAGE("msgs ecdsa");
-    rc = kgv_launch_verify(ctx, I + i_pke, I + i_msge, I + i_sige, ne, I + i_ste, true, se, true);
-    if (rc) return rc;
+    if (e_hi > e_lo) {
+      k_item_msgs<<<nblk(e_hi - e_lo, 128), 128, 0, se>>>(v, reu, itx, plans, (const ItemRef*)(I + i_refe) + e_lo, e_hi - e_lo, true, (uint32_t*)(I + i_msge) + 8 * e_lo);
+      CK(cudaGetLastError());
+      ctx->launches++;
+      STAGE("msgs ecdsa");
+      rc = kgv_launch_verify(ctx, I + i_pke + 33 * e_lo, I + i_msge + 32 * e_lo, I + i_sige + 64 * e_lo, e_hi - e_lo, I + i_ste + e_lo, true, se, true);
+      if (rc) return rc;
+    }
     if (fork) {
       CK(cudaEventRecord(ctx->ev_join, se));
       CK(cudaStreamWaitEvent(st, ctx->ev_join, 0));
     }
     STAGE("verify ecdsa");
+  }
+  if (nr > 1) {
+    if (ns) { rc = kgv_comm_exchange_slices(ctx, ctx->shard_comm, I + i_sts, per_s); if (rc) return rc; }
+    if (ne) { rc = kgv_comm_exchange_slices(ctx, ctx->shard_comm, I + i_ste, per_e); if (rc) return rc; }
+    STAGE("verdict exchange");
   }
   k_resolve<<<nblk(ni, 128), 128, 0, st>>>(v, ni, itx, dres, plans, I + i_sts, I + i_ste, ierr);
   CK(cudaGetLastError());

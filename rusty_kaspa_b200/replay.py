@@ -28,7 +28,8 @@ REPLAY_ACCEPT_COINBASE, REPLAY_SKIP_SCRIPTS, REPLAY_VERIFY_ONLY = 1, 2, 4
 
 
 class ReplayStats(ctypes.Structure):
-    _fields_ = [("n_accepted", ctypes.c_uint64), ("n_sig_checks", ctypes.c_uint64), ("n_host_vm", ctypes.c_uint64)]
+    _fields_ = [("n_accepted", ctypes.c_uint64), ("n_sig_checks", ctypes.c_uint64), ("n_host_vm", ctypes.c_uint64), ("pre_check_ms", ctypes.c_float),
+                ("in_order_ms", ctypes.c_float)]
 
 
 def replay_blocks_array(ranges):
@@ -92,7 +93,8 @@ class DagReplayer:
         blocks_arr = np.ascontiguousarray(blocks_arr, dtype=REPLAY_BLOCK_DTYPE)
         self.ctx._check(self.ctx._lib.kgv_replay_window(self.ctx._h, self.us._h, ctypes.byref(cb), blocks_arr.ctypes.data, len(blocks_arr),
                                                         ctypes.byref(self.tv.params), res.ctypes.data, acc.ctypes.data, ctypes.byref(st)))
-        self.last_stats = {"n_accepted": int(st.n_accepted), "n_sig_checks": int(st.n_sig_checks), "n_host_vm": int(st.n_host_vm)}
+        self.last_stats = {"n_accepted": int(st.n_accepted), "n_sig_checks": int(st.n_sig_checks), "n_host_vm": int(st.n_host_vm), "pre_check_ms": float(st.pre_check_ms),
+                           "in_order_ms": float(st.in_order_ms)}
         return (res, acc) if want_accept else res
 
     def replay_windowed(self, blocks):

@@ -367,6 +367,204 @@ def utxo_diff_rules():
                                   "tests": tests})
 
 
+# ------------------------------------------------------------------------------------ storage mass (KIP-9) cases
+def storage_mass():
+    """consensus/core/src/mass/mod.rs:516-729: test_storage_mass (explicit expected values, evaluated by a tiny interpreter of the test's
+    own statements) and test_storage_mass_pluralities (pairs of transactions that must have EQUAL, non-zero mass)."""
+    src = read("consensus/core/src/mass/mod.rs")
+    consts = read("consensus/core/src/constants.rs")
+    sompi = int(re.search(r"SOMPI_PER_KASPA: u64 = ([\d_]+);", consts).group(1).replace("_", ""))
+    assert re.search(r"STORAGE_MASS_PARAMETER: u64 = SOMPI_PER_KASPA \* 10_000;", consts)
+    env0 = {"SOMPI_PER_KASPA": sompi, "STORAGE_MASS_PARAMETER": sompi * 10_000}
+    unit = int(re.search(r"const UTXO_UNIT_SIZE: u64 = (\d+);", src).group(1))
+
+    def ev(expr, env):
+        e = expr.strip().replace("_u64", "").replace("u64", "")
+        e = re.sub(r"(\d+)\.pow\((\d+)\)", r"(\1**\2)", e)
+        e = re.sub(r"(?<=\d)_(?=\d)", "", e)
+        e = e.replace("/", "//")
+        return int(eval(e, {"__builtins__": {}}, dict(env)))
+
+    def amounts(txt, env):
+        txt = txt.strip()
+        m = re.match(r"\[(.+)(?:;| REP)\s*(\d+)\]$", txt)  # [x; n]
+        if m:
+            return [ev(m.group(1), env)] * int(m.group(2))
+        return [ev(x, env) for x in txt.strip("[]").split(",") if x.strip()]
+
+    # ---- test_storage_mass: statements in order
+    body = src[src.index("fn test_storage_mass()"):src.index("fn generate_tx_from_amounts")]
+    cases, cur, param, env = [], {}, None, dict(env0)
+    body = re.sub(r"//[^\n]*", "", body)
+    body = re.sub(r"\[(\w+); (\d+)\]", r"[\1 REP \2]", body)  # [x; n] must survive the split on ';'
+    for stmt in body.split(";"):
+        st = " ".join(stmt.split())
+        m = re.search(r"let (?:mut )?(tx\d?) = generate_tx_from_amounts\(&(\[.*?\]), &(\[.*?\])\)", st)
+        if m:
+            cur[m.group(1)] = {"ins": amounts(m.group(2), env), "outs": amounts(m.group(3), env)}
+            continue
+        m = re.search(r"let mut (tx\d) = (tx\d?)\.clone\(\)", st)
+        if m:
+            cur[m.group(1)] = {"ins": list(cur[m.group(2)]["ins"]), "outs": list(cur[m.group(2)]["outs"])}
+            continue
+        m = re.search(r"let (\w+) = ([^;]+)$", st)
+        if m and m.group(1) in ("storage_mass_parameter", "base_value"):
+            env[m.group(1)] = ev(m.group(2), env)
+            continue
+        m = re.search(r"(tx\d?)\.tx\.outputs\[(\d+)\]\.value = (.+)$", st)
+        if m:
+            cur[m.group(1)]["outs"][int(m.group(2))] = ev(m.group(3), env)
+            continue
+        if re.search(r"for out in tx\.tx\.outputs\.iter_mut\(\) \{ out\.value \+= 1 \}", st) or "out.value += 1" in st:
+            cur["tx"]["outs"] = [v + 1 for v in cur["tx"]["outs"]]  # (the closing brace shares the statement with what follows)
+        m = re.search(r"tx\.entries\[0\]\.as_mut\(\)\.unwrap\(\)\.amount \+= tx\.tx\.outputs\.len\(\)", st)
+        if m:
+            cur["tx"]["ins"][0] += len(cur["tx"]["outs"])
+            continue
+        if "tx.tx.outputs.pop()" in st:
+            cur["tx"]["outs"].pop()
+            continue
+        m = re.search(r"let storage_mass = MassCalculator::new\(0, 0, 0, (.+?)\)\.calc_contextual_masses\(&(tx\d?)\.as_verifiable\(\)\)\.unwrap\(\)", st)
+        if m:
+            pending = {"ins": list(cur[m.group(2)]["ins"]), "outs": list(cur[m.group(2)]["outs"]), "storage_mass_parameter": ev(m.group(1), env)}
+            continue
+        m = re.search(r"assert_eq!\(storage_mass, (.+)\)$", st)
+        if m:
+            e = m.group(1)
+            pending["expected"] = ev(e, env)
+            cases.append(pending)
+    assert len(cases) == 8 and [c["expected"] for c in cases][:1] == [0] and cases[5]["expected"] == 9000000000 and cases[7]["expected"] == 5000000000, cases
+
+    # ---- test_storage_mass_pluralities
+    pb = src[src.index("fn test_storage_mass_pluralities()"):src.index("fn generate_script_for_plurality")]
+    pl = []
+    for m in re.finditer(r'PluralityTestCase \{\s*name: "([^"]+)",\s*inputs_tx1: &(\[.*?\]),\s*outputs_tx1: &(\[.*?\]),\s*inputs_tx2: &(\[.*?\]),\s*outputs_tx2: &(\[.*?\]),\s*'
+                         r'plurality_index: Some\((\d+)\),\s*desired_plurality: Some\((\d+)\),\s*override_output: (true|false),\s*storage_mass_parameter: ([^,]+),', pb, re.S):
+        pl.append({"name": m.group(1), "inputs_tx1": amounts(m.group(2), env0), "outputs_tx1": amounts(m.group(3), env0), "inputs_tx2": amounts(m.group(4), env0),
+                   "outputs_tx2": amounts(m.group(5), env0), "plurality_index": int(m.group(6)), "desired_plurality": int(m.group(7)), "override_output": m.group(8) == "true",
+                   "storage_mass_parameter": ev(m.group(9), env0), "script_len_for_plurality": (int(m.group(7)) - 1) * unit})
+    assert len(pl) == len(re.findall(r"PluralityTestCase \{", pb)) - 0 and len(pl) >= 8, len(pl)
+    dump("storage_mass.json", {"source": "consensus/core/src/mass/mod.rs:516-729 (test_storage_mass_pluralities, test_storage_mass)",
+                               "note": "every script public key is empty (plurality 1) except the one the plurality cases override: script = (desired_plurality-1)*100 bytes "
+                                       "(generate_script_for_plurality). Plurality cases assert mass(tx1) == mass(tx2) != 0.",
+                               "cases": cases, "plurality_cases": pl})
+
+
+# ------------------------------------------------------------------------------------ body_validation_in_isolation example block
+def body_validation_block():
+    """consensus/src/pipeline/body_processor/body_validation_in_isolation.rs:153-462 (validate_body_in_isolation_test): the example block (a Rust
+    literal) with the hash_merkle_root its header commits to, and the three set-check mutations the test applies with the error each must raise."""
+    src = read("consensus/src/pipeline/body_processor/body_validation_in_isolation.rs")
+    body = src[src.index("fn validate_body_in_isolation_test()"):src.index("async fn merkle_root_missing_parents_known_invalid_test")]
+    body = re.sub(r"//[^\n]*", "", body)
+    hdr = body[body.index("Header::new_finalized("):body.index("vec![\n                Transaction::new(")]
+    merkle = bytes(int(x, 16) for x in re.findall(r"0x([0-9a-f]{2})\b", hdr[hdr.rindex("Hash::from_slice(&["):hdr.index("]),", hdr.rindex("Hash::from_slice(&["))]))
+    assert len(merkle) == 32
+    txs_src = body[body.index("vec![\n                Transaction::new("):body.index("body_processor.validate_body_in_isolation(&example_block.clone()")]
+    toks = re.findall(r"0x[0-9a-fA-F]+|\d[\d_]*|[A-Za-z_][A-Za-z_0-9]*(?:::[A-Za-z_][A-Za-z_0-9]*)*!?|[\[\](){},:;&.]", txs_src)
+    pos = [0]
+
+    def peek():
+        return toks[pos[0]]
+
+    def take(x=None):
+        t = toks[pos[0]]
+        assert x is None or t == x, (t, x, toks[pos[0] - 5:pos[0] + 5])
+        pos[0] += 1
+        return t
+
+    def num(t):
+        return int(t, 16) if t.startswith("0x") else int(t.replace("_", ""))
+
+    def byte_list(close):  # after the opening bracket
+        out = []
+        while peek() != close:
+            t = take()
+            if t != ",":
+                out.append(num(t))
+        take(close)
+        return bytes(out)
+
+    def value():
+        t = take()
+        if t in ("vec!", "scriptvec!"):
+            opener = take()
+            close = "]" if opener == "[" else ")"
+            if peek() in ("TransactionInput", "TransactionOutput", "Transaction::new"):
+                items = []
+                while peek() != close:
+                    if peek() == ",":
+                        take()
+                        continue
+                    items.append(value())
+                take(close)
+                return items
+            return byte_list(close)
+        if t == "Transaction::new":
+            take("(")
+            args = []
+            while peek() != ")":
+                if peek() == ",":
+                    take()
+                    continue
+                args.append(value())
+            take(")")
+            ver, ins, outs, lock, subnet, gas, payload = args
+            return {"version": ver, "inputs": ins, "outputs": outs, "lock_time": lock, "subnetwork_id": subnet, "gas": gas, "payload": payload}
+        if t in ("TransactionInput", "TransactionOutput", "TransactionOutpoint"):
+            take("{")
+            d = {}
+            while peek() != "}":
+                if peek() == ",":
+                    take()
+                    continue
+                k = take()
+                take(":")
+                d[k] = value()
+            take("}")
+            return d
+        if t in ("TransactionId::from_slice", "Hash::from_slice"):
+            take("("); take("&"); take("[")
+            b = byte_list("]")
+            take(")")
+            return b
+        if t == "ScriptPublicKey::new":
+            take("(")
+            ver = value(); take(",")
+            sc = value()
+            if peek() == ",":
+                take()
+            take(")")
+            return {"spk_version": ver, "script": sc}
+        if t == "u64::MAX":
+            return 2**64 - 1
+        if t == "SUBNETWORK_ID_NATIVE":
+            return bytes(20)
+        if t == "SUBNETWORK_ID_COINBASE":
+            return bytes([1]) + bytes(19)
+        return num(t)
+
+    txs = value()
+    assert len(txs) >= 4 and not txs[0]["inputs"] and len(txs[1]["inputs"]) == 2, [len(t["inputs"]) for t in txs]
+    js = []
+    for t in txs:
+        js.append({"version": t["version"], "lock_time": t["lock_time"], "subnetwork_id": t["subnetwork_id"].hex(), "gas": t["gas"], "payload": t["payload"].hex(), "mass": 0,
+                   "inputs": [{"txid": i["previous_outpoint"]["transaction_id"].hex(), "index": i["previous_outpoint"]["index"], "sigscript": i["signature_script"].hex(),
+                               "sequence": i["sequence"], "sig_op_count": i["sig_op_count"]} for i in t["inputs"]],
+                   "outputs": [{"value": o["value"], "spk_version": o["script_public_key"]["spk_version"], "script": o["script_public_key"]["script"].hex()} for o in t["outputs"]]})
+    # the mutations of the test and the error each must raise (lines 423-460)
+    for needle in ("txs.push(txs[1].clone());", "txs[2].inputs[0].previous_outpoint = txs[1].inputs[0].previous_outpoint;",
+                   "txs[3].inputs[0].previous_outpoint = TransactionOutpoint { transaction_id: txs[2].id(), index: 0 };"):
+        assert needle in body, needle
+    order = [body.index("RuleError::DuplicateTransactions(_)"), body.index("RuleError::DoubleSpendInSameBlock(_)"), body.index("RuleError::ChainedTransaction(_)")]
+    assert order == sorted(order)
+    dump("body_validation_block.json", {"source": "consensus/src/pipeline/body_processor/body_validation_in_isolation.rs:153-462 (validate_body_in_isolation_test)",
+                                        "hash_merkle_root": merkle.hex(), "txs": js,
+                                        "mutations": [{"do": "push a clone of txs[1]", "error": "DuplicateTransactions"},
+                                                      {"do": "txs[2].inputs[0].previous_outpoint = txs[1].inputs[0].previous_outpoint", "error": "DoubleSpendInSameBlock"},
+                                                      {"do": "txs[3].inputs[0].previous_outpoint = (txs[2].id(), 0)", "error": "ChainedTransaction"}]})
+
+
 if __name__ == "__main__":
     if not os.path.isdir(REF):
         sys.exit("needs /root/reference (run in the build container)")
@@ -378,3 +576,5 @@ if __name__ == "__main__":
     script_tests()
     muhash()
     utxo_diff_rules()
+    storage_mass()
+    body_validation_block()

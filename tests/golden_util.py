@@ -121,3 +121,59 @@ def simpa_dag_replay_plan(fixture="simpa_goref_1060.json.gz"):
         chain.append(sp(chain[-1]))
     chain.reverse()
     return fx, by, order, sp, ordered_mergeset, chain
+
+
+def bip340_vectors():
+    """tests/golden/bip340_vectors.csv (rows 0-14 of BIP-340's test-vectors.csv, provenance and self-validation in make_bip340.py):
+    returns (pk (n,32), msg (n,32), sig (n,64) uint8 arrays, expected KGV_SIG_* status list, comments)"""
+    import csv
+    import os
+    import numpy as np
+    rows = list(csv.DictReader(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "bip340_vectors.csv"))))
+    hexarr = lambda k, n: np.frombuffer(b"".join(bytes.fromhex(r[k]) for r in rows), dtype=np.uint8).reshape(-1, n).copy()
+    exp = [int(r["kgv_status"]) for r in rows]
+    assert all((e == 1) == (r["verification result"] == "TRUE") for e, r in zip(exp, rows))
+    return hexarr("public key", 32), hexarr("message", 32), hexarr("signature", 64), exp, [r["comment"] for r in rows]
+
+
+def storage_mass_cases():
+    """tests/golden/storage_mass.json -> list of (name, tx dict, entries, storage_mass_parameter, expected mass or None, group) ; transactions of one
+    plurality `group` must have equal non-zero mass (consensus/core/src/mass/mod.rs:516-729)"""
+    d = load("storage_mass.json")
+
+    def tx_of(ins, outs, in_scripts=None, out_scripts=None):
+        n_i, n_o = len(ins), len(outs)
+        in_scripts, out_scripts = in_scripts or [b""] * n_i, out_scripts or [b""] * n_o
+        tx = {"version": 0, "inputs": [{"txid": bytes.fromhex("880eb9819a31821d9d2399e2f35e2433b72637e393d71ecc9b8d0250f49153c3"), "index": i, "sigscript": b"", "sequence": 0,
+                                        "sig_op_count": 0} for i in range(n_i)],
+              "outputs": [{"value": v, "spk_version": 0, "script": s} for v, s in zip(outs, out_scripts)], "lock_time": 1615462089000,
+              "subnetwork_id": bytes(range(1, 11)) + bytes(10), "gas": 0, "payload": b"", "mass": 0}
+        ents = [{"amount": a, "spk_version": 0, "script": s, "block_daa_score": 0, "is_coinbase": False} for a, s in zip(ins, in_scripts)]
+        return tx, ents
+    out = []
+    for k, c in enumerate(d["cases"]):
+        tx, ents = tx_of(c["ins"], c["outs"])
+        out.append((f"case{k}", tx, ents, c["storage_mass_parameter"], c["expected"], None))
+    for g, c in enumerate(d["plurality_cases"]):
+        tx1, e1 = tx_of(c["inputs_tx1"], c["outputs_tx1"])
+        big = bytes([1]) * c["script_len_for_plurality"]
+        isc, osc = [b""] * len(c["inputs_tx2"]), [b""] * len(c["outputs_tx2"])
+        (osc if c["override_output"] else isc)[c["plurality_index"]] = big
+        tx2, e2 = tx_of(c["inputs_tx2"], c["outputs_tx2"], isc, osc)
+        out.append((c["name"] + " /tx1", tx1, e1, c["storage_mass_parameter"], None, g))
+        out.append((c["name"] + " /tx2", tx2, e2, c["storage_mass_parameter"], None, g))
+    return out
+
+
+def body_validation_blocks():
+    """tests/golden/body_validation_block.json -> (hash_merkle_root hex, [(name, txs, expected status name)]): the reference's example block and the three
+    set-check mutations of validate_body_in_isolation_test (body_validation_in_isolation.rs:423-460)"""
+    import copy
+    import pyref
+    d = load("body_validation_block.json")
+    base = [tx_from_json(t) for t in d["txs"]]
+    dup = copy.deepcopy(base); dup.append(copy.deepcopy(dup[1]))
+    dbl = copy.deepcopy(base); dbl[2]["inputs"][0]["txid"], dbl[2]["inputs"][0]["index"] = dbl[1]["inputs"][0]["txid"], dbl[1]["inputs"][0]["index"]
+    chn = copy.deepcopy(base); chn[3]["inputs"][0]["txid"], chn[3]["inputs"][0]["index"] = pyref.tx_id(chn[2]), 0
+    assert [m["error"] for m in d["mutations"]] == ["DuplicateTransactions", "DoubleSpendInSameBlock", "ChainedTransaction"]
+    return d["hash_merkle_root"], [("example block", base, 0), ("duplicate", dup, 1), ("double spend", dbl, 2), ("chained", chn, 3)]

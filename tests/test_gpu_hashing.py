@@ -144,3 +144,21 @@ def test_block_set_checks(oracle):
         seen.add(st)
     assert seen == {0, 1, 2, 3}
     ctx.close()
+
+
+def test_body_validation_example_block_of_the_reference_on_the_gpu(gpu_ctx):
+    """the reference's own test block (body_validation_in_isolation.rs:153-462): kgv_block_hash_merkle_roots reproduces the header's hash_merkle_root,
+    kgv_block_set_checks passes it and reports the test's three mutations as DuplicateTransactions / DoubleSpendInSameBlock / ChainedTransaction -
+    all four blocks in one call"""
+    from golden_util import body_validation_blocks
+    from rusty_kaspa_b200.txbatch import build_batch
+    root, blocks = body_validation_blocks()
+    flat, first = [], [0]
+    for _, txs, _ in blocks:
+        flat += txs
+        first.append(len(flat))
+    b = build_batch(flat)
+    assert gpu_ctx.block_hash_merkle_roots(b, first)[0].tobytes().hex() == root
+    got = gpu_ctx.block_set_checks(b, first)
+    assert got["status"].tolist() == [w for _, _, w in blocks]
+    assert int(got[1]["index"]) == 5 and int(got[3]["index"]) > 0  # the pushed clone is transaction 5 of its block

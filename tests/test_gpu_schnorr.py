@@ -41,3 +41,19 @@ def test_bitmap(gpu_ctx):
         bm = gpu_ctx.status_to_bitmap(st)
         exp = np.packbits((st == 1).astype(np.uint8), bitorder="little")
         assert (bm == exp).all()
+
+
+def test_bip340_test_vectors_on_the_gpu(gpu_ctx):
+    """rows 0-14 of BIP-340's test-vectors.csv through kgv_schnorr_verify: verdicts incl. the parse-error class for unliftable keys;
+    also embedded in a larger batch at every position of a warp so that the rare group-law paths (R at infinity) are taken by single lanes"""
+    from golden_util import bip340_vectors
+    pk, msg, sig, exp, comments = bip340_vectors()
+    got = gpu_ctx.verify_schnorr_batch(pk, msg, sig)
+    assert got.tolist() == exp, [(i, c) for i, (g, e, c) in enumerate(zip(got, exp, comments)) if g != e]
+    fpk, fmsg, fsig, kind = W.schnorr_triples(512, seed=3, n_keys=32, n_nonces=32, frac_bitflip=0.0, frac_adversarial=0.0)
+    for shift in range(0, 32, 5):
+        P, M, S = fpk.copy(), fmsg.copy(), fsig.copy()
+        pos = [(37 * i + shift) % 512 for i in range(15)]
+        P[pos], M[pos], S[pos] = pk, msg, sig
+        g = gpu_ctx.verify_schnorr_batch(P, M, S)
+        assert g[pos].tolist() == exp and (np.delete(g, pos) == 1).all()

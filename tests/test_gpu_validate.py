@@ -170,3 +170,58 @@ def test_host_utxo_diff_applied_to_the_gpu_table():
     assert a.count() == b.count() == len(cur) > 20
     assert MuHash.of_utxo_set(ctx, a).finalize() == MuHash.of_utxo_set(ctx, b).finalize()
     a.close(); b.close(); ctx.close()
+
+
+@pytest.mark.gpu
+def test_storage_mass_cases_of_the_reference_on_the_gpu(gpu_ctx, oracle):
+    """the reference's own storage-mass cases (consensus/core/src/mass/mod.rs:516-729) through k_tx_context: a transaction committing the expected mass
+    passes the mass check, one committing expected + 1 is WrongMass; plurality pairs commit each other's (equal) mass"""
+    from golden_util import storage_mass_cases
+    cases = storage_mass_cases()
+    by_group = {}
+    for name, tx, ents, C, expected, group in cases:
+        if group is not None:
+            by_group.setdefault(group, []).append(oracle_tx.storage_mass(oracle, build_batch([tx], [ents]), 0, C))
+    for name, tx, ents, C, expected, group in cases:
+        want = expected if expected is not None else by_group[group][0]
+        tv = TransactionValidator(gpu_ctx, Params(coinbase_maturity=0, storage_mass_parameter=C))
+        good, bad = dict(tx, mass=want), dict(tx, mass=want + 1)
+        res = tv.validate_populated_transactions(build_batch([good, bad], [ents, ents]), 10, flags=1)  # SkipScriptChecks: context rules only
+        assert res["status"].tolist() == [0, 7], (name, res)
+
+
+@pytest.mark.gpu
+def test_validate_mempool_transactions_in_parallel(gpu_ctx, oracle):
+    """consensus/src/pipeline/virtual_processor/processor.rs:853-878: a batch of mempool transactions against the virtual UTXO set; outcomes are RETURNED per
+    transaction (not filtered): valid ones with their fee (input of the host-side feerate check), orphans as MissingTxOutpoints, bad signatures /
+    wrong mass / immature coinbase spends with their TxRuleError class.  Small and large batches, against the oracle's composed view."""
+    dag = SimDag(seed=23, n_keys=64, n_nonces=128, mix=(0.5, 0.2, 0.15, 0.15), frac_invalid=0.0, coinbase_maturity=4, coinbase_outputs=10)
+    op = oracle_tx.params(coinbase_maturity=4, storage_mass_parameter=dag.C)
+    tv = TransactionValidator(gpu_ctx, Params(coinbase_maturity=4, storage_mass_parameter=dag.C))
+    us = GpuUtxoSet(gpu_ctx, 1 << 14)
+    ost = oracle_tx.State(oracle)
+    for _ in range(12):  # build a virtual UTXO set
+        txs, pov = dag.make_block(20)
+        b = build_batch(txs)
+        acc = np.ones(len(txs), dtype=np.uint8)
+        assert ost.accept(b, acc, pov) == 0
+        ost.commit()
+        us.add_transactions(b, acc, pov)
+    # the "mempool": the next block's transactions (not applied), some made orphans / invalid
+    dag.frac_invalid = 0.3
+    txs, pov = dag.make_block(120)
+    pool = txs[1:]
+    pool[3]["inputs"][0]["txid"] = bytes(32)                    # orphan
+    pool[7]["inputs"][-1]["index"] = 77                         # orphan through a bad index
+    for n in (1, 5, len(pool)):
+        b = build_batch(pool[:n])
+        got = tv.validate_mempool_transactions_in_parallel(us, b, pov)
+        exp = ost.validate(b, pov, 0, op, threads=2)
+        _same_results(got, exp)
+        assert len(got) == n
+    st = set(int(s) for s in got["status"])
+    assert {0, 1, 9} <= st and len(st) >= 4, st
+    ok = got["status"] == 0
+    assert ok.sum() > 40 and (got["fee"][ok] == 1).all()        # the generator pays a fee of 1 sompi per transaction
+    assert us.count() == ost.count()                            # nothing was applied
+    us.close(); ost.close()

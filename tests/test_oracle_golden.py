@@ -127,3 +127,25 @@ def test_blocks_json_reader_matches_the_committed_fixture():
         assert b["hash"].hex() == g["hash"] and b["daa_score"] == g["daa_score"] and b["hash_merkle_root"].hex() == g["hash_merkle_root"]
         assert b["transactions"] == [tx_from_json(t) for t in g["transactions"]]
     assert blocks[0]["utxo_commitment"].hex() == "544eb3142c000f0ad2c76ac41f4222abbababed830eeafee4b6dc56b52d5cac0"  # genesis: EMPTY_MUHASH
+
+
+def test_body_validation_example_block_of_the_reference(oracle):
+    """validate_body_in_isolation_test (body_validation_in_isolation.rs:153-462): the example block's transactions hash to the hash_merkle_root its header
+    literal commits to (tx hash incl. real mainnet-style signature scripts + merkle tree), pass the set checks, and the test's three mutations raise
+    DuplicateTransactions / DoubleSpendInSameBlock / ChainedTransaction in the oracle"""
+    import ctypes
+    import oracle_tx
+    import pyref
+    from golden_util import body_validation_blocks
+    from rusty_kaspa_b200.txbatch import build_batch
+    root, blocks = body_validation_blocks()
+    for name, txs, want in blocks:
+        b = build_batch(txs)
+        if want == 0:
+            hs = oracle_tx.tx_hashes(oracle, b)
+            out = ctypes.create_string_buffer(32)
+            oracle.ok_merkle_root(hs.tobytes(), ctypes.c_size_t(len(hs)), out)
+            assert out.raw.hex() == root == pyref.merkle_root([pyref.tx_hash(t) for t in txs]).hex()
+        ob = oracle_tx.ok_batch(b)
+        idx = ctypes.c_uint32()
+        assert oracle.ok_block_set_checks(ctypes.byref(ob), ctypes.c_uint32(0), ctypes.c_uint32(len(txs)), ctypes.byref(idx)) == want, name

@@ -86,3 +86,17 @@ def test_sign_roundtrip_matches_pyref(oracle):
         assert oracle.ok_ecdsa_pubkey(sk, pk33) and oracle.ok_ecdsa_sign(sk, m, sig)
         assert pk33.raw == pyref.ecdsa_pubkey(sk)
         assert oracle.ok_ecdsa_verify(pk33.raw, m, sig.raw) == 1 == pyref.ecdsa_verify(pk33.raw, m, sig.raw)
+
+
+def test_bip340_test_vectors(oracle):
+    """rows 0-14 of BIP-340's own test-vectors.csv (tests/golden/bip340_vectors.csv): signing KATs, a low-r signature, and every
+    malformed-encoding case the BIP lists (off-curve key, odd-y R, negated message / s, R at infinity, r not on the curve, r = p,
+    s = n, key >= p) through the C oracle and the Python twin"""
+    import pyref
+    from conftest import oracle_schnorr_batch
+    from golden_util import bip340_vectors
+    pk, msg, sig, exp, comments = bip340_vectors()
+    assert len(exp) == 15 and exp.count(1) == 5 and exp.count(2) == 2
+    got = oracle_schnorr_batch(oracle, pk, msg, sig, threads=2)
+    assert got.tolist() == exp, [(i, c) for i, (g, e, c) in enumerate(zip(got, exp, comments)) if g != e]
+    assert [pyref.schnorr_verify(pk[i].tobytes(), msg[i].tobytes(), sig[i].tobytes()) for i in range(15)] == exp

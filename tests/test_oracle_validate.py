@@ -68,3 +68,21 @@ def test_validate_populated_fee_and_context_rules(oracle):
     assert oracle_tx.validate_populated(oracle, build_batch([tx], [e5]), 0, pov, 2, p)["status"] == 4
     # skip script checks accepts a broken signature
     assert oracle_tx.validate_populated(oracle, build_batch([t4], [entries]), 0, entries[0]["block_daa_score"] + 20, 1, oracle_tx.params(storage_mass_parameter=0))["status"] in (0, 7)
+
+
+def test_storage_mass_cases_of_the_reference(oracle):
+    """consensus/core/src/mass/mod.rs:516-729 (tests/golden/storage_mass.json): the 8 explicit values of test_storage_mass and the 8 plurality pairs
+    of test_storage_mass_pluralities (equal, non-zero mass) through the oracle's ok_storage_mass"""
+    from golden_util import storage_mass_cases
+    groups = {}
+    n_exact = 0
+    for name, tx, ents, C, expected, group in storage_mass_cases():
+        m = oracle_tx.storage_mass(oracle, build_batch([tx], [ents]), 0, C)
+        if expected is not None:
+            assert m == expected, (name, m, expected)
+            n_exact += 1
+        else:
+            groups.setdefault(group, []).append(m)
+    assert n_exact == 8 and len(groups) == 8
+    for g, (a, b) in groups.items():
+        assert a == b and a not in (0, None), (g, a, b)
