@@ -242,6 +242,24 @@ int kgv_validate_txs(kgv_ctx* ctx, kgv_utxo_table* t, const kgv_tx_batch* batch,
 int kgv_utxo_apply_accepted(kgv_ctx* ctx, kgv_utxo_table* t, const kgv_tx_batch* batch, const uint8_t* accept, uint64_t pov_daa_score);
 
 /* ------------------------------------------------------------------------------------------------
+ * SigCache: Cache<SigCacheKey, bool> (crypto/txscript/src/caches.rs:14-55; consulted at crypto/txscript/src/lib.rs:589-603, 624-638;
+ * created with 10 000 entries and shared by every clone of the TransactionValidator, transaction_validator/mod.rs:48).
+ * A device-resident, bounded table of verdicts keyed by BLAKE2b-256(kind || signature || public key || message).  Attached to a context
+ * (kgv_set_sigcache; several contexts of one device may share one cache, as the clones share the Arc), it is consulted by the script
+ * phase of kgv_validate_populated / kgv_validate_txs / kgv_replay_window: pairs seen before are answered from the table, only the
+ * misses reach the verification kernels, and their verdicts (true AND false; never parse errors, which the reference raises before its
+ * cache) are remembered.  Full neighbourhoods evict a pseudo-random entry (caches.rs:49-51).  Results never change, only speed:
+ * block-template building and block validation re-meet what the mempool verified (processor.rs:853-914).
+ * capacity is rounded up to a power of two.  counters: hits = get_counts, inserts = insert_counts (caches.rs:57-93).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct kgv_sigcache kgv_sigcache;
+int kgv_sigcache_create(kgv_ctx* ctx, uint64_t capacity, kgv_sigcache** out);
+void kgv_sigcache_destroy(kgv_sigcache* cache);
+int kgv_sigcache_clear(kgv_ctx* ctx, kgv_sigcache* cache);
+int kgv_sigcache_counters(kgv_ctx* ctx, kgv_sigcache* cache, uint64_t* hits, uint64_t* inserts, uint64_t* lookups, uint64_t* evictions);
+int kgv_set_sigcache(kgv_ctx* ctx, kgv_sigcache* cache /* NULL: detach */);
+
+/* ------------------------------------------------------------------------------------------------
  * Multi-GPU (SURVEY.md §8b kgv_shard_allgather, §8e): signature batches shard across GPUs as contiguous ranges, one context (and
  * normally one process) per GPU; the only exchange step of the path is "every rank ends up with every shard's verdicts".
  * The reference has no counterpart (rayon on one host, utxo_validation.rs:269-277).
@@ -316,6 +334,13 @@ typedef struct {
 int kgv_replay_window(kgv_ctx* ctx, kgv_utxo_table* t, const kgv_tx_batch* batch, const kgv_replay_block* blocks, size_t n_blocks,
                       const kgv_params* params, kgv_tx_result* results, uint8_t* accept, kgv_replay_stats* stats);
 
+/* The multiset of what the LAST kgv_replay_window call of this context accepted, per group of blocks: group g = blocks
+ * [group_first_block[g], group_first_block[g+1]) of that window (the mergeset of one chain block); values768[g] = (numerator || denominator) of
+ * MuHash::from_transaction over the accepted transactions of the group incl. accepted coinbases (utxo_validation.rs:116-121,144; spent entries as
+ * found at each block's position).  Must directly follow that kgv_replay_window call (no other batch call in between).
+ * With kgv_muhash_prefix_combine and kgv_muhash_finalize_batch this yields every chain block's utxo_commitment of a window (:188-192). */
+int kgv_replay_muhash(kgv_ctx* ctx, const uint32_t* group_first_block, size_t n_groups, uint8_t* values768);
+
 /* ------------------------------------------------------------------------------------------------
  * Merkle roots: crypto/merkle/src/lib.rs:3-30 calc_merkle_root / merkle_hash.
  * ------------------------------------------------------------------------------------------------ */
@@ -362,6 +387,15 @@ int kgv_muhash_combine(kgv_ctx* ctx, uint8_t* numerator_a, uint8_t* denominator_
  * hash = BLAKE2b-256 keyed "MuHashFinalize".  Sequential by nature (one modular inversion: 3 072 dependent squarings);
  * the reference calls it once per chain block outside the parallel section.  serialized384 may be NULL. */
 int kgv_muhash_finalize(kgv_ctx* ctx, const uint8_t* numerator384, const uint8_t* denominator384, uint8_t* serialized384, uint8_t* hash32);
+/* n finalizations at once: hashes32[i] = MuHash{numerator_i, denominator_i}.finalize() (lib.rs:98-115); value i sits pitch_bytes after value
+ * i - 1 (384 for plain arrays, 768 for (numerator || denominator) records).  ONE modular inversion for the whole batch (Montgomery's
+ * trick over prefix / suffix products built by parallel scans): a chain block's commitment costs five multiplications instead of
+ * 3 072 squarings.  serialized384 (n * 384 contiguous bytes) may be NULL. */
+int kgv_muhash_finalize_batch(kgv_ctx* ctx, const uint8_t* numerators384, const uint8_t* denominators384, size_t n, size_t pitch_bytes, uint8_t* serialized384,
+                              uint8_t* hashes32);
+/* The MuHash::combine chain of a replay (utxo_validation.rs:144): values768 holds n (numerator || denominator) records; on return record i is
+ * init * record 0 * ... * record i (canonical).  init768 may be NULL (= the empty MuHash). */
+int kgv_muhash_prefix_combine(kgv_ctx* ctx, const uint8_t* init768, uint8_t* values768, size_t n);
 /* MuHash::add_utxo (consensus/core/src/muhash.rs:28-33) over every live entry of the table: the UTXO-set commitment
  * numerator (denominator 1). */
 int kgv_utxo_muhash(kgv_ctx* ctx, kgv_utxo_table* t, uint8_t* numerator384);

@@ -57,6 +57,16 @@ int ok_ecdsa_verify(const uint8_t pk33[33], const uint8_t msg32[32], const uint8
 void ok_schnorr_verify_batch(const uint8_t* pk32, const uint8_t* msg32, const uint8_t* sig64, size_t n, uint8_t* status, int nthreads);
 void ok_ecdsa_verify_batch(const uint8_t* pk33, const uint8_t* msg32, const uint8_t* sig64, size_t n, uint8_t* status, int nthreads);
 
+/* "cpu_fast" (ok_secp_fast.c): the speed-oriented second port (GLV, wNAF, effective-affine tables, dedicated squaring) that the
+ * CPU baselines time; verdicts identical to the plain checker's above (tests/test_oracle_secp.py). */
+int ok_schnorr_verify_fast(const uint8_t pk32[32], const uint8_t msg32[32], const uint8_t sig64[64]);
+int ok_ecdsa_verify_fast(const uint8_t pk33[33], const uint8_t msg32[32], const uint8_t sig64[64]);
+void ok_schnorr_verify_batch_fast(const uint8_t* pk32, const uint8_t* msg32, const uint8_t* sig64, size_t n, uint8_t* status, int nthreads);
+void ok_ecdsa_verify_batch_fast(const uint8_t* pk33, const uint8_t* msg32, const uint8_t* sig64, size_t n, uint8_t* status, int nthreads);
+/* route the signature checks of ok_validate.c (ok_state_validate / ok_state_replay) through the fast port: on for the CPU baselines,
+ * off (default) when the oracle acts as the checker */
+void ok_use_fast_verify(int on);
+
 /* test-vector generation helpers (BIP-340 signing with aux=0^32; ECDSA with a
  * SHA-256 derived nonce and low-S normalisation).  Return 1 on success. */
 int ok_schnorr_pubkey(const uint8_t seckey32[32], uint8_t pk32[32]);

@@ -14,6 +14,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+static int g_fast_verify = 0;
+void ok_use_fast_verify(int on) { g_fast_verify = on; }
+
 /* ------------------------------------------------------------------ standard-class script check */
 static int sighash_type_ok(uint8_t t) { return t == 1 || t == 2 || t == 4 || t == 0x81 || t == 0x82 || t == 0x84; }
 
@@ -26,7 +29,8 @@ static int check_sig(const ok_batch* b, const ok_utxo_entry* entries, size_t tx,
   if (keylen != (size_t)(ecdsa ? 33 : 32)) return OK_SCRIPT_PUBKEY_FORMAT;
   uint8_t msg[32];
   ok_sighash(b, entries, tx, idx, hash_type, ecdsa, msg);
-  int st = ecdsa ? ok_ecdsa_verify(key, msg, sig) : ok_schnorr_verify(key, msg, sig);
+  int st = g_fast_verify ? (ecdsa ? ok_ecdsa_verify_fast(key, msg, sig) : ok_schnorr_verify_fast(key, msg, sig))
+                         : (ecdsa ? ok_ecdsa_verify(key, msg, sig) : ok_schnorr_verify(key, msg, sig));
   if (st == OK_SIG_PK_PARSE_ERR || st == OK_SIG_SIG_PARSE_ERR) return OK_SCRIPT_INVALID_SIGNATURE;
   *valid = st == OK_SIG_VALID;
   return -1;

@@ -39,6 +39,11 @@ SYMBOLS = [
     ("kgv_utxo_digest", _c.c_int, [_c.c_void_p, _c.c_void_p, _u8p]),
     ("kgv_validate_txs", _c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_uint64, _c.c_uint32, _c.c_void_p, _u8p]),
     ("kgv_utxo_apply_accepted", _c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _u8p, _c.c_uint64]),
+    ("kgv_sigcache_create", _c.c_int, [_c.c_void_p, _c.c_uint64, _c.POINTER(_c.c_void_p)]),
+    ("kgv_sigcache_destroy", None, [_c.c_void_p]),
+    ("kgv_sigcache_clear", _c.c_int, [_c.c_void_p, _c.c_void_p]),
+    ("kgv_sigcache_counters", _c.c_int, [_c.c_void_p, _c.c_void_p, _c.POINTER(_c.c_uint64), _c.POINTER(_c.c_uint64), _c.POINTER(_c.c_uint64), _c.POINTER(_c.c_uint64)]),
+    ("kgv_set_sigcache", _c.c_int, [_c.c_void_p, _c.c_void_p]),
     ("kgv_comm_unique_id", _c.c_int, [_u8p]),
     ("kgv_comm_create", _c.c_int, [_c.c_void_p, _c.c_int, _c.c_int, _u8p, _c.c_size_t, _c.POINTER(_c.c_void_p)]),
     ("kgv_comm_destroy", None, [_c.c_void_p]),
@@ -58,6 +63,9 @@ SYMBOLS = [
     ("kgv_muhash_txs", _c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _u8p, _c.c_uint64, _u8p, _u8p]),
     ("kgv_muhash_combine", _c.c_int, [_c.c_void_p, _u8p, _u8p, _u8p, _u8p]),
     ("kgv_muhash_finalize", _c.c_int, [_c.c_void_p, _u8p, _u8p, _u8p, _u8p]),
+    ("kgv_muhash_finalize_batch", _c.c_int, [_c.c_void_p, _u8p, _u8p, _c.c_size_t, _c.c_size_t, _u8p, _u8p]),
+    ("kgv_muhash_prefix_combine", _c.c_int, [_c.c_void_p, _u8p, _u8p, _c.c_size_t]),
+    ("kgv_replay_muhash", _c.c_int, [_c.c_void_p, _u8p, _c.c_size_t, _u8p]),
     ("kgv_utxo_muhash", _c.c_int, [_c.c_void_p, _c.c_void_p, _u8p]),
     ("kgv_script_execute", _c.c_int, [_c.c_void_p, _c.c_uint32, _c.c_uint32, _c.c_void_p, _c.c_void_p, _u8p]),
     ("kgv_check_scripts_host", _c.c_int, [_c.c_void_p, _c.c_void_p, _u8p, _c.c_size_t, _u8p]),

@@ -25,6 +25,7 @@ static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 int kgv_batch_to_device(kgv_ctx* ctx, const kgv_tx_batch* b, kgv_dev_batch* out, bool need_entries) {
   if (!b) { ctx->err = "null batch"; return KGV_ERR_ARG; }
+  ctx->last_replay.valid = false;  // whatever the last replay staged may be overwritten from here on
   if ((b->n_txs && !b->txs) || (b->n_inputs && !b->inputs) || (b->n_outputs && !b->outputs) || (b->n_bytes && !b->bytes) ||
       (need_entries && b->n_inputs && !b->entries)) {
     ctx->err = "batch array missing";

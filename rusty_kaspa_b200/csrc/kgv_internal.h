@@ -4,6 +4,7 @@
 #include <cstdint>
 #include <mutex>
 #include <string>
+#include <vector>
 
 #ifndef KGV_BLOCK
 #define KGV_BLOCK 128         // threads per block of the verification kernels
@@ -16,6 +17,7 @@
 #define KGV_ITEMS 4           // signatures per thread sharing one modular inversion (see k_schnorr_verify)
 #endif
 
+struct kgv_dev_batch_fwd;
 struct kgv_ctx {
   int device = 0;
   cudaStream_t own_stream = nullptr;
@@ -39,7 +41,17 @@ struct kgv_ctx {
   size_t d_replay_cap = 0;
   uint8_t* d_mu = nullptr;      // MuHash element arrays, product-tree levels and wide-product scratch rows
   size_t d_mu_cap = 0;
+  // state of the last kgv_replay_window call, kept for kgv_replay_muhash (cleared by any call that stages another batch)
+  struct {
+    bool valid = false;
+    kgv_dev_batch_fwd* unused_ = nullptr;
+    const void *txs = nullptr, *inputs = nullptr, *outputs = nullptr, *bytes = nullptr;
+    size_t nt = 0, ni = 0, no = 0, n_blocks = 0;
+    size_t o_ids = 0, o_itx = 0, o_otx = 0, o_ent = 0, o_acc = 0, o_txb = 0, o_rng = 0;  // offsets into d_replay
+  } last_replay;
+  struct kgv_sigcache* sigcache = nullptr;  // kgv_set_sigcache: verdicts of the validation calls are looked up / remembered here
   struct kgv_comm* shard_comm = nullptr;  // kgv_set_sharding: signature checks of the validation calls are split over its ranks
+  std::vector<uint8_t*> parked;  // outgrown per-call buffers, released when the caller synchronises / destroys the context (kgv_reserve)
   uint64_t launches = 0;
   int resident_blocks = 148 * KGV_BLOCKS_PER_SM;  // verification kernels: blocks that fit the device at once (persistent grid)
   std::recursive_mutex mu;  // recursive: the host-VM resolution inside a validation call re-enters the ABI (kgv_sighash, kgv_*_verify)
@@ -65,7 +77,7 @@ int kgv_batch_to_device(kgv_ctx* ctx, const kgv_tx_batch* b, kgv_dev_batch* out,
 // Enqueue a verification kernel on device-resident SoA item arrays (no locking, no copies): used by the
 // fused validation path.  ecdsa: pk stride 33, else 32.
 int kgv_launch_verify(kgv_ctx* ctx, const uint8_t* dpk, const uint8_t* dmsg, const uint8_t* dsig, size_t n, uint8_t* dstatus, bool ecdsa,
-                      cudaStream_t on = nullptr, bool use_on = false);
+                      cudaStream_t on = nullptr, bool use_on = false, const uint32_t* index = nullptr, const uint32_t* n_dev = nullptr);
 
 // ---- MuHash product trees (kgv_muhash.cu) ----
 // Reserve the level-0 element arrays of the two trees (denominator = removed elements, numerator = added elements):
@@ -74,6 +86,10 @@ int kgv_mu_reserve(kgv_ctx* ctx, size_t n_den, size_t n_num, uint32_t** e_den, u
 // Multiply each tree down to one value (denominator on ctx->stream, numerator on the side stream) and write the two
 // canonical residues (384 little-endian bytes each) to host or device memory.
 int kgv_mu_reduce(kgv_ctx* ctx, size_t n_den, size_t n_num, uint8_t* out_num384, uint8_t* out_den384);
+// out + g * out_pitch_words = product of the level-0 elements E[lo[g] .. hi[g]) with flags[flag_index[j]] != 0 (one 16-lane group per range)
+int kgv_mu_range_products(kgv_ctx* ctx, const uint32_t* E, size_t stride, const uint8_t* flags, const uint32_t* flag_index, const uint32_t* lo, const uint32_t* hi, uint32_t n_segs,
+                          uint32_t* out, size_t out_pitch_words, cudaStream_t st);
+int kgv_mu_canonicalize(kgv_ctx* ctx, uint32_t* vals, size_t pitch_words, size_t n, cudaStream_t st);
 
 // ---- shared pieces of the validation path (kgv_validate.cu) ----
 struct kgv_utxo_table;
@@ -83,3 +99,12 @@ struct kgv_utxo_table;
 // buf holds all ranks' contributions.  Peer transport if the communicator is connected, else NCCL (in place).
 int kgv_comm_exchange_slices(kgv_ctx* ctx, struct kgv_comm* c, uint8_t* buf, size_t per);
 int kgv_comm_ranks(const struct kgv_comm* c, int* rank);
+
+// ---- signature cache (kgv_sigcache.cu): device verdict table keyed by BLAKE2b-256(kind || sig || pk || msg) ----
+// Looks every item up; status[i] = cached verdict or 0xFF; writes the digests (32 B per item, reused by the insert), the compacted list of
+// misses and their count (device).  Enqueued on `st`.
+int kgv_sigcache_lookup(kgv_ctx* ctx, struct kgv_sigcache* c, const uint8_t* pk, const uint8_t* msg, const uint8_t* sig, size_t n, bool ecdsa, uint8_t* status, uint8_t* digests,
+                        uint32_t* miss_index, uint32_t* n_miss_dev, cudaStream_t st);
+// remembers the verdicts (0 / 1 only, as the reference: parse errors never reach its cache) of the listed items
+int kgv_sigcache_insert(kgv_ctx* ctx, struct kgv_sigcache* c, const uint8_t* status, const uint8_t* digests, const uint32_t* miss_index, const uint32_t* n_miss_dev, size_t n_max,
+                        cudaStream_t st);

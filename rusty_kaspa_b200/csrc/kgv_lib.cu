@@ -87,9 +87,11 @@ __global__ void __launch_bounds__(128) k_build_gtab(uint32_t* __restrict__ gtab)
 // cross-thread synchronisation.  Pending state sits in (L1-resident) local memory between the phases.
 template <bool ALIGNED>
 __global__ void __launch_bounds__(KGV_BLOCK, KGV_BLOCKS_PER_SM)
-k_schnorr_verify(const uint8_t* __restrict__ pk, const uint8_t* __restrict__ msg, const uint8_t* __restrict__ sig, size_t n,
-                 uint8_t* __restrict__ status, const uint32_t* __restrict__ gtab) {
+k_schnorr_verify(const uint8_t* __restrict__ pk, const uint8_t* __restrict__ msg, const uint8_t* __restrict__ sig, size_t n_arg,
+                 uint8_t* __restrict__ status, const uint32_t* __restrict__ gtab, const uint32_t* __restrict__ index, const uint32_t* __restrict__ n_dev) {
+  // index / n_dev (both optional): verify only the listed items (the signature-cache misses), their count read on the device
   extern __shared__ uint32_t smem[];
+  const size_t n = n_dev ? (size_t)*n_dev : n_arg;
   const size_t total = (size_t)gridDim.x * KGV_BLOCK;
   const size_t tid = (size_t)blockIdx.x * KGV_BLOCK + threadIdx.x;
   SmemTab tab{smem + threadIdx.x};
@@ -107,6 +109,7 @@ k_schnorr_verify(const uint8_t* __restrict__ pk, const uint8_t* __restrict__ msg
     size_t i = base + tid + (size_t)j * total;
     st[j] = KGV_ST_INVALID;
     if (i >= n) continue;
+    if (index) i = index[i];
     uint32_t pkw[8], mw[8], sw[16];
     load_be32<ALIGNED>(pkw, pk + 32 * i);
     load_be32<ALIGNED>(mw, msg + 32 * i);
@@ -137,7 +140,7 @@ k_schnorr_verify(const uint8_t* __restrict__ pk, const uint8_t* __restrict__ msg
 #pragma unroll 1
   for (int j = 0; j < KGV_ITEMS; j++) {
     size_t i = base + tid + (size_t)j * total;
-    if (i < n) status[i] = st[j];
+    if (i < n) status[index ? index[i] : i] = st[j];
   }
   }
 }
@@ -146,9 +149,10 @@ struct sc_words { uint32_t v[8]; };
 
 template <bool ALIGNED>
 __global__ void __launch_bounds__(KGV_BLOCK, KGV_BLOCKS_PER_SM)
-k_ecdsa_verify(const uint8_t* __restrict__ pk, const uint8_t* __restrict__ msg, const uint8_t* __restrict__ sig, size_t n,
-               uint8_t* __restrict__ status, const uint32_t* __restrict__ gtab) {
+k_ecdsa_verify(const uint8_t* __restrict__ pk, const uint8_t* __restrict__ msg, const uint8_t* __restrict__ sig, size_t n_arg,
+               uint8_t* __restrict__ status, const uint32_t* __restrict__ gtab, const uint32_t* __restrict__ index, const uint32_t* __restrict__ n_dev) {
   extern __shared__ uint32_t smem[];
+  const size_t n = n_dev ? (size_t)*n_dev : n_arg;
   const size_t total = (size_t)gridDim.x * KGV_BLOCK;
   const size_t tid = (size_t)blockIdx.x * KGV_BLOCK + threadIdx.x;
   SmemTab tab{smem + threadIdx.x};
@@ -164,6 +168,7 @@ k_ecdsa_verify(const uint8_t* __restrict__ pk, const uint8_t* __restrict__ msg, 
     size_t i = base + tid + (size_t)j * total;
     st[j] = KGV_ST_INVALID;
     if (i >= n) continue;
+    if (index) i = index[i];
     uint32_t pkw[8], mw[8], sw[16];
     const uint8_t* kp = pk + 33 * i;  // 33-byte stride: never word aligned
     uint32_t tag = kp[0];
@@ -198,7 +203,7 @@ k_ecdsa_verify(const uint8_t* __restrict__ pk, const uint8_t* __restrict__ msg, 
 #pragma unroll 1
   for (int j = 0; j < KGV_ITEMS; j++) {
     size_t i = base + tid + (size_t)j * total;
-    if (i < n) status[i] = st[j];
+    if (i < n) status[index ? index[i] : i] = st[j];
   }
   }
 }
@@ -296,21 +301,26 @@ int kgv_ptr_is_device(const void* p) {
   return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
 
-// Per-call device buffers grow through the stream-ordered allocator (cudaMallocAsync / cudaFreeAsync on the context's stream):
-// cudaFree would synchronise the WHOLE device, which deadlocks a process that drives several contexts of one device whose
-// kernels wait for each other (the peer-exchange wait kernels of kgv_comm.cu), and stalls unrelated streams everywhere else.
+// Per-call device buffers only ever grow.  The outgrown allocation is NOT freed on the spot: cudaFree synchronises the whole device, which
+// stalls every other stream and deadlocks a process that drives several contexts of one device whose kernels wait for each other (the
+// peer-exchange wait kernels of kgv_comm.cu); cudaMallocAsync was tried and blocks in the same situation (measured).  Outgrown buffers are
+// parked and released by kgv_synchronize / kgv_destroy, i.e. at points where the caller has declared the context idle.  Growth is
+// geometric (x1.25), so the parked memory stays below ~4x the live buffer.
 int kgv_reserve(kgv_ctx* ctx, uint8_t** buf, size_t* cap, size_t need) {
   if (*cap >= need) return KGV_OK;
-  if (*buf) {
-    // work of this call already queued on the side stream may still read the old buffer
-    CK(cudaEventRecord(ctx->ev_join, ctx->aux_stream));
-    CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
-    CK(cudaFreeAsync(*buf, ctx->stream));
-    *buf = nullptr; *cap = 0;
-  }
+  if (*buf) { ctx->parked.push_back(*buf); *buf = nullptr; *cap = 0; }
   size_t want = need + need / 4 + 4096;
-  cudaError_t e = cudaMallocAsync((void**)buf, want, ctx->stream);
-  if (e != cudaSuccess) { ctx->err = std::string("cudaMallocAsync failed: ") + cudaGetErrorString(e); (void)cudaGetLastError(); *buf = nullptr; return KGV_ERR_NOMEM; }
+  cudaError_t e = cudaMalloc((void**)buf, want);
+  if (e != cudaSuccess) {
+    // memory pressure: now it is worth a device synchronisation to give the parked buffers back and try again
+    (void)cudaGetLastError();
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->aux_stream);
+    for (uint8_t* p : ctx->parked) cudaFree(p);
+    ctx->parked.clear();
+    e = cudaMalloc((void**)buf, want);
+  }
+  if (e != cudaSuccess) { ctx->err = std::string("cudaMalloc failed: ") + cudaGetErrorString(e); (void)cudaGetLastError(); *buf = nullptr; return KGV_ERR_NOMEM; }
   *cap = want;
   return KGV_OK;
 }
@@ -365,8 +375,8 @@ extern "C" void kgv_destroy(kgv_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   if (ctx->gtab) cudaFree(ctx->gtab);
   for (uint8_t* b : {ctx->d_in, ctx->d_out, ctx->d_batch, ctx->d_scratch, ctx->d_mu, ctx->d_work, ctx->d_replay})
-    if (b) cudaFreeAsync(b, ctx->own_stream);
-  cudaStreamSynchronize(ctx->own_stream);
+    if (b) cudaFree(b);
+  for (uint8_t* b : ctx->parked) cudaFree(b);
   for (cudaEvent_t e : ctx->ev_chunk) if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : ctx->ev_time) if (e) cudaEventDestroy(e);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
@@ -395,6 +405,11 @@ extern "C" int kgv_synchronize(kgv_ctx* ctx) {
   std::lock_guard<std::recursive_mutex> g(ctx->mu);
   CK(cudaSetDevice(ctx->device));
   CK(cudaStreamSynchronize(ctx->stream));
+  if (!ctx->parked.empty()) {  // the caller declared the context idle: outgrown buffers can go
+    CK(cudaStreamSynchronize(ctx->aux_stream));
+    for (uint8_t* p : ctx->parked) cudaFree(p);
+    ctx->parked.clear();
+  }
   return KGV_OK;
 }
 
@@ -405,7 +420,7 @@ extern "C" uint64_t kgv_launch_count(const kgv_ctx* ctx) { return ctx ? ctx->lau
 // signature verification entry points
 // ---------------------------------------------------------------------------------------------
 int kgv_launch_verify(kgv_ctx* ctx, const uint8_t* dpk, const uint8_t* dmsg, const uint8_t* dsig, size_t n, uint8_t* dst, bool ecdsa,
-                      cudaStream_t on, bool use_on) {
+                      cudaStream_t on, bool use_on, const uint32_t* index, const uint32_t* n_dev) {
   if (n == 0) return KGV_OK;
   cudaStream_t st = use_on ? on : ctx->stream;
   const int smem = KGV_BLOCK * 128 * (int)sizeof(uint32_t);
@@ -415,11 +430,11 @@ int kgv_launch_verify(kgv_ctx* ctx, const uint8_t* dpk, const uint8_t* dmsg, con
   unsigned blocks = (unsigned)(want < (size_t)ctx->resident_blocks ? want : (size_t)ctx->resident_blocks);
   bool aligned = (((uintptr_t)dmsg | (uintptr_t)dsig | (ecdsa ? 0 : (uintptr_t)dpk)) & 31) == 0;
   if (ecdsa) {
-    if (aligned) k_ecdsa_verify<true><<<blocks, KGV_BLOCK, smem, st>>>(dpk, dmsg, dsig, n, dst, ctx->gtab);
-    else k_ecdsa_verify<false><<<blocks, KGV_BLOCK, smem, st>>>(dpk, dmsg, dsig, n, dst, ctx->gtab);
+    if (aligned) k_ecdsa_verify<true><<<blocks, KGV_BLOCK, smem, st>>>(dpk, dmsg, dsig, n, dst, ctx->gtab, index, n_dev);
+    else k_ecdsa_verify<false><<<blocks, KGV_BLOCK, smem, st>>>(dpk, dmsg, dsig, n, dst, ctx->gtab, index, n_dev);
   } else {
-    if (aligned) k_schnorr_verify<true><<<blocks, KGV_BLOCK, smem, st>>>(dpk, dmsg, dsig, n, dst, ctx->gtab);
-    else k_schnorr_verify<false><<<blocks, KGV_BLOCK, smem, st>>>(dpk, dmsg, dsig, n, dst, ctx->gtab);
+    if (aligned) k_schnorr_verify<true><<<blocks, KGV_BLOCK, smem, st>>>(dpk, dmsg, dsig, n, dst, ctx->gtab, index, n_dev);
+    else k_schnorr_verify<false><<<blocks, KGV_BLOCK, smem, st>>>(dpk, dmsg, dsig, n, dst, ctx->gtab, index, n_dev);
   }
   CK(cudaGetLastError());
   ctx->launches++;

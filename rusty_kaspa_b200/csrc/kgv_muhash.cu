@@ -288,3 +288,284 @@ extern "C" int kgv_muhash_finalize(kgv_ctx* ctx, const uint8_t* numerator384, co
   if (!odev) CK(cudaStreamSynchronize(ctx->stream));
   return KGV_OK;
 }
+
+
+// ---------------------------------------------------------------------------------------------
+// Batched MuHash work for a replay window: segmented products, running (prefix) products and ONE modular inversion for any number
+// of finalizations.  All values here are contiguous 96-word little-endian residues ("pitch" words apart); every multiplication is
+// done by a 16-lane group (u3072_coop_mul_mod), 8 groups per block.
+// Reference: MuHash::combine chain of calculate_utxo_state (utxo_validation.rs:144) and MuHash::finalize per chain block (:188-192,
+// crypto/muhash/src/lib.rs:98-115).  The reference pays one 3072-bit inversion per chain block; here n finalizations cost one
+// inversion + 5n multiplications (Montgomery's trick with prefix / suffix products built by parallel scans).
+// Zero is not handled specially (a MuHash element is 0 or p only if a ChaCha20 stream is all-zero / equals p: probability 2^-3072).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void coop_copy(int lane, bool act, uint32_t* dst, const uint32_t* src) {
+  if (act && lane < KGV_U3072_BLOCKS) {
+    uint32_t r[8];
+    u3072_load_block(r, src, 1, 0, lane);
+    u3072_store_block(dst, 1, 0, lane, r);
+  }
+  __syncwarp();
+}
+__device__ __forceinline__ void coop_set_one(int lane, bool act, uint32_t* dst) {
+  if (act && lane < KGV_U3072_BLOCKS) {
+    uint32_t r[8] = {lane == 0 ? 1u : 0u, 0, 0, 0, 0, 0, 0, 0};
+    u3072_store_block(dst, 1, 0, lane, r);
+  }
+  __syncwarp();
+}
+
+// out[g] = product of the level-0 elements E[lo[g] .. hi[g]) whose flag is set (flags == nullptr: all); empty product = 1
+__global__ void __launch_bounds__(128) k_u3072_range_product(const uint32_t* __restrict__ E, size_t stride, const uint8_t* __restrict__ flags, const uint32_t* __restrict__ flag_index,
+                                                             const uint32_t* __restrict__ lo, const uint32_t* __restrict__ hi, uint32_t n_segs, uint32_t* __restrict__ out,
+                                                             size_t out_pitch) {
+  __shared__ U3072Coop sm[KGV_COOP_GROUPS];
+  const int grp = threadIdx.x >> 4, lane = threadIdx.x & 15;
+  const uint32_t g = blockIdx.x * KGV_COOP_GROUPS + grp;
+  const bool mine = g < n_segs;
+  const uint32_t a = mine ? lo[g] : 0, b = mine ? hi[g] : 0;
+  // both groups of a warp walk in lockstep: the trip count is the longer of the two ranges
+  const uint32_t len = b - a;
+  const uint32_t other = __shfl_xor_sync(0xFFFFFFFFu, len, 16);
+  const uint32_t trips = len > other ? len : other;
+  uint32_t* acc = out + out_pitch * (size_t)(mine ? g : 0);
+  bool started = false;
+  for (uint32_t it = 0; it < trips; it++) {
+    const uint32_t j = a + it;
+    const bool have = mine && j < b && (!flags || flags[flag_index ? flag_index[j] : j]);
+    if (have && !started && lane < KGV_U3072_BLOCKS) {
+      uint32_t r[8];
+      u3072_load_block(r, E, stride, j, lane);
+      u3072_store_block(acc, 1, 0, lane, r);
+    }
+    __syncwarp();
+    u3072_coop_mul_mod(sm[grp], lane, have && started, acc, 1, 0, acc, 1, 0, E, stride, j);
+    started = started || have;
+  }
+  coop_set_one(lane, mine && !started, acc);
+}
+
+// element i of a value array with a pitch (in words); rev walks the array backwards
+__device__ __forceinline__ uint32_t* u3072_at(uint32_t* base, size_t pitch, size_t n, size_t i, bool rev) { return base + pitch * (rev ? n - 1 - i : i); }
+
+// blocked inclusive scan (products), three launches: chunks in parallel, then the chunk totals, then the carry-in of every chunk
+#define KGV_SCAN_CHUNK 32
+__global__ void __launch_bounds__(128) k_u3072_scan_chunks(uint32_t* __restrict__ vals, size_t pitch, size_t n, bool rev) {
+  __shared__ U3072Coop sm[KGV_COOP_GROUPS];
+  const int grp = threadIdx.x >> 4, lane = threadIdx.x & 15;
+  const size_t c = (size_t)blockIdx.x * KGV_COOP_GROUPS + grp;
+  const size_t first = c * KGV_SCAN_CHUNK;
+  for (size_t k = 1; k < KGV_SCAN_CHUNK; k++) {
+    const bool act = first + k < n;
+    uint32_t* cur = u3072_at(vals, pitch, n, act ? first + k : 0, rev);
+    const uint32_t* prev = u3072_at(vals, pitch, n, act ? first + k - 1 : 0, rev);
+    u3072_coop_mul_mod(sm[grp], lane, act, cur, 1, 0, cur, 1, 0, prev, 1, 0);
+  }
+}
+// tot[c] = product of chunks 0..c (inclusive), sequentially by one group (n / 32 multiplications)
+__global__ void __launch_bounds__(32) k_u3072_scan_totals(uint32_t* __restrict__ vals, size_t pitch, size_t n, bool rev, uint32_t* __restrict__ tot) {
+  __shared__ U3072Coop sm;
+  const int lane = threadIdx.x & 15;
+  const bool act = threadIdx.x < 16;
+  const size_t n_chunks = (n + KGV_SCAN_CHUNK - 1) / KGV_SCAN_CHUNK;
+  for (size_t c = 0; c < n_chunks; c++) {
+    const size_t last = (c + 1) * KGV_SCAN_CHUNK - 1 < n ? (c + 1) * KGV_SCAN_CHUNK - 1 : n - 1;
+    const uint32_t* v = u3072_at(vals, pitch, n, last, rev);
+    if (c == 0) coop_copy(lane, act, tot, v);
+    else u3072_coop_mul_mod(sm, lane, act, tot + 96 * c, 1, 0, tot + 96 * (c - 1), 1, 0, v, 1, 0);
+  }
+}
+__global__ void __launch_bounds__(128) k_u3072_scan_apply(uint32_t* __restrict__ vals, size_t pitch, size_t n, bool rev, const uint32_t* __restrict__ tot) {
+  __shared__ U3072Coop sm[KGV_COOP_GROUPS];
+  const int grp = threadIdx.x >> 4, lane = threadIdx.x & 15;
+  const size_t i = (size_t)blockIdx.x * KGV_COOP_GROUPS + grp + KGV_SCAN_CHUNK;  // the first chunk has no carry-in
+  const bool act = i < n;
+  uint32_t* cur = u3072_at(vals, pitch, n, act ? i : 0, rev);
+  u3072_coop_mul_mod(sm[grp], lane, act, cur, 1, 0, cur, 1, 0, tot + 96 * (act ? i / KGV_SCAN_CHUNK - 1 : 0), 1, 0);
+}
+// vals[0] *= init  (start of a running product)
+__global__ void __launch_bounds__(32) k_u3072_mul_first(uint32_t* __restrict__ vals, const uint32_t* __restrict__ init, int n_arrays, size_t array_off) {
+  __shared__ U3072Coop sm[2];
+  const int grp = threadIdx.x >> 4, lane = threadIdx.x & 15;
+  const bool act = grp < n_arrays;
+  uint32_t* v = vals + array_off * (act ? grp : 0);
+  u3072_coop_mul_mod(sm[grp], lane, act, v, 1, 0, v, 1, 0, init + 96 * (act ? grp : 0), 1, 0);
+}
+
+// inv = a^(p-2): p - 2 = (2^3051 - 1) * 2^21 + 993433 (3 072 squarings, ~30 multiplications), one 16-lane group.  w: [a | cur | saved]
+__device__ __forceinline__ void coop_inverse(U3072Coop* sm, int lane, bool act, uint32_t* a, uint32_t* cur, uint32_t* saved) {
+  auto mul = [&](uint32_t* r, const uint32_t* x, const uint32_t* y) { coop_mul_contig(sm, lane, act, r, x, y); };
+  coop_copy(lane, act, cur, a);
+  int k = 1;
+  for (int bit = 10; bit >= 0; bit--) {  // cur = a^(2^k - 1), k following the bits of 3051 = 0b101111101011 from the top
+    coop_copy(lane, act, saved, cur);
+    for (int q = 0; q < k; q++) mul(cur, cur, cur);
+    mul(cur, cur, saved);
+    k *= 2;
+    if ((3051 >> bit) & 1) { mul(cur, cur, cur); mul(cur, cur, a); k += 1; }
+  }
+  for (int bit = 20; bit >= 0; bit--) {
+    mul(cur, cur, cur);
+    if ((993433u >> bit) & 1u) mul(cur, cur, a);
+  }
+}
+__global__ void __launch_bounds__(32) k_u3072_inverse_one(uint32_t* __restrict__ w) {
+  __shared__ U3072Coop sm;
+  coop_inverse(&sm, threadIdx.x & 15, threadIdx.x < 16, w, w + 96, w + 192);
+}
+// Montgomery's trick, parallel form: inv_i = I * P[i-1] * S[i+1] with P / S the prefix / suffix products of the denominators and
+// I = 1 / P[n-1]; then value_i = num_i * inv_i.  out: n contiguous values
+__global__ void __launch_bounds__(128) k_muhash_divide_all(const uint32_t* __restrict__ num, size_t num_pitch, const uint32_t* __restrict__ P, const uint32_t* __restrict__ S,
+                                                           const uint32_t* __restrict__ I, size_t n, uint32_t* __restrict__ out) {
+  __shared__ U3072Coop sm[KGV_COOP_GROUPS];
+  const int grp = threadIdx.x >> 4, lane = threadIdx.x & 15;
+  const size_t i = (size_t)blockIdx.x * KGV_COOP_GROUPS + grp;
+  const bool act = i < n;
+  const size_t k = act ? i : 0;
+  uint32_t* o = out + 96 * k;
+  coop_copy(lane, act, o, I);
+  u3072_coop_mul_mod(sm[grp], lane, act && k > 0, o, 1, 0, o, 1, 0, P + 96 * (k > 0 ? k - 1 : 0), 1, 0);
+  u3072_coop_mul_mod(sm[grp], lane, act && k + 1 < n, o, 1, 0, o, 1, 0, S + 96 * (k + 1 < n ? k + 1 : 0), 1, 0);
+  u3072_coop_mul_mod(sm[grp], lane, act, o, 1, 0, o, 1, 0, num + num_pitch * k, 1, 0);
+}
+__global__ void __launch_bounds__(128) k_muhash_emit_hashes(const uint32_t* __restrict__ vals, size_t n, uint32_t* __restrict__ serialized, uint32_t* __restrict__ hashes) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t r[96];
+  u3072_canonical(r, vals + 96 * i, 1, 0);
+  Blake2b h;
+  b2b_init_muhash_finalize(h);
+  for (int k = 0; k < 96; k++) { if (serialized) serialized[96 * i + k] = r[k]; b2b_u32(h, r[k]); }
+  uint64_t d[4];
+  b2b_final(h, d);
+  for (int k = 0; k < 4; k++) { hashes[8 * i + 2 * k] = (uint32_t)d[k]; hashes[8 * i + 2 * k + 1] = (uint32_t)(d[k] >> 32); }
+}
+__global__ void k_u3072_canonicalize(uint32_t* __restrict__ vals, size_t pitch, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t r[96];
+  u3072_canonical(r, vals + pitch * i, 1, 0);
+  for (int k = 0; k < 96; k++) vals[pitch * i + k] = r[k];
+}
+
+// inclusive scan of n values (device array, pitch words apart) on stream st; tot: scratch for ceil(n/32) values
+int kgv_mu_scan(kgv_ctx* ctx, uint32_t* vals, size_t pitch, size_t n, bool rev, uint32_t* tot, cudaStream_t st) {
+  if (n <= 1) return KGV_OK;
+  const size_t n_chunks = (n + KGV_SCAN_CHUNK - 1) / KGV_SCAN_CHUNK;
+  k_u3072_scan_chunks<<<nblk(n_chunks, KGV_COOP_GROUPS), 128, 0, st>>>(vals, pitch, n, rev);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  if (n_chunks > 1) {
+    k_u3072_scan_totals<<<1, 32, 0, st>>>(vals, pitch, n, rev, tot);
+    CK(cudaGetLastError());
+    k_u3072_scan_apply<<<nblk(n - KGV_SCAN_CHUNK, KGV_COOP_GROUPS), 128, 0, st>>>(vals, pitch, n, rev, tot);
+    CK(cudaGetLastError());
+    ctx->launches += 2;
+  }
+  return KGV_OK;
+}
+
+extern "C" int kgv_muhash_finalize_batch(kgv_ctx* ctx, const uint8_t* numerators384, const uint8_t* denominators384, size_t n, size_t pitch_bytes, uint8_t* serialized384,
+                                         uint8_t* hashes32) {
+  if (!ctx) return KGV_ERR_ARG;
+  std::lock_guard<std::recursive_mutex> g(ctx->mu);
+  if (n == 0) return KGV_OK;
+  if (!numerators384 || !denominators384 || !hashes32 || pitch_bytes < 384 || (pitch_bytes & 3)) { ctx->err = "bad argument"; return KGV_ERR_ARG; }
+  CK(cudaSetDevice(ctx->device));
+  const bool dev = kgv_ptr_is_device(numerators384);
+  if (kgv_ptr_is_device(denominators384) != dev || kgv_ptr_is_device(hashes32) != dev) { ctx->err = "all buffers of one call must be host pointers or all device pointers"; return KGV_ERR_ARG; }
+  const size_t n_chunks = (n + KGV_SCAN_CHUNK - 1) / KGV_SCAN_CHUNK;
+  // layout: [num in (host path only)] [P n] [S n] [out n] [tot chunks] [inverse scratch 3] [hashes n*32 (host path)] [serialized (host path)]
+  const size_t span = (n - 1) * pitch_bytes + 384;
+  size_t o_num = 0, o_den = al256(dev ? 0 : span), o_P = al256(o_den + (dev ? 0 : span)), o_S = al256(o_P + n * 384), o_out = al256(o_S + n * 384), o_tot = al256(o_out + n * 384),
+         o_inv = al256(o_tot + n_chunks * 384), o_h = al256(o_inv + 3 * 384), o_ser = al256(o_h + n * 32);
+  int rc = kgv_reserve(ctx, &ctx->d_mu, &ctx->d_mu_cap, al256(o_ser + (serialized384 ? n * 384 : 0)));
+  if (rc) return rc;
+  uint8_t* M = ctx->d_mu;
+  cudaStream_t st = ctx->stream;
+  const uint32_t* dnum = (const uint32_t*)numerators384;
+  const uint32_t* dden = (const uint32_t*)denominators384;
+  if (!dev) {
+    // a strided host array is one contiguous span (the pitch interleaves numerators and denominators of MuHash records)
+    CK(cudaMemcpyAsync(M + o_num, numerators384, span, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(M + o_den, denominators384, span, cudaMemcpyHostToDevice, st));
+    dnum = (const uint32_t*)(M + o_num); dden = (const uint32_t*)(M + o_den);
+  }
+  uint32_t *P = (uint32_t*)(M + o_P), *S = (uint32_t*)(M + o_S), *out = (uint32_t*)(M + o_out), *tot = (uint32_t*)(M + o_tot), *inv = (uint32_t*)(M + o_inv);
+  CK(cudaMemcpy2DAsync(P, 384, dden, pitch_bytes, 384, n, cudaMemcpyDeviceToDevice, st));
+  CK(cudaMemcpyAsync(S, P, n * 384, cudaMemcpyDeviceToDevice, st));
+  rc = kgv_mu_scan(ctx, P, 96, n, false, tot, st);
+  if (rc) return rc;
+  rc = kgv_mu_scan(ctx, S, 96, n, true, tot, st);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(inv, P + 96 * (n - 1), 384, cudaMemcpyDeviceToDevice, st));
+  k_u3072_inverse_one<<<1, 32, 0, st>>>(inv);
+  CK(cudaGetLastError());
+  k_muhash_divide_all<<<nblk(n, KGV_COOP_GROUPS), 128, 0, st>>>(dnum, pitch_bytes / 4, P, S, inv + 96, n, out);
+  CK(cudaGetLastError());
+  uint32_t* dh = dev ? (uint32_t*)hashes32 : (uint32_t*)(M + o_h);
+  uint32_t* dser = !serialized384 ? nullptr : (dev ? (uint32_t*)serialized384 : (uint32_t*)(M + o_ser));
+  k_muhash_emit_hashes<<<nblk(n, 128), 128, 0, st>>>(out, n, dser, dh);
+  CK(cudaGetLastError());
+  ctx->launches += 3;
+  if (!dev) {
+    CK(cudaMemcpyAsync(hashes32, dh, n * 32, cudaMemcpyDeviceToHost, st));
+    if (serialized384) CK(cudaMemcpyAsync(serialized384, dser, n * 384, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+  }
+  return KGV_OK;
+}
+
+extern "C" int kgv_muhash_prefix_combine(kgv_ctx* ctx, const uint8_t* init768, uint8_t* values768, size_t n) {
+  if (!ctx) return KGV_ERR_ARG;
+  std::lock_guard<std::recursive_mutex> g(ctx->mu);
+  if (n == 0) return KGV_OK;
+  if (!values768) { ctx->err = "null argument"; return KGV_ERR_ARG; }
+  CK(cudaSetDevice(ctx->device));
+  const bool dev = kgv_ptr_is_device(values768);
+  const size_t n_chunks = (n + KGV_SCAN_CHUNK - 1) / KGV_SCAN_CHUNK;
+  size_t o_v = 0, o_tot = al256(dev ? 0 : n * 768), o_init = al256(o_tot + n_chunks * 384);
+  int rc = kgv_reserve(ctx, &ctx->d_mu, &ctx->d_mu_cap, al256(o_init + 768));
+  if (rc) return rc;
+  uint8_t* M = ctx->d_mu;
+  cudaStream_t st = ctx->stream;
+  uint32_t* v = (uint32_t*)values768;
+  if (!dev) { CK(cudaMemcpyAsync(M + o_v, values768, n * 768, cudaMemcpyHostToDevice, st)); v = (uint32_t*)(M + o_v); }
+  if (init768) {
+    CK(cudaMemcpyAsync(M + o_init, init768, 768, kgv_ptr_is_device(init768) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+    k_u3072_mul_first<<<1, 32, 0, st>>>(v, (const uint32_t*)(M + o_init), 2, 96);
+    CK(cudaGetLastError());
+    ctx->launches++;
+  }
+  uint32_t* tot = (uint32_t*)(M + o_tot);
+  rc = kgv_mu_scan(ctx, v, 192, n, false, tot, st);        // numerators
+  if (rc) return rc;
+  rc = kgv_mu_scan(ctx, v + 96, 192, n, false, tot, st);   // denominators
+  if (rc) return rc;
+  k_u3072_canonicalize<<<nblk(2 * n, 128), 128, 0, st>>>(v, 96, 2 * n);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  if (!dev) {
+    CK(cudaMemcpyAsync(values768, v, n * 768, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+  }
+  return KGV_OK;
+}
+
+// products of ranges of level-0 elements (kgv_replay_muhash): E has `stride` elements; flags[flag_index[j]] != 0 selects element j
+int kgv_mu_range_products(kgv_ctx* ctx, const uint32_t* E, size_t stride, const uint8_t* flags, const uint32_t* flag_index, const uint32_t* lo, const uint32_t* hi, uint32_t n_segs,
+                          uint32_t* out, size_t out_pitch_words, cudaStream_t st) {
+  if (n_segs == 0) return KGV_OK;
+  k_u3072_range_product<<<nblk(n_segs, KGV_COOP_GROUPS), 128, 0, st>>>(E, stride, flags, flag_index, lo, hi, n_segs, out, out_pitch_words);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  return KGV_OK;
+}
+
+int kgv_mu_canonicalize(kgv_ctx* ctx, uint32_t* vals, size_t pitch_words, size_t n, cudaStream_t st) {
+  if (!n) return KGV_OK;
+  k_u3072_canonicalize<<<nblk(n, 128), 128, 0, st>>>(vals, pitch_words, n);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  return KGV_OK;
+}

@@ -155,12 +155,47 @@ __device__ __forceinline__ void prefetch_range(const void* p, size_t bytes, uint
   for (uintptr_t q = lo + 128 * (uintptr_t)rtid; q < hi; q += 128 * (uintptr_t)nth) prefetch_l2((const void*)q);
 }
 
-// The walk is a chain of dependent memory accesses per block (record -> key -> slot -> entry -> verdict -> slot update); left to
-// itself every link is a DRAM miss (~1 us) and a block costs ~20 us.  So the kernel runs a two-block look-ahead entirely with
-// L2 prefetches: while block b is decided, the records of block b+2 (transactions, inputs, outputs, ids, script verdicts) are
-// prefetched by address range, and for block b+1 - whose records are L2 hits by then - the table slots its inputs will probe,
-// the slots its outputs will be inserted into and the script bytes those inserts copy.  The walk itself then only meets L2 hits.
+// The walk is a chain of dependent memory accesses per block (record -> key -> slot -> entry -> verdict -> slot update).  Left in global
+// memory every link costs an L2 round trip (~0.3 us on a two-die B200) or a DRAM miss (~1 us): ~40 links = 17-20 us per block (measured).
+// So each block is STAGED in shared memory first: all 1024 threads copy its transaction / input / output records, tx ids, script verdicts
+// and index maps with independent 8-byte loads (one memory latency for everything), then the output scripts the inserts will store; the
+// three phases then run out of shared memory and touch global memory only for the table itself (probe, claim, store) and for the results.
+// Table lines are prefetched into L2 one block ahead, record ranges two blocks ahead.  Blocks too large for the staging area take the
+// same code path with the pointers left on the global arrays.
+#define RP_MAXT 320u
+#define RP_MAXI 640u
+#define RP_MAXO 768u
+#define RP_SCR 40u  // staged bytes per output script (standard scripts are 34 / 35 bytes)
+struct ReplaySmem {
+  kgv_tx txs[RP_MAXT];
+  kgv_input inputs[RP_MAXI];
+  kgv_output outputs[RP_MAXO];
+  uint64_t ids[4 * RP_MAXT];
+  kgv_tx_result pre[RP_MAXT];
+  DevEntry dent[RP_MAXI];
+  UtxoSlot* slot[RP_MAXI];
+  uint32_t itx[RP_MAXI];
+  uint32_t otx[RP_MAXO];
+  uint32_t scr[RP_MAXO][RP_SCR / 4];
+  uint8_t acc[RP_MAXT];
+};
+
+__device__ __forceinline__ void copy8(void* dst, const void* src, size_t bytes, uint32_t tid, uint32_t nth) {  // both 8-byte aligned
+  const size_t n = bytes >> 3;
+  const uint64_t* s = (const uint64_t*)src;
+  uint64_t* d = (uint64_t*)dst;
+  for (size_t i = tid; i < n; i += nth) d[i] = s[i];
+}
+__device__ __forceinline__ void copy4(void* dst, const void* src, size_t bytes, uint32_t tid, uint32_t nth) {
+  const size_t n = bytes >> 2;
+  const uint32_t* s = (const uint32_t*)src;
+  uint32_t* d = (uint32_t*)dst;
+  for (size_t i = tid; i < n; i += nth) d[i] = s[i];
+}
+
 __global__ void __launch_bounds__(1024, 1) k_replay_inorder(ReplayArgs a) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  ReplaySmem& S = *reinterpret_cast<ReplaySmem*>(smem_raw);
   const uint32_t tid = threadIdx.x, nth = blockDim.x, rtid = nth - 1 - tid;
   __shared__ unsigned long long s_acc;
   __shared__ int s_live, s_tomb;  // table counter deltas of this launch (one global atomic at the end instead of one per entry)
@@ -203,11 +238,44 @@ __global__ void __launch_bounds__(1024, 1) k_replay_inorder(ReplayArgs a) {
     const ReplayRange bl = a.ranges[bi];
     prefetch_records(bi + 2);
     if (bl.t1 == bl.t0) { prefetch_slots(bi + 1); continue; }
-    const uint32_t i0 = bl.i0, i1 = bl.i1, o0 = bl.o0, o1 = bl.o1;
+    const uint32_t t0 = bl.t0, t1 = bl.t1, i0 = bl.i0, i1 = bl.i1, o0 = bl.o0, o1 = bl.o1;
+    const bool staged = t1 - t0 <= RP_MAXT && i1 - i0 <= RP_MAXI && o1 - o0 <= RP_MAXO;
+    // absolute-index views of this block's data: shared memory when staged, the global arrays otherwise
+    const kgv_tx* p_txs = a.b.txs;
+    const kgv_input* p_in = a.b.inputs;
+    const kgv_output* p_out = a.b.outputs;
+    const uint64_t* p_ids = a.ids;
+    const kgv_tx_result* p_pre = a.pre;
+    const uint32_t *p_itx = a.itx, *p_otx = a.otx;
+    DevEntry* p_dent = a.dent;
+    UtxoSlot** p_slot = a.slotp;
+    uint8_t* p_acc = a.accept;
+    if (staged) {
+      copy8(S.txs, a.b.txs + t0, (size_t)(t1 - t0) * sizeof(kgv_tx), tid, nth);
+      copy8(S.inputs, a.b.inputs + i0, (size_t)(i1 - i0) * sizeof(kgv_input), tid, nth);
+      copy8(S.outputs, a.b.outputs + o0, (size_t)(o1 - o0) * sizeof(kgv_output), tid, nth);
+      copy8(S.ids, a.ids + 4 * (size_t)t0, (size_t)(t1 - t0) * 32, tid, nth);
+      copy8(S.pre, a.pre + t0, (size_t)(t1 - t0) * sizeof(kgv_tx_result), tid, nth);
+      copy4(S.itx, a.itx + i0, (size_t)(i1 - i0) * 4, tid, nth);
+      copy4(S.otx, a.otx + o0, (size_t)(o1 - o0) * 4, tid, nth);
+      p_txs = S.txs - t0; p_in = S.inputs - i0; p_out = S.outputs - o0; p_ids = S.ids - 4 * (size_t)t0; p_pre = S.pre - t0;
+      p_itx = S.itx - i0; p_otx = S.otx - o0; p_dent = S.dent - i0; p_slot = S.slot - i0; p_acc = S.acc - t0;
+      __syncthreads();
+      if (!(bl.flags & KGV_REPLAY_VERIFY_ONLY))  // scripts the inserts will store (consumed in phase C, two barriers from here)
+        for (uint32_t o = o0 + rtid; o < o1; o += nth) {
+          const kgv_output& out = p_out[o];
+          if (out.script_len <= RP_SCR) {
+            uint32_t w[17];
+            load_script_words(w, a.b.bytes + out.script_off, out.script_len);
+#pragma unroll
+            for (int q = 0; q < (int)(RP_SCR / 4); q++) S.scr[o - o0][q] = w[q];
+          }
+        }
+    }
     // ---- A: populate from the table as it stands after the previous block (utxo_validation.rs:319-327)
     for (uint32_t i = i0 + tid; i < i1; i += nth) {
       uint32_t k[9];
-      input_key(k, a.b.inputs[i]);
+      input_key(k, p_in[i]);
       SlotHead h;
       UtxoSlot* s = table_find(a.t, k, h);
       DevEntry d;
@@ -222,53 +290,59 @@ __global__ void __launch_bounds__(1024, 1) k_replay_inorder(ReplayArgs a) {
           d.script = (const uint8_t*)dst;
         }
       } else entry_absent(d);
-      a.dent[i] = d;
-      a.slotp[i] = s;
+      p_dent[i] = d;
+      p_slot[i] = s;
+      if (staged) a.dent[i] = d;  // the global copy feeds kgv_replay_muhash
     }
     prefetch_slots(bi + 1);
     __syncthreads();
     // ---- B: context rules and the acceptance decision
-    for (uint32_t ti = bl.t0 + tid; ti < bl.t1; ti += nth) {
-      const bool cb = ti == bl.t0 || tx_is_coinbase(a.b.txs[ti]);
-      kgv_tx_result r = tx_context_rules(a.b, ti, bl.pov, KGV_FLAGS_SKIP_SCRIPT_CHECKS, a.prm, cb);
-      bool acc;
-      if (cb) acc = (ti == bl.t0) && (bl.flags & KGV_REPLAY_ACCEPT_COINBASE);
-      else {
-        acc = r.status == KGV_TX_OK;
-        if (acc && !(bl.flags & KGV_REPLAY_SKIP_SCRIPTS)) {
-          const kgv_tx_result p = a.pre[ti];
-          if (p.status != KGV_TX_OK) { r.status = p.status; r.script_err = p.script_err; r.fail_input = p.fail_input; acc = false; }
+    {
+      const BatchView sb{p_txs, p_in, p_out, p_dent, a.b.bytes};
+      for (uint32_t ti = t0 + tid; ti < t1; ti += nth) {
+        const bool cb = ti == t0 || tx_is_coinbase(p_txs[ti]);
+        kgv_tx_result r = tx_context_rules(sb, ti, bl.pov, KGV_FLAGS_SKIP_SCRIPT_CHECKS, a.prm, cb);
+        bool acc;
+        if (cb) acc = (ti == t0) && (bl.flags & KGV_REPLAY_ACCEPT_COINBASE);
+        else {
+          acc = r.status == KGV_TX_OK;
+          if (acc && !(bl.flags & KGV_REPLAY_SKIP_SCRIPTS)) {
+            const kgv_tx_result p = p_pre[ti];
+            if (p.status != KGV_TX_OK) { r.status = p.status; r.script_err = p.script_err; r.fail_input = p.fail_input; acc = false; }
+          }
         }
+        if (bl.flags & KGV_REPLAY_VERIFY_ONLY) acc = false;
+        a.res[ti] = r;
+        p_acc[ti] = acc ? 1 : 0;
+        if (staged) a.accept[ti] = acc ? 1 : 0;
+        if (acc && !cb) atomicAdd(&s_acc, 1ull);
       }
-      if (bl.flags & KGV_REPLAY_VERIFY_ONLY) acc = false;
-      a.res[ti] = r;
-      a.accept[ti] = acc ? 1 : 0;
-      if (acc && !cb) atomicAdd(&s_acc, 1ull);
     }
     __syncthreads();
     // ---- C: UtxoDiff::add_transaction straight into the table (utxo_diff.rs:233-247).  One CTA: the barrier orders these writes
     // before the next block's probes, no device-wide fence is needed inside the walk.
     if (!(bl.flags & KGV_REPLAY_VERIFY_ONLY)) {
       for (uint32_t i = i0 + tid; i < i1; i += nth) {
-        if (!a.accept[a.itx[i]]) continue;
-        UtxoSlot* s = a.slotp[i];
+        if (!p_acc[p_itx[i]]) continue;
+        UtxoSlot* s = p_slot[i];
         *(volatile uint32_t*)&s->state = SLOT_TOMB;
         atomicSub(&s_live, 1);
         atomicAdd(&s_tomb, 1);
       }
       for (uint32_t o = o0 + tid; o < o1; o += nth) {
-        const uint32_t ti = a.otx[o];
-        if (!a.accept[ti]) continue;
-        const kgv_tx& tx = a.b.txs[ti];
-        const kgv_output& out = a.b.outputs[o];
+        const uint32_t ti = p_otx[o];
+        if (!p_acc[ti]) continue;
+        const kgv_tx& tx = p_txs[ti];
+        const kgv_output& out = p_out[o];
         uint32_t k[9];
 #pragma unroll
-        for (int w = 0; w < 4; w++) { uint64_t q = a.ids[4 * (size_t)ti + w]; k[2 * w] = (uint32_t)q; k[2 * w + 1] = (uint32_t)(q >> 32); }
+        for (int w = 0; w < 4; w++) { uint64_t q = p_ids[4 * (size_t)ti + w]; k[2 * w] = (uint32_t)q; k[2 * w + 1] = (uint32_t)(q >> 32); }
         k[8] = o - tx.first_output;
-        table_put<false>(a.t, k, out.value, bl.pov, out.spk_version, (ti == bl.t0 || tx_is_coinbase(tx)) ? 1u : 0u, a.b.bytes + out.script_off, out.script_len, &s_live, &s_tomb);
+        const uint8_t* scr = (staged && out.script_len <= RP_SCR) ? (const uint8_t*)S.scr[o - o0] : a.b.bytes + out.script_off;
+        table_put<false>(a.t, k, out.value, bl.pov, out.spk_version, (ti == t0 || tx_is_coinbase(tx)) ? 1u : 0u, scr, out.script_len, &s_live, &s_tomb);
       }
-      __syncthreads();
     }
+    __syncthreads();
   }
   __threadfence();
   __syncthreads();
@@ -396,7 +470,9 @@ extern "C" int kgv_replay_window(kgv_ctx* ctx, kgv_utxo_table* table, const kgv_
   a.prm = *prm;
   a.pre = pre; a.res = res; a.accept = dacc; a.stats = cnt;
   if (stats) CK(cudaEventRecord(ctx->ev_time[1], st));
-  k_replay_inorder<<<1, 1024, 0, st>>>(a);
+  static bool smem_set = false;
+  if (!smem_set) { CK(cudaFuncSetAttribute(k_replay_inorder, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ReplaySmem))); smem_set = true; }
+  k_replay_inorder<<<1, 1024, sizeof(ReplaySmem), st>>>(a);
   CK(cudaGetLastError());
   ctx->launches++;
   if (stats) CK(cudaEventRecord(ctx->ev_time[2], st));
@@ -409,10 +485,124 @@ extern "C" int kgv_replay_window(kgv_ctx* ctx, kgv_utxo_table* table, const kgv_
     CK(cudaMemcpyAsync(&n_acc, cnt, 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
   }
+  ctx->last_replay.valid = true;
+  ctx->last_replay.txs = d.txs; ctx->last_replay.inputs = d.inputs; ctx->last_replay.outputs = d.outputs; ctx->last_replay.bytes = d.bytes;
+  ctx->last_replay.nt = nt; ctx->last_replay.ni = ni; ctx->last_replay.no = no; ctx->last_replay.n_blocks = n_blocks;
+  ctx->last_replay.o_ids = o_ids; ctx->last_replay.o_itx = o_itx; ctx->last_replay.o_otx = o_otx; ctx->last_replay.o_ent = o_ent; ctx->last_replay.o_acc = o_acc;
+  ctx->last_replay.o_txb = o_txb; ctx->last_replay.o_rng = o_rng;
   if (stats) {
     stats->n_accepted = n_acc; stats->n_sig_checks = n_items; stats->n_host_vm = n_vm;
     CK(cudaEventElapsedTime(&stats->pre_check_ms, ctx->ev_time[0], ctx->ev_time[1]));
     CK(cudaEventElapsedTime(&stats->in_order_ms, ctx->ev_time[1], ctx->ev_time[2]));
   }
+  return KGV_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// kgv_replay_muhash: MuHash::from_transaction of everything the last kgv_replay_window call accepted, combined per group of
+// blocks (the mergeset of one chain block): what calculate_utxo_state folds into ctx.multiset_hash (utxo_validation.rs:120,144).
+// Spent entries are the ones the in-order pass found at each block's position (kept in the window state with their scripts).
+// ---------------------------------------------------------------------------------------------
+__global__ void k_replay_tx_pov(const ReplayRange* __restrict__ ranges, const uint32_t* __restrict__ tx_block, uint32_t n_txs, uint64_t* __restrict__ tx_pov, uint8_t* __restrict__ tx_first) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_txs) return;
+  const ReplayRange r = ranges[tx_block[t]];
+  tx_pov[t] = r.pov;
+  tx_first[t] = t == r.t0 ? 1 : 0;
+}
+__global__ void __launch_bounds__(128) k_muhash_replay_elements(BatchView b, size_t n_inputs, size_t n_outputs, const uint32_t* __restrict__ input_tx, const uint32_t* __restrict__ output_tx,
+                                                                const uint8_t* __restrict__ accept, const uint64_t* __restrict__ txids, const uint64_t* __restrict__ tx_pov,
+                                                                const uint8_t* __restrict__ tx_first, uint32_t* __restrict__ e_den, uint32_t* __restrict__ e_num) {
+  size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < n_inputs) {
+    const uint32_t ti = input_tx[g];
+    const DevEntry& e = b.entries[g];
+    if (!accept[ti] || !e.found) return;  // never multiplied (flagged off in the range product)
+    const kgv_input& in = b.inputs[g];
+    uint32_t k[9];
+    input_key(k, in);
+    uint64_t d[4];
+    muhash_utxo_digest(d, k, in.prev_index, e.block_daa_score, e.amount, e.is_coinbase != 0, e.spk_version, e.script, e.script_len);
+    muhash_expand_store(e_den, n_inputs, g, d);
+    return;
+  }
+  g -= n_inputs;
+  if (g >= n_outputs) return;
+  const uint32_t ti = output_tx[g];
+  if (!accept[ti]) return;
+  const kgv_tx& tx = b.txs[ti];
+  const kgv_output& out = b.outputs[g];
+  uint32_t k[8];
+#pragma unroll
+  for (int w = 0; w < 4; w++) { k[2 * w] = (uint32_t)txids[4 * (size_t)ti + w]; k[2 * w + 1] = (uint32_t)(txids[4 * (size_t)ti + w] >> 32); }
+  uint64_t d[4];
+  muhash_utxo_digest(d, k, (uint32_t)(g - tx.first_output), tx_pov[ti], out.value, tx_first[ti] || tx_is_coinbase(tx), out.spk_version, b.bytes + out.script_off, out.script_len);
+  muhash_expand_store(e_num, n_outputs, g, d);
+}
+__global__ void k_replay_group_ranges(const ReplayRange* __restrict__ ranges, const uint32_t* __restrict__ group_first, uint32_t n_groups, uint32_t* __restrict__ ilo, uint32_t* __restrict__ ihi,
+                                      uint32_t* __restrict__ olo, uint32_t* __restrict__ ohi) {
+  uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_groups) return;
+  const uint32_t b0 = group_first[g], b1 = group_first[g + 1];
+  uint32_t i0 = 0, i1 = 0, o0 = 0, o1 = 0;
+  bool any = false;
+  for (uint32_t b = b0; b < b1; b++) {  // empty blocks carry no range
+    const ReplayRange r = ranges[b];
+    if (r.t1 == r.t0) continue;
+    if (!any) { i0 = r.i0; o0 = r.o0; any = true; }
+    i1 = r.i1; o1 = r.o1;
+  }
+  ilo[g] = i0; ihi[g] = any ? i1 : i0; olo[g] = o0; ohi[g] = any ? o1 : o0;
+}
+
+extern "C" int kgv_replay_muhash(kgv_ctx* ctx, const uint32_t* group_first_block, size_t n_groups, uint8_t* values768) {
+  if (!ctx) return KGV_ERR_ARG;
+  std::lock_guard<std::recursive_mutex> g(ctx->mu);
+  if (n_groups == 0) return KGV_OK;
+  if (!group_first_block || !values768) { ctx->err = "null argument"; return KGV_ERR_ARG; }
+  if (!ctx->last_replay.valid) { ctx->err = "kgv_replay_muhash must directly follow the kgv_replay_window call it refers to"; return KGV_ERR_ARG; }
+  const auto& L = ctx->last_replay;
+  if (group_first_block[0] != 0 || group_first_block[n_groups] != L.n_blocks) { ctx->err = "groups must tile the blocks of the window"; return KGV_ERR_ARG; }
+  for (size_t i = 0; i < n_groups; i++) if (group_first_block[i] > group_first_block[i + 1]) { ctx->err = "group offsets not monotone"; return KGV_ERR_ARG; }
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  uint8_t* R = ctx->d_replay;
+  const size_t nt = L.nt, ni = L.ni, no = L.no;
+  // scratch (d_work is free between validation calls)
+  size_t o_pov = 0, o_first = al256(nt * 8), o_gf = al256(o_first + nt), o_ilo = al256(o_gf + (n_groups + 1) * 4), o_ihi = al256(o_ilo + n_groups * 4), o_olo = al256(o_ihi + n_groups * 4),
+         o_ohi = al256(o_olo + n_groups * 4), o_val = al256(o_ohi + n_groups * 4);
+  int rc = kgv_reserve(ctx, &ctx->d_work, &ctx->d_work_cap, al256(o_val + n_groups * 768));
+  if (rc) return rc;
+  uint8_t* Wk = ctx->d_work;
+  uint32_t *e_den = nullptr, *e_num = nullptr;
+  rc = kgv_mu_reserve(ctx, ni, no, &e_den, &e_num);
+  if (rc) return rc;
+  const ReplayRange* ranges = (const ReplayRange*)(R + L.o_rng);
+  const uint32_t *itx = (const uint32_t*)(R + L.o_itx), *otx = (const uint32_t*)(R + L.o_otx), *txb = (const uint32_t*)(R + L.o_txb);
+  const uint8_t* acc = R + L.o_acc;
+  CK(cudaMemcpyAsync(Wk + o_gf, group_first_block, (n_groups + 1) * 4, cudaMemcpyHostToDevice, st));
+  k_replay_tx_pov<<<nblk(nt, 256), 256, 0, st>>>(ranges, txb, (uint32_t)nt, (uint64_t*)(Wk + o_pov), Wk + o_first);
+  CK(cudaGetLastError());
+  BatchView v{(const kgv_tx*)L.txs, (const kgv_input*)L.inputs, (const kgv_output*)L.outputs, (const DevEntry*)(R + L.o_ent), (const uint8_t*)L.bytes};
+  if (ni + no) {
+    k_muhash_replay_elements<<<nblk(ni + no, 128), 128, 0, st>>>(v, ni, no, itx, otx, acc, (const uint64_t*)(R + L.o_ids), (const uint64_t*)(Wk + o_pov), Wk + o_first, e_den, e_num);
+    CK(cudaGetLastError());
+  }
+  k_replay_group_ranges<<<nblk(n_groups, 128), 128, 0, st>>>(ranges, (const uint32_t*)(Wk + o_gf), (uint32_t)n_groups, (uint32_t*)(Wk + o_ilo), (uint32_t*)(Wk + o_ihi),
+                                                            (uint32_t*)(Wk + o_olo), (uint32_t*)(Wk + o_ohi));
+  CK(cudaGetLastError());
+  ctx->launches += 3;
+  uint32_t* vals = (uint32_t*)(Wk + o_val);
+  // an input of an accepted transaction is always found (the context rules saw it), so accept[itx[j]] alone selects the denominators
+  rc = kgv_mu_range_products(ctx, e_num, no, acc, otx, (const uint32_t*)(Wk + o_olo), (const uint32_t*)(Wk + o_ohi), (uint32_t)n_groups, vals, 192, st);
+  if (rc) return rc;
+  rc = kgv_mu_range_products(ctx, e_den, ni, acc, itx, (const uint32_t*)(Wk + o_ilo), (const uint32_t*)(Wk + o_ihi), (uint32_t)n_groups, vals + 96, 192, st);
+  if (rc) return rc;
+  rc = kgv_mu_canonicalize(ctx, vals, 96, 2 * n_groups, st);
+  if (rc) return rc;
+  const bool dev = kgv_ptr_is_device(values768);
+  CK(cudaMemcpyAsync(values768, vals, n_groups * 768, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+  if (!dev) CK(cudaStreamSynchronize(st));
   return KGV_OK;
 }

@@ -610,7 +610,11 @@ int kgv_scripts_phase(kgv_ctx* ctx, const BatchView& v, size_t nt, size_t ni, co
   size_t i_pks = 0, i_sigs = al256(i_pks + ns * 32), i_msgs = al256(i_sigs + ns * 64), i_refs = al256(i_msgs + ns * 32), i_sts = al256(i_refs + ns * sizeof(ItemRef));
   size_t i_pke = al256(i_sts + (nr > 1 ? nr * per_s : ns)), i_sige = al256(i_pke + ne * 33), i_msge = al256(i_sige + ne * 64), i_refe = al256(i_msge + ne * 32),
          i_ste = al256(i_refe + ne * sizeof(ItemRef));
-  size_t total2 = al256(i_ste + (nr > 1 ? nr * per_e : ne) + 64);
+  // signature cache (kgv_set_sigcache; not combined with sharding): digests, miss lists and miss counts of the two item kinds
+  kgv_sigcache* sc = nr == 1 ? ctx->sigcache : nullptr;
+  size_t i_digs = al256(i_ste + (nr > 1 ? nr * per_e : ne) + 64), i_idxs = al256(i_digs + (sc ? ns * 32 : 0)), i_dige = al256(i_idxs + (sc ? ns * 4 : 0)),
+         i_idxe = al256(i_dige + (sc ? ne * 32 : 0)), i_nm = al256(i_idxe + (sc ? ne * 4 : 0));
+  size_t total2 = al256(i_nm + 64);
   rc = kgv_reserve(ctx, &ctx->d_in, &ctx->d_in_cap, total2);
   if (rc) return rc;
   uint8_t* I = ctx->d_in;
@@ -629,8 +633,17 @@ int kgv_scripts_phase(kgv_ctx* ctx, const BatchView& v, size_t nt, size_t ni, co
       CK(cudaGetLastError());
       ctx->launches++;
       STAGE("msgs schnorr");
-      rc = kgv_launch_verify(ctx, I + i_pks + 32 * s_lo, I + i_msgs + 32 * s_lo, I + i_sigs + 64 * s_lo, s_hi - s_lo, I + i_sts + s_lo, false);
-      if (rc) return rc;
+      if (sc) {  // hits are answered from the table, only the misses are verified (and remembered)
+        rc = kgv_sigcache_lookup(ctx, sc, I + i_pks, I + i_msgs, I + i_sigs, ns, false, I + i_sts, I + i_digs, (uint32_t*)(I + i_idxs), (uint32_t*)(I + i_nm), st);
+        if (rc) return rc;
+        rc = kgv_launch_verify(ctx, I + i_pks, I + i_msgs, I + i_sigs, ns, I + i_sts, false, nullptr, false, (const uint32_t*)(I + i_idxs), (const uint32_t*)(I + i_nm));
+        if (rc) return rc;
+        rc = kgv_sigcache_insert(ctx, sc, I + i_sts, I + i_digs, (const uint32_t*)(I + i_idxs), (const uint32_t*)(I + i_nm), ns, st);
+        if (rc) return rc;
+      } else {
+        rc = kgv_launch_verify(ctx, I + i_pks + 32 * s_lo, I + i_msgs + 32 * s_lo, I + i_sigs + 64 * s_lo, s_hi - s_lo, I + i_sts + s_lo, false);
+        if (rc) return rc;
+      }
       STAGE("verify schnorr");
     }
   }
@@ -645,8 +658,17 @@ int kgv_scripts_phase(kgv_ctx* ctx, const BatchView& v, size_t nt, size_t ni, co
       CK(cudaGetLastError());
       ctx->launches++;
       STAGE("msgs ecdsa");
-      rc = kgv_launch_verify(ctx, I + i_pke + 33 * e_lo, I + i_msge + 32 * e_lo, I + i_sige + 64 * e_lo, e_hi - e_lo, I + i_ste + e_lo, true, se, true);
-      if (rc) return rc;
+      if (sc) {
+        rc = kgv_sigcache_lookup(ctx, sc, I + i_pke, I + i_msge, I + i_sige, ne, true, I + i_ste, I + i_dige, (uint32_t*)(I + i_idxe), (uint32_t*)(I + i_nm) + 1, se);
+        if (rc) return rc;
+        rc = kgv_launch_verify(ctx, I + i_pke, I + i_msge, I + i_sige, ne, I + i_ste, true, se, true, (const uint32_t*)(I + i_idxe), (const uint32_t*)(I + i_nm) + 1);
+        if (rc) return rc;
+        rc = kgv_sigcache_insert(ctx, sc, I + i_ste, I + i_dige, (const uint32_t*)(I + i_idxe), (const uint32_t*)(I + i_nm) + 1, ne, se);
+        if (rc) return rc;
+      } else {
+        rc = kgv_launch_verify(ctx, I + i_pke + 33 * e_lo, I + i_msge + 32 * e_lo, I + i_sige + 64 * e_lo, e_hi - e_lo, I + i_ste + e_lo, true, se, true);
+        if (rc) return rc;
+      }
     }
     if (fork) {
       CK(cudaEventRecord(ctx->ev_join, se));

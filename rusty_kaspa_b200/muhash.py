@@ -85,3 +85,27 @@ class MuHash:
         num = _buf()
         ctx._check(ctx._lib.kgv_utxo_muhash(ctx._h, utxo_set._h, num.ctypes.data))
         return cls(ctx, num.tobytes(), _ONE)
+
+
+# ---- batched forms (a replay window's worth of chain blocks at once) ----
+def finalize_batch(ctx, values768, want_serialized=False):
+    """values768: (n, 768) uint8 array of (numerator || denominator) records -> (n, 32) array of MuHash::finalize() hashes
+    [and the (n, 384) serialized values].  One modular inversion for the whole batch (kgv_muhash_finalize_batch)."""
+    v = np.ascontiguousarray(values768, dtype=np.uint8).reshape(-1, 768)
+    n = len(v)
+    h = np.zeros((n, 32), dtype=np.uint8)
+    ser = np.zeros((n, 384), dtype=np.uint8) if want_serialized else None
+    if n:
+        ctx._check(ctx._lib.kgv_muhash_finalize_batch(ctx._h, v.ctypes.data, v.ctypes.data + 384, n, 768, ser.ctypes.data if want_serialized else None, h.ctypes.data))
+    return (h, ser) if want_serialized else h
+
+
+def prefix_combine(ctx, values768, init=None):
+    """running MuHash::combine chain: record i becomes init * record 0 * ... * record i (kgv_muhash_prefix_combine). init: a MuHash or None."""
+    v = np.ascontiguousarray(values768, dtype=np.uint8).reshape(-1, 768).copy()
+    ib = None
+    if init is not None:
+        ib = np.frombuffer(init.numerator + init.denominator, dtype=np.uint8).copy()
+    if len(v):
+        ctx._check(ctx._lib.kgv_muhash_prefix_combine(ctx._h, ib.ctypes.data if ib is not None else None, v.ctypes.data, len(v)))
+    return v

@@ -97,6 +97,14 @@ class DagReplayer:
                            "in_order_ms": float(st.in_order_ms)}
         return (res, acc) if want_accept else res
 
+    def replay_muhash(self, group_first_block):
+        """kgv_replay_muhash for the window just replayed: (n_groups, 768) uint8 (numerator || denominator) of what each group of blocks accepted"""
+        gf = np.ascontiguousarray(group_first_block, dtype=np.uint32)
+        out = np.zeros((len(gf) - 1, 768), dtype=np.uint8)
+        if len(gf) > 1:
+            self.ctx._check(self.ctx._lib.kgv_replay_muhash(self.ctx._h, gf.ctypes.data, len(gf) - 1, out.ctypes.data))
+        return out
+
     def replay_windowed(self, blocks):
         """blocks: list of (txs, pov[, flags]) forming ONE window. Returns per-block RESULT arrays (same values as blockwise)."""
         blocks = list(blocks)

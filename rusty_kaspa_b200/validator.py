@@ -171,3 +171,36 @@ class TransactionValidator:
         cb = _c_batch(batch, with_entries=False)
         self.ctx._check(self._lib.kgv_validate_txs(self.ctx._h, utxo_set._h, ctypes.byref(cb), int(pov_daa_score), int(flags), ctypes.byref(self.params), res.ctypes.data))
         return res
+
+
+class SigCache:
+    """Device-resident verdict cache (kgv_sigcache): the counterpart of `Cache<SigCacheKey, bool>` (crypto/txscript/src/caches.rs:14-55).
+    attach(ctx) makes every validation call of that context consult and fill it."""
+
+    def __init__(self, ctx, capacity=10_000):
+        self.ctx = ctx
+        h = ctypes.c_void_p()
+        ctx._check(ctx._lib.kgv_sigcache_create(ctx._h, int(capacity), ctypes.byref(h)))
+        self._h = h
+
+    def attach(self, ctx=None):
+        c = ctx or self.ctx
+        c._check(c._lib.kgv_set_sigcache(c._h, self._h))
+
+    def detach(self, ctx=None):
+        c = ctx or self.ctx
+        c._check(c._lib.kgv_set_sigcache(c._h, None))
+
+    def clear(self):
+        self.ctx._check(self.ctx._lib.kgv_sigcache_clear(self.ctx._h, self._h))
+
+    def counters(self):
+        v = [ctypes.c_uint64() for _ in range(4)]
+        self.ctx._check(self.ctx._lib.kgv_sigcache_counters(self.ctx._h, self._h, *[ctypes.byref(x) for x in v]))
+        return dict(zip(("hits", "inserts", "lookups", "evictions"), (int(x.value) for x in v)))
+
+    def close(self):
+        if self._h:
+            self.detach()
+            self.ctx._lib.kgv_sigcache_destroy(self._h)
+            self._h = None

@@ -181,3 +181,39 @@ def test_replay_block_flags_follow_the_reference_semantics(gpu_ctx, oracle):
         assert r.us.count() == ost.count()
     assert r.us.digest() == ost.digest() and seen_flags >= {0, 1, 2, 3, 4, 5}
     r.close(); ost.close(); g.close()
+
+
+@pytest.mark.parametrize("fixture", ["simpa_goref_1060.json.gz", "simpa_goref_pruning_5000.json.gz"])
+def test_whole_virtual_chain_as_one_replay_window_reproduces_every_header_commitment(gpu_ctx, fixture):
+    """The reference's simpa DAG fixtures, their whole virtual chain as ONE kgv_replay_window call: per chain block the merged blocks in consensus
+    order with the chain block's daa score, the selected parent flagged ACCEPT_COINBASE | SKIP_SCRIPTS (utxo_validation.rs:116-140).  Then
+    kgv_replay_muhash (one multiset per chain block), kgv_muhash_prefix_combine (the running multiset hash) and kgv_muhash_finalize_batch
+    (ONE inversion for all chain blocks): EVERY header's utxoCommitment is reproduced (check_every = 1), and the final table's MuHash equals the tip's."""
+    from golden_util import simpa_dag_replay_plan
+    from rusty_kaspa_b200 import MuHash
+    from rusty_kaspa_b200.muhash import finalize_batch, prefix_combine
+    from rusty_kaspa_b200.replay import (DagReplayer, REPLAY_ACCEPT_COINBASE, REPLAY_SKIP_SCRIPTS, replay_blocks_array)
+    fx, by, order, sp, ordered_mergeset, chain = simpa_dag_replay_plan(fixture)
+    txs, ranges, group_first = [], [], [0]
+    for b in chain[1:]:
+        pov = by[b]["daa_score"]
+        for k, mb in enumerate(ordered_mergeset(b)):
+            t = by[mb]["txs"]
+            ranges.append((len(txs), len(t), pov, (REPLAY_ACCEPT_COINBASE | REPLAY_SKIP_SCRIPTS) if k == 0 else 0))
+            txs.extend(t)
+        group_first.append(len(ranges))
+    r = DagReplayer(gpu_ctx, Params(coinbase_maturity=fx["coinbase_maturity"], storage_mass_parameter=fx["storage_mass_parameter"]), 1 << 16)
+    res, acc = r.replay_window(build_batch(txs), replay_blocks_array(ranges), want_accept=True)
+    per_group = r.replay_muhash(group_first)
+    running = prefix_combine(gpu_ctx, per_group)
+    hashes = finalize_batch(gpu_ctx, running)
+    want = [by[b]["utxo_commitment"] for b in chain[1:]]
+    got = [h.tobytes().hex() for h in hashes]
+    bad = [i for i, (g, w) in enumerate(zip(got, want)) if g != w]
+    assert not bad, (len(bad), bad[:5])
+    assert MuHash.of_utxo_set(gpu_ctx, r.us).finalize().hex() == want[-1]
+    n_acc = int(acc.sum()) - (len(chain) - 1)
+    assert len(want) > 30 and n_acc > 150
+    if "5000" in fixture:
+        assert len(want) > 1500 and n_acc > 4500
+    r.close()

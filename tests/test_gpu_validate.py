@@ -225,3 +225,60 @@ def test_validate_mempool_transactions_in_parallel(gpu_ctx, oracle):
     assert ok.sum() > 40 and (got["fee"][ok] == 1).all()        # the generator pays a fee of 1 sompi per transaction
     assert us.count() == ost.count()                            # nothing was applied
     us.close(); ost.close()
+
+
+@pytest.mark.gpu
+def test_signature_cache_changes_speed_never_results(gpu_ctx, oracle):
+    """SigCache analogue (crypto/txscript/src/caches.rs:14-55, lib.rs:589-603): with a cache attached the verdicts of a mixed window (valid, wrong,
+    malformed signatures of all classes) are identical to the uncached ones; a second validation of the same window is answered entirely from the
+    table (hits == lookups of that call, no inserts); a changed signature misses; parse errors are never cached; a tiny cache evicts but stays
+    correct; the mempool -> block re-validation pattern hits."""
+    from rusty_kaspa_b200.validator import SigCache
+    from rusty_kaspa_b200 import simgen
+    fk, fe, txs = simgen.funded_window(600, n_keys=64, n_nonces=128, mix=(0.4, 0.2, 0.2, 0.2))
+    ents, k = [], 0
+    for t in txs:
+        ents.append(fe[k:k + len(t["inputs"])]); k += len(t["inputs"])
+    rng = np.random.default_rng(3)
+    for i in rng.choice(len(txs), size=90, replace=False):  # corrupt: bit flip in a signature, or an unliftable / foreign key encoding via the spk
+        ss = bytearray(txs[i]["inputs"][0]["sigscript"])
+        ss[5 + int(rng.integers(0, 50))] ^= 1 << int(rng.integers(0, 8))
+        txs[i]["inputs"][0]["sigscript"] = bytes(ss)
+    for i in rng.choice(len(txs), size=30, replace=False):
+        e = ents[i][0]
+        if len(e["script"]) == 34:  # P2PK: make the key an x with no curve point (parse error class)
+            ents[i][0] = dict(e, script=bytes([0x20]) + W._non_residue_x(rng).to_bytes(32, "big") + bytes([0xAC]))
+    b = build_batch(txs, ents)
+    tv = TransactionValidator(gpu_ctx, Params(storage_mass_parameter=simgen.DEFAULT_STORAGE_MASS_PARAMETER))
+    base = tv.validate_populated_transactions(b, 10, flags=2)
+    assert len(set(zip(base["status"].tolist(), base["script_err"].tolist()))) >= 4
+    sc = SigCache(gpu_ctx, 1 << 14)
+    sc.attach()
+    try:
+        r1 = tv.validate_populated_transactions(b, 10, flags=2)
+        c1 = sc.counters()
+        r2 = tv.validate_populated_transactions(b, 10, flags=2)
+        c2 = sc.counters()
+        for r in (r1, r2):
+            assert (r["status"] == base["status"]).all() and (r["script_err"] == base["script_err"]).all() and (r["fail_input"] == base["fail_input"]).all()
+        assert c1["hits"] < c1["lookups"] and c1["inserts"] > 1000
+        n_parse = c1["lookups"] - c1["hits"] - c1["inserts"]          # looked up, verified, not remembered: the parse-error verdicts (and duplicates)
+        assert c2["lookups"] == 2 * c1["lookups"] and c2["hits"] - c1["hits"] >= c1["inserts"] - 5 and c2["inserts"] - c1["inserts"] <= n_parse + 5
+        # a changed signature is a different key
+        t2 = [dict(t) for t in txs]
+        ss = bytearray(t2[0]["inputs"][0]["sigscript"]); ss[20] ^= 4
+        t2[0] = dict(t2[0], inputs=[dict(t2[0]["inputs"][0], sigscript=bytes(ss))] + t2[0]["inputs"][1:])
+        r3 = tv.validate_populated_transactions(build_batch(t2, ents), 10, flags=2)
+        assert r3["status"][0] != 0 and (r3["status"][1:] == base["status"][1:]).all()
+    finally:
+        sc.close()
+    small = SigCache(gpu_ctx, 64)
+    small.attach()
+    try:
+        for _ in range(3):
+            r = tv.validate_populated_transactions(b, 10, flags=2)
+            assert (r["status"] == base["status"]).all() and (r["script_err"] == base["script_err"]).all()
+        assert small.counters()["evictions"] > 100
+    finally:
+        small.close()
+    assert (tv.validate_populated_transactions(b, 10, flags=2)["status"] == base["status"]).all()  # detached again

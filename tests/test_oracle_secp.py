@@ -100,3 +100,55 @@ def test_bip340_test_vectors(oracle):
     got = oracle_schnorr_batch(oracle, pk, msg, sig, threads=2)
     assert got.tolist() == exp, [(i, c) for i, (g, e, c) in enumerate(zip(got, exp, comments)) if g != e]
     assert [pyref.schnorr_verify(pk[i].tobytes(), msg[i].tobytes(), sig[i].tobytes()) for i in range(15)] == exp
+
+
+def _batch(fn, pk, msg, sig, threads=4):
+    import numpy as np
+    st = np.zeros(len(pk), dtype=np.uint8)
+    vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    fn(vp(pk), vp(msg), vp(sig), ctypes.c_size_t(len(pk)), vp(st), threads)
+    return st
+
+
+def test_fast_cpu_port_equals_the_plain_checker(oracle):
+    """oracle/ok_secp_fast.c (GLV + wNAF + effective-affine tables: the port the CPU baselines time) must return the plain checker's verdicts
+    bit for bit: mixed Schnorr and ECDSA batches with every adversarial class, the BIP-340 vectors, the crafted ECDSA edge cases (r + n < p wrap,
+    low-S boundary, foreign key tags), and scalars that stress the GLV split (tiny, huge, near n/2, near lambda multiples)"""
+    import numpy as np
+    from golden_util import bip340_vectors
+    pk, msg, sig, kind = W.schnorr_triples(6000, seed=13, n_keys=512, n_nonces=512, frac_bitflip=0.15, frac_adversarial=0.15)
+    a, b = _batch(oracle.ok_schnorr_verify_batch, pk, msg, sig), _batch(oracle.ok_schnorr_verify_batch_fast, pk, msg, sig)
+    assert (a == b).all() and set(a) == {0, 1, 2}
+    pk, msg, sig, kind = W.ecdsa_triples(6000, seed=14, n_keys=512, n_nonces=512, frac_bitflip=0.15, frac_adversarial=0.2)
+    a, b = _batch(oracle.ok_ecdsa_verify_batch, pk, msg, sig), _batch(oracle.ok_ecdsa_verify_batch_fast, pk, msg, sig)
+    assert (a == b).all() and set(a) == {0, 1, 2, 3}
+    bpk, bmsg, bsig, exp, _ = bip340_vectors()
+    assert _batch(oracle.ok_schnorr_verify_batch_fast, bpk, bmsg, bsig).tolist() == exp
+    sys_path_tests = __import__("os").path.dirname(__import__("os").path.abspath(__file__))
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("t_gpu_ecdsa", __import__("os").path.join(sys_path_tests, "test_gpu_ecdsa.py"))
+    mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
+    cases = mod._crafted_ecdsa_edge_cases()
+    cpk = np.frombuffer(b"".join(c[0] for c in cases), dtype=np.uint8).reshape(-1, 33).copy()
+    cmsg = np.frombuffer(b"".join(c[1] for c in cases), dtype=np.uint8).reshape(-1, 32).copy()
+    csig = np.frombuffer(b"".join(c[2] for c in cases), dtype=np.uint8).reshape(-1, 64).copy()
+    assert _batch(oracle.ok_ecdsa_verify_batch_fast, cpk, cmsg, csig).tolist() == [c[3] for c in cases]
+    # ECDSA with hand-picked u2 = r/s values that stress the endomorphism split: Q = d*G, choose s so that u2 hits the target
+    N, G = pyref.N, pyref.G
+    lam = 0x5363AD4CC05C30E0A5261C028812645A122E22EA20816678DF02967C1B23BD72
+    rnd = random.Random(8)
+    rows = []
+    for target in [1, 2, N - 1, N - 2, (N - 1) // 2, (N + 1) // 2, lam, N - lam, (lam * 3) % N, 2**128, 2**128 - 1, 2**129 + 5, (lam + 1) % N, (lam * lam) % N]:
+        d, k = rnd.randrange(1, N), rnd.randrange(1, N)
+        r = pyref.pt_mul(k, G)[0] % N
+        s = r * pow(target, -1, N) % N           # u2 = r / s = target
+        m = (s * k - r * d) % N                  # makes the signature valid
+        if s > N // 2:                            # keep low S (negating s negates u1, u2: still exercises |u2| = target)
+            s, m = N - s, m                       # now invalid for this message; both ports must still agree
+        Q = pyref.pt_mul(d, G)
+        rows.append((bytes([2 + (Q[1] & 1)]) + Q[0].to_bytes(32, "big"), m.to_bytes(32, "big"), r.to_bytes(32, "big") + s.to_bytes(32, "big")))
+    gpk = np.frombuffer(b"".join(x[0] for x in rows), dtype=np.uint8).reshape(-1, 33).copy()
+    gmsg = np.frombuffer(b"".join(x[1] for x in rows), dtype=np.uint8).reshape(-1, 32).copy()
+    gsig = np.frombuffer(b"".join(x[2] for x in rows), dtype=np.uint8).reshape(-1, 64).copy()
+    a, b = _batch(oracle.ok_ecdsa_verify_batch, gpk, gmsg, gsig), _batch(oracle.ok_ecdsa_verify_batch_fast, gpk, gmsg, gsig)
+    assert (a == b).all() and 1 in a
