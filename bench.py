@@ -499,6 +499,80 @@ def measure_small_batches(ctx):
     return {"what": "median wall-clock ms of one kgv_validate_txs call, host arrays in, verdicts out", "ms_by_batch_size": out}
 
 
+def merge_clocks(per_rank):
+    """clocks of every rank -> one record: the LOWEST median SM clock, the union of throttle reasons"""
+    rows = [c for c in per_rank if c]
+    if not rows:
+        return None
+    sm = [c["sm_mhz"] for c in rows if c.get("sm_mhz")]
+    out = dict(rows[0])
+    out["sm_mhz"] = min(sm) if sm else None
+    out["sm_mhz_per_rank"] = [c.get("sm_mhz") for c in rows]
+    out["reasons"] = sorted(set(r for c in rows for r in (c.get("reasons") or [])))
+    out["ranks_sampled"] = len(rows)
+    return out
+
+
+def measure_dag_replay_sharded(ctx, dev, comm, rank, world, n_blocks, tpb, window):
+    """BASELINE configs[4]: the IBD-shaped replay with the signature batches sharded over the GPUs.  Every rank generates the SAME chain (same
+    seed) window by window (streaming: bounded memory; generation is outside the timed region), replays each window against its own replica
+    of the UTXO table with kgv_set_sharding on - each rank verifies 1/N of the candidate (signature, key) pairs, the verdict bytes are
+    exchanged through the communicator, scripts are resolved and the in-order pass runs identically everywhere.  Time = sum over windows of
+    the slowest rank's wall clock per window (a barrier before each window)."""
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    from rusty_kaspa_b200 import GpuUtxoSet, Params, simgen
+    from rusty_kaspa_b200.replay import REPLAY_BLOCK_DTYPE, ReplayStats
+    from rusty_kaspa_b200.validator import RESULT_DTYPE
+    from rusty_kaspa_b200.verifier import _KgvTxBatch
+    gen = simgen.FastDag(seed=0x6B61737061, n_keys=1024, n_nonces=4096, frac_two_inputs=0.5, frac_invalid=0.01, coinbase_outputs=16)
+    prm = Params(coinbase_maturity=gen.maturity, storage_mass_parameter=gen.C)
+    us = GpuUtxoSet(ctx, 1 << 25)
+    comm.shard_validation(True)
+    lib, h = ctx._lib, ctx._h
+    cudart = torch.cuda.cudart()
+    st = ReplayStats()
+    total_s = gen_s = 0.0
+    n_txs = n_sig = n_acc = done = 0
+    try:
+        while done < n_blocks:
+            k = min(window, n_blocks - done)
+            t0 = time.perf_counter()
+            gen.generate(k, tpb)
+            b, first, pov = gen.take()
+            gen_s += time.perf_counter() - t0
+            arr = np.zeros(k, dtype=REPLAY_BLOCK_DTYPE)
+            arr["first_tx"], arr["n_txs"], arr["pov_daa_score"], arr["flags"] = first[:-1], np.diff(first), pov, 1
+            res = np.zeros(len(b.txs), dtype=RESULT_DTYPE)
+            pinned = [a for a in (b.txs, b.inputs, b.outputs, b.arena, res) if a.nbytes and int(cudart.cudaHostRegister(a.ctypes.data, a.nbytes, 0)) == 0]
+            cb = _KgvTxBatch(b.txs.ctypes.data, len(b.txs), b.inputs.ctypes.data, len(b.inputs), b.outputs.ctypes.data, len(b.outputs), None, b.arena.ctypes.data, len(b.arena))
+            dist.barrier()
+            t0 = time.perf_counter()
+            ctx._check(lib.kgv_replay_window(h, us._h, C.byref(cb), arr.ctypes.data, k, C.byref(prm), res.ctypes.data, None, C.byref(st)))
+            dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            total_s += float(dt.item())
+            for a in pinned:
+                cudart.cudaHostUnregister(a.ctypes.data)
+            n_txs += len(b.txs) - k; n_sig += int(st.n_sig_checks); n_acc += int(st.n_accepted)
+            done += k
+        cnt = gen.counts()
+        assert n_acc == n_txs - cnt["n_invalid"] and us.count() == cnt["n_utxos"], (n_acc, n_txs, cnt)
+        dig = torch.frombuffer(bytearray(us.digest()), dtype=torch.uint8).to(dev)
+        alld = torch.zeros(32 * world, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(alld, dig)
+        assert all(torch.equal(alld[:32], alld[32 * r:32 * r + 32]) for r in range(world)), "table replicas diverged"
+    finally:
+        comm.shard_validation(False)
+        us.close(); gen.close()
+    return {"workload": f"config 5 shape: generated chain of {n_blocks} blocks (<= {tpb} txs/block, mixed 1-/2-input P2PK Schnorr, ~1% invalid) replayed in order on every rank "
+                        f"against its own 2^25-slot table replica, signature checks sharded over {world} GPUs (kgv_set_sharding), verdict bytes exchanged through the "
+                        f"library communicator, kgv_replay_window over {window} blocks per call from page-locked host arrays (uploads inside the timed region)",
+            "n_blocks": n_blocks, "n_txs": n_txs, "n_sig_checks": n_sig, "n_gpus": world, "txs_per_s": n_txs / total_s, "blocks_per_s": n_blocks / total_s,
+            "sig_checks_per_s": n_sig / total_s, "seconds": total_s, "generation_s": round(gen_s, 1), "replicas_identical": True}
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -519,19 +593,36 @@ def run_ours(args, rank, world, local_rank):
     ctx = rk.GpuContext(local_rank)  # raises if libkgv.so / device is missing
     stream = torch.cuda.Stream(device=dev)
     ctx.use_stream(stream.cuda_stream)
+    comm = None
     with torch.cuda.stream(stream):
+        if world > 1:
+            from rusty_kaspa_b200.comm import ShardComm
+            # torch.distributed is the bootstrap only (NCCL id / peer handles); the data path is libkgv's own exchange
+            comm = ShardComm.from_torch_distributed(ctx, slice_capacity=max(1 << 22, (n + 7) // 8 + 4096), nccl=args.collective == "nccl", peer=args.collective == "peer")
         dpk, dmsg, dsig = (torch.from_numpy(a).to(dev) for a in (pk, msg, sig))
         dst = torch.empty(n, dtype=torch.uint8, device=dev)
-        nbm = (n + 7) // 8
+        nbm = 4 * ((n + 31) // 32)
         dbm = torch.empty(nbm, dtype=torch.uint8, device=dev)
         gathered = torch.empty(nbm * world, dtype=torch.uint8, device=dev) if world > 1 else None
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
+        def exchange():
+            """every rank ends up with every shard's validity bitmap"""
+            if world == 1:
+                ctx.status_to_bitmap(dst, n=n, bitmap=dbm)
+            elif args.collective == "peer":   # the bitmap kernel writes straight into every peer over NVLink, consumers wait on local flags
+                e = comm.publish_bitmap(dst.data_ptr(), n)
+                comm.wait(e, nbm, gathered.data_ptr())
+            elif args.collective == "nccl":   # ncclAllGather called from the library
+                ctx.status_to_bitmap(dst, n=n, bitmap=dbm)
+                comm.allgather(dbm.data_ptr(), nbm, gathered.data_ptr())
+            else:                             # torch.distributed (round-1 form, kept for comparison)
+                ctx.status_to_bitmap(dst, n=n, bitmap=dbm)
+                dist.all_gather_into_tensor(gathered, dbm)
+
         def step():
             ctx.verify_schnorr_batch(dpk, dmsg, dsig, n=n, status=dst)
-            ctx.status_to_bitmap(dst, n=n, bitmap=dbm)
-            if world > 1:
-                dist.all_gather_into_tensor(gathered, dbm)
+            exchange()
 
         for _ in range(max(args.warmup, 3)):
             step()
@@ -540,8 +631,7 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
         sampler = ClockSampler(local_rank)
-        if rank == 0:
-            sampler.start()
+        sampler.start()
         launches0 = ctx.launch_count
         evs = []
         for _ in range(args.steps):
@@ -550,9 +640,7 @@ def run_ours(args, rank, world, local_rank):
             e0.record(stream)
             ctx.verify_schnorr_batch(dpk, dmsg, dsig, n=n, status=dst)
             ek.record(stream)
-            ctx.status_to_bitmap(dst, n=n, bitmap=dbm)
-            if world > 1:
-                dist.all_gather_into_tensor(gathered, dbm)
+            exchange()
             e1.record(stream)
             evs.append((e0, ek, e1))
         stream.synchronize()
@@ -560,7 +648,7 @@ def run_ours(args, rank, world, local_rank):
         if world > 1:
             dist.barrier()
         launches = ctx.launch_count - launches0
-        clocks = sampler.stop() if rank == 0 else None
+        clocks = sampler.stop()
         step_ms = [a.elapsed_time(c) for a, _, c in evs]
         kern_ms = [a.elapsed_time(b) for a, b, _ in evs]
         total_ms = float(sum(step_ms))
@@ -568,32 +656,64 @@ def run_ours(args, rank, world, local_rank):
         st = dst.cpu().numpy()
         assert int((st == 1).sum()) == expected_valid, "GPU verdicts disagree with the generator's ground truth"
         assert not (st[kind != 0] == 1).any()
+        mine = np.zeros(nbm, dtype=np.uint8)
+        pb = np.packbits((st == 1).astype(np.uint8), bitorder="little")
+        mine[:len(pb)] = pb
         if world > 1:
             bm_all = gathered.cpu().numpy()
-            assert (bm_all[rank * nbm:(rank + 1) * nbm] == np.packbits((st == 1).astype(np.uint8), bitorder="little")).all()
+            assert (bm_all[rank * nbm:(rank + 1) * nbm] == mine).all()
+            chk = torch.tensor([int(bm_all.astype(np.uint64).sum())], dtype=torch.int64, device=dev)
+            lo, hi = chk.clone(), chk.clone()
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+            assert int(lo.item()) == int(hi.item()), "ranks hold different gathered bitmaps"
 
-        # ---- end-to-end through the C ABI with HOST (pinned) buffers: H2D + kernel + D2H per step
+        # ---- end to end: HOST (pinned) buffers in, verdicts / gathered bitmap out, every step
         hpk, hmsg, hsig = (torch.from_numpy(a).pin_memory() for a in (pk, msg, sig))
         hst = torch.empty(n, dtype=torch.uint8).pin_memory()
+        hall = torch.empty(nbm * world, dtype=torch.uint8).pin_memory() if world > 1 else None
         e2e_steps = max(2, min(args.steps, 5))
+
+        def e2e_step():
+            if world == 1:  # kgv_schnorr_verify with host pointers: chunked H2D overlapped with the verification, D2H of the verdicts
+                ctx.verify_schnorr_batch(hpk.numpy(), hmsg.numpy(), hsig.numpy(), n=n, status=hst.numpy())
+            else:           # device-pointer form with the caller's copies, so that the exchange sits inside the step: H2D, verify, exchange, D2H of the gathered bitmap
+                dpk.copy_(hpk, non_blocking=True); dmsg.copy_(hmsg, non_blocking=True); dsig.copy_(hsig, non_blocking=True)
+                ctx.verify_schnorr_batch(dpk, dmsg, dsig, n=n, status=dst)
+                exchange()
+                hall.copy_(gathered, non_blocking=True)
+                stream.synchronize()
         for _ in range(2):
-            ctx.verify_schnorr_batch(hpk.numpy(), hmsg.numpy(), hsig.numpy(), n=n, status=hst.numpy())
+            e2e_step()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
-            ctx.verify_schnorr_batch(hpk.numpy(), hmsg.numpy(), hsig.numpy(), n=n, status=hst.numpy())
+            e2e_step()
         e2e_s = time.perf_counter() - t0
-        assert int((hst.numpy() == 1).sum()) == expected_valid
+        if world == 1:
+            assert int((hst.numpy() == 1).sum()) == expected_valid
+        else:
+            assert (hall.numpy()[rank * nbm:(rank + 1) * nbm] == mine).all()
+
+        # ---- config 5: the DAG replay with the signature checks sharded over the ranks (kgv_set_sharding), table replicas
+        rep5 = None
+        if world > 1 and args.replay_blocks_multi > 0:
+            rep5 = measure_dag_replay_sharded(ctx, dev, comm, rank, world, args.replay_blocks_multi, 150, args.replay_window)
 
     # max over ranks
+    cl_all = [clocks]
+    if world > 1:
+        cl_all = [None] * world
+        dist.all_gather_object(cl_all, clocks)
     if world > 1:
         t = torch.tensor([total_ms, e2e_s, float(sum(kern_ms))], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms, e2e_s, kern_total_ms = (float(x) for x in t.tolist())
     else:
         kern_total_ms = float(sum(kern_ms))
+    if comm is not None:
+        comm.close()
     if rank != 0:
         return
 
@@ -639,7 +759,9 @@ def run_ours(args, rank, world, local_rank):
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32 limbs (256-bit modular integer)", "data": "synthetic",
             "config": {"workload": "1Mi standalone BIP-340 Schnorr triples per GPU, batch-verify (BASELINE configs[1]); "
-                                   "98% valid / 1% bit-flips / 1% adversarial; bitmap pack" + (" + NCCL all-gather of shard bitmaps" if world > 1 else ""),
+                                   "98% valid / 1% bit-flips / 1% adversarial; bitmap pack" + (f" + exchange of the shard bitmaps ({args.collective})" if world > 1 else ""),
+                       "collective": None if world == 1 else {"peer": "kgv_shard_publish_bitmap / kgv_shard_wait: peer stores over NVLink + epoch flags (libkgv)",
+                                                              "nccl": "kgv_shard_allgather: ncclAllGather called from libkgv", "torch": "torch.distributed all_gather_into_tensor"}[args.collective],
                        "items_per_gpu_per_step": n, "input_bytes_per_gpu": 128 * n, "l2": "256 MiB flush write before every timed step; inputs 128 MiB > L2",
                        "parallelism": f"{world} independent shard(s), one process per GPU", "generation_s": round(gen_s, 1)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
@@ -647,8 +769,11 @@ def run_ours(args, rank, world, local_rank):
                          "note": "integer-issue bound by construction: 129 algorithmic bytes per verify vs 4.1e5 integer instructions; the binding roofline is integer_issue",
                          "integer_issue": integer_issue_roofline(n, kern_ms_avg, clocks)},
             "cpu_baseline": cpu,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 128 * n * world, "d2h_bytes_per_step": n * world,
-                    "steps": e2e_steps, "how": "kgv_schnorr_verify through the C ABI with pinned host buffers: H2D + kernel + D2H + sync inside the timed region (host clock)"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 128 * n * world, "d2h_bytes_per_step": (n if world == 1 else nbm * world) * world,
+                    "steps": e2e_steps,
+                    "how": ("kgv_schnorr_verify through the C ABI with pinned host buffers: H2D + kernel + D2H + sync inside the timed region (host clock)" if world == 1 else
+                            "per rank and step: H2D of the rank's triples from pinned memory, kgv_schnorr_verify (device pointers), the bitmap exchange, D2H of the gathered bitmap, sync "
+                            "(host clock, max over ranks)")},
             "dag_replay": rep, "tx_validation": txv, "tx_validation_ecdsa_multisig": txv4, "ecdsa": ecd, "small_batches": small, "utxo_table": utx, "gpu_launches": int(launches), "clocks": clocks}
     emit_json_line(line)
 
@@ -683,6 +808,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=N_DEFAULT, help="triples per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--collective", default="peer", choices=["peer", "nccl", "torch"], help="N > 1: how the shard bitmaps are exchanged")
+    ap.add_argument("--replay-blocks-multi", type=int, default=100000, help="N > 1: blocks of the sharded DAG-replay leg (BASELINE configs[4]: 100k blocks; 0 = skip)")
     ap.add_argument("--replay-blocks", type=int, default=10000, help="blocks of the DAG-replay leg (BASELINE configs[2]: 10k blocks; 0 = skip)")
     ap.add_argument("--replay-window", type=int, default=1024, help="blocks per kgv_replay_window call")
     ap.add_argument("--tx-window", type=int, default=32768, help="transactions in the secondary txs-validated/s measurement (0 = skip)")

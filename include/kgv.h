@@ -229,6 +229,19 @@ int kgv_utxo_apply_diff(kgv_ctx* ctx, kgv_utxo_table* t, const uint8_t* rem_keys
 int kgv_utxo_count(kgv_ctx* ctx, kgv_utxo_table* t, uint64_t* count);
 int kgv_utxo_digest(kgv_ctx* ctx, kgv_utxo_table* t, uint8_t out32[32]);
 
+/* Composed views (consensus/core/src/utxo/utxo_view.rs:22-35 ComposedUtxoView / UtxoViewComposition::compose; UtxoDiff utxo_diff.rs:15-19):
+ * a DIFF LAYER on the device.  The returned handle is a kgv_utxo_table that every call accepting a table accepts; it behaves as base ∘ diff:
+ *   lookups (kgv_utxo_lookup, the populate step of kgv_validate_txs / kgv_replay_window) probe the layer first - an entry it added is found, an
+ *   outpoint it removed is absent - and fall through to `base` otherwise (`base` may itself be a view: views nest like the reference's
+ *   utxo_set ∘ accumulated_diff ∘ mergeset_diff, processor.rs:437,527);
+ *   writes (kgv_utxo_apply_diff, kgv_utxo_apply_accepted, the in-order pass of kgv_replay_window) go to the layer only: removing an entry that
+ *   lives below records a removal marker, removing the layer's own addition cancels it, re-adding a removed outpoint keeps the lower entry hidden.
+ * `base` is never modified until kgv_utxo_view_commit folds the layer into it (write_diff_batch, utxo_set.rs:107-112); kgv_utxo_view_discard drops
+ * the layer's content (a candidate chain that lost).  Count / digest / MuHash are defined on plain tables only. */
+int kgv_utxo_view_create(kgv_ctx* ctx, kgv_utxo_table* base, uint64_t capacity_slots, kgv_utxo_table** out);
+int kgv_utxo_view_commit(kgv_ctx* ctx, kgv_utxo_table* view);
+int kgv_utxo_view_discard(kgv_ctx* ctx, kgv_utxo_table* view);
+
 /* validate_transactions_in_parallel (utxo_validation.rs:262-278) against the table: populate every input
  * by table lookup (:319-327), then as kgv_validate_populated.  batch->entries is ignored.
  * Unlike kgv_validate_populated this call never reports KGV_TX_NEEDS_HOST_VM: transactions with non-standard scripts are

@@ -145,6 +145,7 @@ struct ReplayArgs {
   kgv_tx_result* res;       // final verdicts
   uint8_t* accept;
   unsigned long long* stats; // [0] accepted transactions
+  unsigned long long* timers; // KGV_DEBUG only: cycles per phase (stage, scripts, A, B, C)
 };
 
 // L2 prefetch of the 128-byte lines covering [p, p + bytes), dealt to the threads from the TOP of the CTA downwards (the low
@@ -234,6 +235,9 @@ __global__ void __launch_bounds__(1024, 1) k_replay_inorder(ReplayArgs a) {
   prefetch_records(1);
   __syncthreads();
   prefetch_slots(0);
+  long long tk[6] = {0, 0, 0, 0, 0, 0}, c0 = 0;  // KGV_DEBUG: cycles per phase, as seen by thread 0
+#define RP_TICK(k) do { if (a.timers && tid == 0) { long long c1 = clock64(); tk[k] += c1 - c0; c0 = c1; } } while (0)
+  if (a.timers && tid == 0) c0 = clock64();
   for (uint32_t bi = 0; bi < a.n_blocks; bi++) {
     const ReplayRange bl = a.ranges[bi];
     prefetch_records(bi + 2);
@@ -261,6 +265,7 @@ __global__ void __launch_bounds__(1024, 1) k_replay_inorder(ReplayArgs a) {
       p_txs = S.txs - t0; p_in = S.inputs - i0; p_out = S.outputs - o0; p_ids = S.ids - 4 * (size_t)t0; p_pre = S.pre - t0;
       p_itx = S.itx - i0; p_otx = S.otx - o0; p_dent = S.dent - i0; p_slot = S.slot - i0; p_acc = S.acc - t0;
       __syncthreads();
+      RP_TICK(0);
       if (!(bl.flags & KGV_REPLAY_VERIFY_ONLY))  // scripts the inserts will store (consumed in phase C, two barriers from here)
         for (uint32_t o = o0 + rtid; o < o1; o += nth) {
           const kgv_output& out = p_out[o];
@@ -272,6 +277,7 @@ __global__ void __launch_bounds__(1024, 1) k_replay_inorder(ReplayArgs a) {
           }
         }
     }
+    RP_TICK(1);
     // ---- A: populate from the table as it stands after the previous block (utxo_validation.rs:319-327)
     for (uint32_t i = i0 + tid; i < i1; i += nth) {
       uint32_t k[9];
@@ -296,6 +302,7 @@ __global__ void __launch_bounds__(1024, 1) k_replay_inorder(ReplayArgs a) {
     }
     prefetch_slots(bi + 1);
     __syncthreads();
+    RP_TICK(2);
     // ---- B: context rules and the acceptance decision
     {
       const BatchView sb{p_txs, p_in, p_out, p_dent, a.b.bytes};
@@ -319,15 +326,22 @@ __global__ void __launch_bounds__(1024, 1) k_replay_inorder(ReplayArgs a) {
       }
     }
     __syncthreads();
+    RP_TICK(3);
     // ---- C: UtxoDiff::add_transaction straight into the table (utxo_diff.rs:233-247).  One CTA: the barrier orders these writes
     // before the next block's probes, no device-wide fence is needed inside the walk.
     if (!(bl.flags & KGV_REPLAY_VERIFY_ONLY)) {
       for (uint32_t i = i0 + tid; i < i1; i += nth) {
         if (!p_acc[p_itx[i]]) continue;
         UtxoSlot* s = p_slot[i];
-        *(volatile uint32_t*)&s->state = SLOT_TOMB;
-        atomicSub(&s_live, 1);
-        atomicAdd(&s_tomb, 1);
+        if (!a.t.below) {  // plain table: the slot becomes a tombstone
+          *(volatile uint32_t*)&s->state = SLOT_TOMB;
+          atomicSub(&s_live, 1);
+          atomicAdd(&s_tomb, 1);
+        } else {           // diff layer: cancel its own entry, or record a removal marker for an entry that lives below
+          uint32_t k[9];
+          input_key(k, p_in[i]);
+          table_erase_found<false>(a.t, k, s, s >= a.t.slots && s <= a.t.slots + a.t.mask, &s_live, &s_tomb);
+        }
       }
       for (uint32_t o = o0 + tid; o < o1; o += nth) {
         const uint32_t ti = p_otx[o];
@@ -343,9 +357,11 @@ __global__ void __launch_bounds__(1024, 1) k_replay_inorder(ReplayArgs a) {
       }
     }
     __syncthreads();
+    RP_TICK(4);
   }
   __threadfence();
   __syncthreads();
+  if (a.timers && tid == 0) for (int q = 0; q < 6; q++) a.timers[q] = (unsigned long long)tk[q];
   if (tid == 0) {
     a.stats[0] = s_acc;
     atomicAdd(&a.t.counters[0], (unsigned long long)(long long)s_live);
@@ -469,6 +485,7 @@ extern "C" int kgv_replay_window(kgv_ctx* ctx, kgv_utxo_table* table, const kgv_
   a.ranges = (const ReplayRange*)(R + o_rng); a.n_blocks = (uint32_t)n_blocks;
   a.prm = *prm;
   a.pre = pre; a.res = res; a.accept = dacc; a.stats = cnt;
+  a.timers = kgv_debug_on() ? cnt + 2 : nullptr;
   if (stats) CK(cudaEventRecord(ctx->ev_time[1], st));
   static bool smem_set = false;
   if (!smem_set) { CK(cudaFuncSetAttribute(k_replay_inorder, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ReplaySmem))); smem_set = true; }
@@ -476,6 +493,13 @@ extern "C" int kgv_replay_window(kgv_ctx* ctx, kgv_utxo_table* table, const kgv_
   CK(cudaGetLastError());
   ctx->launches++;
   if (stats) CK(cudaEventRecord(ctx->ev_time[2], st));
+  if (kgv_debug_on()) {
+    unsigned long long tk[6];
+    CK(cudaMemcpyAsync(tk, cnt + 2, sizeof tk, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    fprintf(stderr, "[kgv] in-order cycles per block: stage %.0f  scripts %.0f  A(populate+prefetch) %.0f  B(context) %.0f  C(apply) %.0f\n", (double)tk[0] / n_blocks,
+            (double)tk[1] / n_blocks, (double)tk[2] / n_blocks, (double)tk[3] / n_blocks, (double)tk[4] / n_blocks);
+  }
   STAGE("replay in-order");
   const bool dev_out = kgv_ptr_is_device(results);
   CK(cudaMemcpyAsync(results, res, nt * sizeof(kgv_tx_result), dev_out ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));

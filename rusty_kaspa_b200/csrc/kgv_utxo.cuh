@@ -17,6 +17,10 @@
 #define SLOT_FULL 1u
 #define SLOT_TOMB 2u
 #define SLOT_BUSY 3u
+// states that exist only in DIFF LAYERS (views, see below): a removal marker (the key is absent in this view whatever the layers below hold) and
+// an added entry that additionally hides an older entry of the same key in a lower layer (UtxoDiff: the outpoint is in `remove` AND in `add`)
+#define SLOT_REMOVED 4u
+#define SLOT_FULLH 5u
 #define INLINE_SCRIPT 68u
 #define SLOT_SCRIPT_BYTE 60u  // byte offset of the inline script inside the slot (word 15)
 
@@ -36,6 +40,10 @@ struct kgv_utxo_table {
   uint8_t* overflow = nullptr;   // long scripts (append-only: offsets stay valid for the life of the table)
   uint64_t overflow_cap = 0;
   unsigned long long* counters = nullptr;  // [0] live entries, [1] tombstones, [2] overflow bytes used, [3] insert failures, [8..15] digest scratch
+  // Composed views (consensus/core/src/utxo/utxo_view.rs:22-35: ComposedUtxoView = base view + UtxoDiff, nesting arbitrarily): a table with
+  // base != nullptr is a DIFF LAYER over `base`; lookups probe it first and fall through, writes go to it and never touch what lies below.
+  kgv_utxo_table* base = nullptr;
+  struct TableView* d_view = nullptr;  // this table's TableView in device memory (what an upper layer's `below` points to)
 };
 
 struct TableView {
@@ -44,8 +52,9 @@ struct TableView {
   uint8_t* overflow;
   uint64_t overflow_cap;
   unsigned long long* counters;
+  const TableView* below;  // next lower layer of a composed view, nullptr for a plain table
 };
-static inline TableView view_of(const kgv_utxo_table* t) { return TableView{t->slots, t->mask, t->overflow, t->overflow_cap, t->counters}; }
+static inline TableView view_of(const kgv_utxo_table* t) { return TableView{t->slots, t->mask, t->overflow, t->overflow_cap, t->counters, t->base ? t->base->d_view : nullptr}; }
 
 namespace kgv {
 
@@ -109,19 +118,38 @@ __device__ __forceinline__ void slot_load_head(SlotHead& h, const UtxoSlot* s) {
   ld256_cg(h.w, s);
   ld256_cg(h.w + 8, (const uint8_t*)s + 32);
 }
-// returns the slot holding key k (its first 64 bytes in `head`), or nullptr.  The table must not be modified concurrently
-// by an operation on the SAME key.
-__device__ __forceinline__ UtxoSlot* table_find(const TableView& t, const uint32_t* k, SlotHead& head) {
+// one layer: the slot holding key k in state FULL / FULLH / REMOVED (its first 64 bytes in `head`), or nullptr.  The table must not be
+// modified concurrently by an operation on the SAME key.
+__device__ __forceinline__ UtxoSlot* layer_find(const TableView& t, const uint32_t* k, SlotHead& head) {
   uint64_t i = key_hash(k) & t.mask;
   for (uint64_t probes = 0; probes <= t.mask; probes++) {
     UtxoSlot* s = &t.slots[i];
     slot_load_head(head, s);
     const uint32_t st = head.state();
     if (st == SLOT_EMPTY) return nullptr;
-    if (st == SLOT_FULL && head.key_is(k)) return s;
+    if ((st == SLOT_FULL || st >= SLOT_REMOVED) && head.key_is(k)) return s;
     i = (i + 1) & t.mask;
   }
   return nullptr;
+}
+// UtxoView::get on the composed view: the first layer from the top that knows the key decides (added entry -> found, removal marker -> absent),
+// utxo_view.rs:22-35.  *in_top (optional) tells whether the returned slot belongs to the top layer.
+__device__ __forceinline__ UtxoSlot* table_find(const TableView& t, const uint32_t* k, SlotHead& head, bool* in_top = nullptr) {
+  UtxoSlot* s = layer_find(t, k, head);
+  if (in_top) *in_top = true;
+  if (s) return head.state() == SLOT_REMOVED ? nullptr : s;
+  if (in_top) *in_top = false;
+  for (const TableView* L = t.below; L; L = L->below) {
+    s = layer_find(*L, k, head);
+    if (s) return head.state() == SLOT_REMOVED ? nullptr : s;
+  }
+  return nullptr;
+}
+// the layer of a composed view a slot belongs to (its overflow arena holds the slot's long script)
+__device__ __forceinline__ const TableView* layer_of(const TableView& t, const UtxoSlot* s) {
+  for (const TableView* L = &t; L; L = L->below)
+    if (s >= L->slots && s <= L->slots + L->mask) return L;
+  return &t;
 }
 __device__ __forceinline__ void head_to_entry(DevEntry& e, const TableView& t, const UtxoSlot* s, const SlotHead& h) {
   e.amount = h.amount();
@@ -134,7 +162,7 @@ __device__ __forceinline__ void head_to_entry(DevEntry& e, const TableView& t, c
   else {
     uint64_t off;
     memcpy(&off, s->script, 8);
-    e.script = t.overflow + off;
+    e.script = (t.below ? layer_of(t, s)->overflow : t.overflow) + off;
   }
   e.found = 1;
 }
@@ -166,10 +194,21 @@ __device__ __forceinline__ void load_script_words(uint32_t* w, const uint8_t* p,
 // Keys inserted concurrently by one kernel must be distinct (API contract), so a slot another thread is
 // filling (BUSY) always belongs to a different key and is simply skipped: no thread ever waits on another.
 // FENCE = false: the caller is a single CTA whose barriers order the slot contents before the state word for every reader.
+// In a diff layer (t.below != nullptr) the write goes to the top layer only: an added entry becomes FULLH when a lower layer (or a removal
+// marker of this layer) holds the key, and `marker` = true stores a removal marker instead of an entry (UtxoDiff::remove_entry of an entry
+// that lives below, utxo_diff.rs:249-258).
 template <bool FENCE = true>
 __device__ __forceinline__ uint32_t table_put(const TableView& t, const uint32_t* k, uint64_t amount, uint64_t daa, uint32_t spk_version, uint32_t is_coinbase,
-                                              const uint8_t* script, uint32_t script_len, int* s_live = nullptr, int* s_tomb = nullptr) {
+                                              const uint8_t* script, uint32_t script_len, int* s_live = nullptr, int* s_tomb = nullptr, bool marker = false) {
   // s_live / s_tomb: optional shared-memory accumulators for the live / tombstone counters (a single-CTA caller flushes them once)
+  uint32_t final_state = marker ? SLOT_REMOVED : SLOT_FULL;
+  if (t.below && !marker) {
+    SlotHead hb;
+    for (const TableView* L = t.below; L; L = L->below) {
+      UtxoSlot* sb = layer_find(*L, k, hb);
+      if (sb) { if (hb.state() != SLOT_REMOVED) final_state = SLOT_FULLH; break; }
+    }
+  }
   uint64_t i = key_hash(k) & t.mask;
   UtxoSlot* target = nullptr;
   UtxoSlot* tomb = nullptr;
@@ -179,8 +218,13 @@ __device__ __forceinline__ uint32_t table_put(const TableView& t, const uint32_t
     UtxoSlot* s = &t.slots[i];
     slot_load_head(h, s);
     const uint32_t st = h.state();
-    if (st == SLOT_FULL) {
-      if (h.key_is(k)) { target = s; replace = true; break; }
+    if (st == SLOT_FULL || st >= SLOT_REMOVED) {
+      if (h.key_is(k)) {
+        target = s; replace = true;
+        if (st == SLOT_REMOVED && !marker) final_state = SLOT_FULLH;  // re-adding what this layer removed: the lower entry stays hidden
+        if (st == SLOT_FULLH && !marker) final_state = SLOT_FULLH;
+        break;
+      }
       continue;
     }
     if (st == SLOT_TOMB) { if (!tomb) tomb = s; continue; }
@@ -203,7 +247,7 @@ __device__ __forceinline__ uint32_t table_put(const TableView& t, const uint32_t
   }
   if (!target) { atomicAdd(&t.counters[3], 1ull); return 0; }
   uint32_t w[32];
-  w[0] = replace ? SLOT_FULL : SLOT_BUSY;
+  w[0] = replace ? final_state : SLOT_BUSY;
 #pragma unroll
   for (int j = 0; j < 9; j++) w[1 + j] = k[j];
   w[10] = (uint32_t)amount; w[11] = (uint32_t)(amount >> 32);
@@ -230,18 +274,31 @@ __device__ __forceinline__ uint32_t table_put(const TableView& t, const uint32_t
   st256(target, w);
   if (!replace) {
     if (FENCE) __threadfence();
-    *(volatile uint32_t*)&target->state = SLOT_FULL;
+    *(volatile uint32_t*)&target->state = final_state;
     if (s_live) atomicAdd(s_live, 1); else atomicAdd(&t.counters[0], 1ull);
   }
   return replace ? 2u : 1u;
 }
+// erase of an entry already located (slot s, found in the top layer or below): a plain table tombstones the slot; a diff layer turns its own
+// added entry back into nothing (FULL) or into a removal marker (FULLH), and records a removal marker for an entry that lives below.
+template <bool FENCE = true>
+__device__ __forceinline__ void table_erase_found(const TableView& t, const uint32_t* k, UtxoSlot* s, bool in_top, int* s_live = nullptr, int* s_tomb = nullptr) {
+  if (!in_top) {
+    table_put<FENCE>(t, k, 0, 0, 0, 0, nullptr, 0, s_live, s_tomb, true);
+    return;
+  }
+  const uint32_t st = *(volatile uint32_t*)&s->state;
+  if (st == SLOT_FULLH) { *(volatile uint32_t*)&s->state = SLOT_REMOVED; return; }  // still one entry of this layer (now a marker)
+  *(volatile uint32_t*)&s->state = SLOT_TOMB;
+  if (s_live) { atomicSub(s_live, 1); atomicAdd(s_tomb, 1); }
+  else { atomicAdd(&t.counters[0], (unsigned long long)-1); atomicAdd(&t.counters[1], 1ull); }
+}
 __device__ __forceinline__ uint32_t table_erase(const TableView& t, const uint32_t* k) {
   SlotHead h;
-  UtxoSlot* s = table_find(t, k, h);
+  bool in_top;
+  UtxoSlot* s = table_find(t, k, h, &in_top);
   if (!s) return 0;
-  *(volatile uint32_t*)&s->state = SLOT_TOMB;
-  atomicAdd(&t.counters[0], (unsigned long long)-1);
-  atomicAdd(&t.counters[1], 1ull);
+  table_erase_found(t, k, s, in_top);
   return 1;
 }
 

@@ -439,14 +439,86 @@ extern "C" int kgv_utxo_create(kgv_ctx* ctx, uint64_t capacity_slots, kgv_utxo_t
   }
   CK(cudaMemsetAsync(t->slots, 0, cap * sizeof(UtxoSlot), ctx->stream));
   CK(cudaMemsetAsync(t->counters, 0, 16 * sizeof(unsigned long long), ctx->stream));
+  CK(cudaMalloc((void**)&t->d_view, sizeof(TableView)));
+  TableView hv = view_of(t);
+  CK(cudaMemcpyAsync(t->d_view, &hv, sizeof hv, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   *out = t;
   return KGV_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// composed views: a diff layer on the device (utxo_view.rs:22-35, utxo_diff.rs:15-19)
+// ---------------------------------------------------------------------------------------------
+extern "C" int kgv_utxo_view_create(kgv_ctx* ctx, kgv_utxo_table* base, uint64_t capacity_slots, kgv_utxo_table** out) {
+  if (!ctx || !base || !out) return KGV_ERR_ARG;
+  int rc = kgv_utxo_create(ctx, capacity_slots, out);
+  if (rc) return rc;
+  std::lock_guard<std::recursive_mutex> g(ctx->mu);
+  (*out)->base = base;
+  TableView hv = view_of(*out);  // now with `below`
+  CK(cudaMemcpyAsync((*out)->d_view, &hv, sizeof hv, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return KGV_OK;
+}
+// write_diff_batch (utxo_set.rs:107-112): delete what the layer removed, put what it added - applied to the layer below through that layer's own
+// view semantics (so a stack of diffs folds downwards one level at a time)
+__global__ void k_view_commit_removes(TableView top, TableView below) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > top.mask) return;
+  const UtxoSlot* s = &top.slots[i];
+  const uint32_t st = s->state;
+  if (st != SLOT_REMOVED && st != SLOT_FULLH) return;
+  uint32_t k[9];
+#pragma unroll
+  for (int w = 0; w < 9; w++) k[w] = s->key[w];
+  table_erase(below, k);
+}
+__global__ void k_view_commit_adds(TableView top, TableView below) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > top.mask) return;
+  const UtxoSlot* s = &top.slots[i];
+  const uint32_t st = s->state;
+  if (st != SLOT_FULL && st != SLOT_FULLH) return;
+  SlotHead h;
+  slot_load_head(h, s);
+  DevEntry e;
+  TableView solo = top;
+  solo.below = nullptr;
+  head_to_entry(e, solo, s, h);
+  uint32_t k[9];
+#pragma unroll
+  for (int w = 0; w < 9; w++) k[w] = s->key[w];
+  table_put(below, k, e.amount, e.block_daa_score, e.spk_version, e.is_coinbase, e.script, e.script_len);
+}
+static int view_clear(kgv_ctx* ctx, kgv_utxo_table* v) {
+  CK(cudaMemsetAsync(v->slots, 0, (v->mask + 1) * sizeof(UtxoSlot), ctx->stream));
+  CK(cudaMemsetAsync(v->counters, 0, 16 * sizeof(unsigned long long), ctx->stream));
+  return KGV_OK;
+}
+extern "C" int kgv_utxo_view_commit(kgv_ctx* ctx, kgv_utxo_table* view) {
+  if (!ctx || !view || !view->base) return KGV_ERR_ARG;
+  std::lock_guard<std::recursive_mutex> g(ctx->mu);
+  CK(cudaSetDevice(ctx->device));
+  TableView top = view_of(view), below = view_of(view->base);
+  k_view_commit_removes<<<nblk(view->mask + 1, 128), 128, 0, ctx->stream>>>(top, below);
+  CK(cudaGetLastError());
+  k_view_commit_adds<<<nblk(view->mask + 1, 128), 128, 0, ctx->stream>>>(top, below);
+  CK(cudaGetLastError());
+  ctx->launches += 2;
+  return view_clear(ctx, view);
+}
+extern "C" int kgv_utxo_view_discard(kgv_ctx* ctx, kgv_utxo_table* view) {
+  if (!ctx || !view || !view->base) return KGV_ERR_ARG;
+  std::lock_guard<std::recursive_mutex> g(ctx->mu);
+  CK(cudaSetDevice(ctx->device));
+  return view_clear(ctx, view);
 }
 extern "C" void kgv_utxo_destroy(kgv_ctx* ctx, kgv_utxo_table* t) {
   if (!t) return;
   if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
   cudaFree(t->slots); cudaFree(t->overflow); cudaFree(t->counters);
+  if (t->d_view) cudaFree(t->d_view);
   delete t;
 }
 
@@ -531,6 +603,7 @@ extern "C" int kgv_utxo_apply_diff(kgv_ctx* ctx, kgv_utxo_table* t, const uint8_
 extern "C" int kgv_utxo_count(kgv_ctx* ctx, kgv_utxo_table* t, uint64_t* count) {
   if (!ctx || !t || !count) return KGV_ERR_ARG;
   std::lock_guard<std::recursive_mutex> g(ctx->mu);
+  if (t->base) { ctx->err = "count / digest / MuHash are defined on plain tables: commit the view first"; return KGV_ERR_ARG; }
   CK(cudaSetDevice(ctx->device));
   unsigned long long c[4];
   CK(cudaMemcpyAsync(c, t->counters, sizeof c, cudaMemcpyDeviceToHost, ctx->stream));
@@ -543,6 +616,7 @@ extern "C" int kgv_utxo_count(kgv_ctx* ctx, kgv_utxo_table* t, uint64_t* count) 
 extern "C" int kgv_utxo_digest(kgv_ctx* ctx, kgv_utxo_table* t, uint8_t out32[32]) {
   if (!ctx || !t || !out32) return KGV_ERR_ARG;
   std::lock_guard<std::recursive_mutex> g(ctx->mu);
+  if (t->base) { ctx->err = "count / digest / MuHash are defined on plain tables: commit the view first"; return KGV_ERR_ARG; }
   CK(cudaSetDevice(ctx->device));
   unsigned long long* acc = t->counters + 8;
   CK(cudaMemsetAsync(acc, 0, 8 * sizeof(unsigned long long), ctx->stream));
@@ -976,6 +1050,7 @@ extern "C" int kgv_utxo_muhash(kgv_ctx* ctx, kgv_utxo_table* t, uint8_t* numerat
   if (!ctx || !t) return KGV_ERR_ARG;
   std::lock_guard<std::recursive_mutex> g(ctx->mu);
   if (!numerator384) { ctx->err = "null argument"; return KGV_ERR_ARG; }
+  if (t->base) { ctx->err = "count / digest / MuHash are defined on plain tables: commit the view first"; return KGV_ERR_ARG; }
   CK(cudaSetDevice(ctx->device));
   const uint64_t slots = t->mask + 1;
   const size_t chunk = slots < ((uint64_t)1 << 17) ? (size_t)slots : ((size_t)1 << 17);

@@ -79,6 +79,23 @@ class GpuUtxoSet:
             self._lib.kgv_utxo_destroy(self.ctx._h, self._h)
             self._h = None
 
+    # ---- composed views (utxo_view.rs:22-35): a diff layer over this set
+    def compose(self, capacity_slots=1 << 16):
+        """UtxoViewComposition::compose: a GpuUtxoSet that behaves as self ∘ (an initially empty diff); writes through it never touch self"""
+        v = GpuUtxoSet.__new__(GpuUtxoSet)
+        v.ctx, v._lib = self.ctx, self._lib
+        h = ctypes.c_void_p()
+        self.ctx._check(self._lib.kgv_utxo_view_create(self.ctx._h, self._h, int(capacity_slots), ctypes.byref(h)))
+        v._h, v.base = h, self
+        return v
+
+    def commit(self):
+        """fold this diff layer into the set below it (write_diff_batch) and empty it"""
+        self.ctx._check(self._lib.kgv_utxo_view_commit(self.ctx._h, self._h))
+
+    def discard(self):
+        self.ctx._check(self._lib.kgv_utxo_view_discard(self.ctx._h, self._h))
+
     def get(self, keys36, script_stride=128):
         """keys36: (n, 36) uint8. Returns (found (n,), entries (n,) ENTRY_DTYPE, scripts (n, stride))."""
         keys36 = np.ascontiguousarray(keys36, dtype=np.uint8).reshape(-1, 36)

@@ -91,6 +91,9 @@ class State:
     def accept(self, b, accept, pov):
         ob = ok_batch(b)
         a = np.ascontiguousarray(accept, dtype=np.uint8)
+        if not hasattr(self, "_log"):
+            self._log = []
+        self._log.append((b, a.copy(), pov))  # lets a test rebuild an equal state (the C oracle has no clone)
         return self.lib.ok_state_accept(self.h, ctypes.byref(ob), a.ctypes.data_as(ctypes.c_void_p), ctypes.c_uint64(pov))
 
     def commit(self):

@@ -161,4 +161,4 @@ def test_body_validation_example_block_of_the_reference_on_the_gpu(gpu_ctx):
     assert gpu_ctx.block_hash_merkle_roots(b, first)[0].tobytes().hex() == root
     got = gpu_ctx.block_set_checks(b, first)
     assert got["status"].tolist() == [w for _, _, w in blocks]
-    assert int(got[1]["index"]) == 5 and int(got[3]["index"]) > 0  # the pushed clone is transaction 5 of its block
+    assert int(got[1]["index"]) == first[1] + 5 and int(got[3]["index"]) > 0  # the pushed clone is transaction 5 of its block (absolute index)

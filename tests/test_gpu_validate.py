@@ -282,3 +282,74 @@ def test_signature_cache_changes_speed_never_results(gpu_ctx, oracle):
     finally:
         small.close()
     assert (tv.validate_populated_transactions(b, 10, flags=2)["status"] == base["status"]).all()  # detached again
+
+
+@pytest.mark.gpu
+def test_composed_views_leave_the_base_untouched_and_commit_like_write_diff_batch(gpu_ctx, oracle):
+    """ComposedUtxoView on the device (utxo_view.rs:22-35): a diff layer over the GPU table.  Blocks validated and applied THROUGH a view see
+    base ∘ diff (spent entries absent, created entries present, chained across blocks), the base stays bit-identical (digest), a nested view stacks a
+    second diff, discard = the candidate chain lost (reorg: the other branch is then validated against the unchanged base), commit = write_diff_batch:
+    base then equals the oracle state that applied the same blocks directly."""
+    dag = SimDag(seed=41, n_keys=64, n_nonces=128, mix=(0.6, 0.2, 0.1, 0.1), frac_invalid=0.1, coinbase_maturity=2, coinbase_outputs=8)
+    op = oracle_tx.params(coinbase_maturity=2, storage_mass_parameter=dag.C)
+    tv = TransactionValidator(gpu_ctx, Params(coinbase_maturity=2, storage_mass_parameter=dag.C))
+    base = GpuUtxoSet(gpu_ctx, 1 << 14)
+    ost = oracle_tx.State(oracle)
+
+    def step(us, o, txs, pov):
+        b = build_batch(txs)
+        exp = o.validate(b, pov, 0, op, threads=2)
+        got = tv.validate_transactions_in_parallel(us, b, pov)
+        _same_results(got, exp)
+        acc = np.array([1 if (i == 0 or got[i]["status"] == 0) else 0 for i in range(len(txs))], dtype=np.uint8)
+        assert o.accept(b, acc, pov) == 0
+        us.add_transactions(b, acc, pov)
+        return b, acc
+
+    for _ in range(8):                                   # history, applied to the base directly
+        step(base, ost, *dag.make_block(16)); ost.commit()
+    d0, n0 = base.digest(), base.count()
+    blocks = [dag.make_block(16) for _ in range(6)]
+    # ---- branch X = blocks[0:4] through a view, with a nested view for the last two
+    view = base.compose(1 << 12)
+    ox = oracle_tx.State(oracle); _copy_state(ost, ox, base, oracle)
+    spent_keys = []
+    for txs, pov in blocks[:2]:
+        b, acc = step(view, ox, txs, pov)
+        spent_keys += [bytes(b.inputs["prev_txid"][i]) + int(b.inputs["prev_index"][i]).to_bytes(4, "little") for t in np.nonzero(acc)[0] for i in
+                       range(int(b.txs["first_input"][t]), int(b.txs["first_input"][t] + b.txs["n_inputs"][t]))]
+    assert base.digest() == d0 and base.count() == n0     # the base never moved
+    k = np.frombuffer(b"".join(spent_keys), dtype=np.uint8).reshape(-1, 36)
+    in_base = base.get(k)[0]
+    assert in_base.sum() > 10 and not view.get(k)[0][in_base == 1].any()   # spent through the view: still in the base, absent in the view
+    upper = view.compose(1 << 12)
+    for txs, pov in blocks[2:4]:
+        step(upper, ox, txs, pov)
+    assert base.digest() == d0
+    # ---- reorg: branch X loses; branch Y = an alternative block validated against the untouched base through a fresh layer
+    upper.discard(); view.discard()
+    assert view.get(k)[0].tolist() == in_base.tolist()
+    oy = oracle_tx.State(oracle); _copy_state(ost, oy, base, oracle)
+    dag2 = SimDag(seed=41, n_keys=64, n_nonces=128, mix=(0.6, 0.2, 0.1, 0.1), frac_invalid=0.1, coinbase_maturity=2, coinbase_outputs=8)
+    for _ in range(8):
+        dag2.make_block(16)                                # same history (same seed), then a DIFFERENT continuation
+    dag2.rng = np.random.default_rng(999)
+    for _ in range(3):
+        step(view, oy, *dag2.make_block(16))
+    # ---- commit = write_diff_batch: the base becomes what the oracle holds after applying branch Y directly
+    view.commit()
+    oy.commit()
+    assert base.count() == oy.count() and base.digest() == oy.digest() and base.digest() != d0
+    upper.close(); view.close(); base.close()
+    for o in (ost, ox, oy):
+        o.close()
+
+
+def _copy_state(src, dst, base_us, oracle):
+    """dst := the UTXO set of src (test helper: re-inserts every entry the GPU base table holds, read back through the oracle's getter)"""
+    # the oracle has no clone; replaying is cheap: export through the composed getter of src via the GPU table's own content is not possible without
+    # keys, so the helper keeps a side list on the State object
+    for b, acc, pov in getattr(src, "_log", []):
+        assert dst.accept(b, acc, pov) == 0
+        dst.commit()
+    dst._log = list(getattr(src, "_log", []))
