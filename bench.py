@@ -434,12 +434,14 @@ def measure_ecdsa(ctx, dev, stream, n, steps):
 
 def measure_utxo_table(ctx, dev, stream, peak_gbs):
     """K5: the GPU UTXO table on its own: 4 Mi entries in a 16 Mi-slot (2 GiB) table; every timed call looks up a DIFFERENT random
-    1 Mi of them (occupied slots = 512 MiB, four times L2), keys and results device-resident.
-    Algorithmic bytes per lookup: 36 B key + one 128 B slot read + 32 B entry + 1 B flag written."""
+    permutation of all 4 Mi entries (occupied slots = 512 MiB, four times L2), keys and results device-resident; then erase / re-insert of 1 Mi
+    entries per call (kgv_utxo_apply_diff, device arrays).  Algorithmic bytes per lookup: 36 B key + one 128 B slot = 164 B
+    (+ 33 B of results written).  The probe itself reads only the first 64 bytes of a slot (two LDG.256), so DRAM moves LESS than that."""
     import torch
     from rusty_kaspa_b200 import GpuUtxoSet
     from rusty_kaspa_b200.txbatch import ENTRY_DTYPE
-    n_ent, n = 1 << 22, 1 << 20
+    n_ent = 1 << 22
+    n = n_ent
     rng = np.random.default_rng(7)
     keys = rng.integers(0, 256, size=(n_ent, 36), dtype=np.uint8)
     ent = np.zeros(n_ent, dtype=ENTRY_DTYPE)
@@ -453,8 +455,9 @@ def measure_utxo_table(ctx, dev, stream, peak_gbs):
     ctx.synchronize()
     ins_s = time.perf_counter() - t0
     assert us.count() == n_ent
-    reps = 5
-    dks = [torch.from_numpy(keys[rng.choice(n_ent, size=n, replace=False)]).to(dev) for _ in range(reps + 1)]
+    reps = 4
+    dkeys = torch.from_numpy(keys).to(dev)
+    dks = [dkeys[torch.randperm(n_ent, device=dev)].contiguous() for _ in range(reps + 1)]
     de = torch.empty(n * ENTRY_DTYPE.itemsize, dtype=torch.uint8, device=dev)
     df = torch.empty(n, dtype=torch.uint8, device=dev)
     call = lambda dk: ctx._check(ctx._lib.kgv_utxo_lookup(ctx._h, us._h, dk.data_ptr(), n, de.data_ptr(), None, 0, df.data_ptr()))
@@ -467,12 +470,35 @@ def measure_utxo_table(ctx, dev, stream, peak_gbs):
     e1.record(stream)
     stream.synchronize()
     s = e0.elapsed_time(e1) * 1e-3 / reps
+    # erase + re-insert 1 Mi entries per call, device arrays
+    m = 1 << 20
+    sel = torch.randperm(n_ent, device=dev)[:m]
+    dk1 = dkeys[sel].contiguous()
+    dent = torch.from_numpy(ent.view(np.uint8).reshape(-1, ENTRY_DTYPE.itemsize)).to(dev)[sel].contiguous()
+    darena = torch.from_numpy(arena).to(dev)
+    drs, das = torch.empty(m, dtype=torch.uint8, device=dev), torch.empty(m, dtype=torch.uint8, device=dev)
+    lib, h = ctx._lib, ctx._h
+    erase = lambda: ctx._check(lib.kgv_utxo_apply_diff(h, us._h, dk1.data_ptr(), m, drs.data_ptr(), None, None, None, 0, 0, None))
+    insert = lambda: ctx._check(lib.kgv_utxo_apply_diff(h, us._h, None, 0, None, dk1.data_ptr(), dent.data_ptr(), darena.data_ptr(), len(arena), m, das.data_ptr()))
+    erase(); insert(); stream.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    t_er = t_in = 0.0
+    for _ in range(3):
+        ev[0].record(stream); erase(); ev[1].record(stream); insert(); ev[2].record(stream); stream.synchronize()
+        t_er += ev[0].elapsed_time(ev[1]) * 1e-3 / 3; t_in += ev[1].elapsed_time(ev[2]) * 1e-3 / 3
+    assert int(drs.sum().item()) == m and us.count() == n_ent
     us.close()
-    gbs = n * (36 + 128 + 32 + 1) / s * 1e-9
-    return {"what": "k_utxo_lookup, 1 Mi random hits per call out of 4 Mi entries in a 2 GiB table (device-resident keys/results, new keys every call)",
+    gbs = n * 164 / s * 1e-9
+    return {"what": "k_utxo_lookup, 4 Mi random hits per call (every entry of a 2 GiB table, new order every call; device-resident keys/results)",
             "lookups_per_s": n / s, "ms_per_call": s * 1e3, "insert_4Mi_entries_host_arrays_ms": ins_s * 1e3,
+            "erase_per_s": m / t_er, "insert_per_s": m / t_in,
             "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak_gbs, "unit": "GB/s", "frac": gbs / peak_gbs if peak_gbs else None,
-                         "bytes_per_lookup": 197}}
+                         "bytes_per_lookup": 164, "note": "SURVEY §8d bytes (36 B key + one 128 B slot); 33 more bytes per lookup are written (entry + found flag); "
+                                                          "the probe reads 64 of the slot's 128 bytes"},
+            "roofline_erase": {"achieved": m * 164 / t_er * 1e-9, "peak": peak_gbs, "unit": "GB/s", "frac": m * 164 / t_er * 1e-9 / peak_gbs if peak_gbs else None,
+                               "bytes_per_op": 164},
+            "roofline_insert": {"achieved": m * (36 + 32 + 34 + 128) / t_in * 1e-9, "peak": peak_gbs, "unit": "GB/s",
+                                "frac": m * (36 + 32 + 34 + 128) / t_in * 1e-9 / peak_gbs if peak_gbs else None, "bytes_per_op": 230}}
 
 
 def measure_small_batches(ctx):
@@ -743,14 +769,17 @@ def run_ours(args, rank, world, local_rank):
                "per_quota_cpu": sample / dt / (quota or logical),
                "sample": f"first {sample} triples of the same batch, oracle/ok_secp_fast.c (GLV + wNAF CPU port of the reference path), {threads} pthreads; verdicts identical to the GPU's"}
 
-    txv = txv4 = ecd = small = utx = rep = None
+    txv = ecd = small = utx = rep = rep4 = None
     if world == 1 and args.replay_blocks > 0:
         with torch.cuda.stream(stream):
             rep = measure_dag_replay(ctx, dev, args.replay_blocks, 150, args.replay_window, 0 if args.no_cpu_baseline else 12.0)
+            # BASELINE configs[3]: ECDSA + P2SH 2-of-3 multisig, 500 k transactions: 50 % P2PK-ECDSA, 25 % P2SH Schnorr 2-of-3, 25 % P2SH ECDSA 2-of-3,
+            # ~1 % invalid of every class (wrong order => NullFail, corrupted => EvalFalse, high S, bad hash type, ...), as a chain replayed in order
+            rep4 = measure_dag_replay(ctx, dev, max(64, int(args.replay_blocks * 0.35)), 150, args.replay_window, 0 if args.no_cpu_baseline else 8.0,
+                                      mix=(0.0, 0.5, 0.25, 0.25), label="config 4", seed=0x4B475634)
     if world == 1 and args.tx_window > 0:
         with torch.cuda.stream(stream):
             txv = measure_tx_validation(ctx, dev, args.tx_window, max(2, min(args.steps, 5)))
-            txv4 = measure_tx_validation(ctx, dev, args.tx_window, max(2, min(args.steps, 5)), mix=(0.5, 0.0, 0.25, 0.25), label="config 4 shape")
             ecd = measure_ecdsa(ctx, dev, stream, min(n, 1 << 19), 3)
             small = measure_small_batches(ctx)
             utx = measure_utxo_table(ctx, dev, stream, peak)
@@ -767,14 +796,15 @@ def run_ours(args, rank, world, local_rank):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": peak_src, "kernel": "k_schnorr_verify", "kernel_ms": kern_ms_avg,
                          "note": "integer-issue bound by construction: 129 algorithmic bytes per verify vs 4.1e5 integer instructions; the binding roofline is integer_issue",
-                         "integer_issue": integer_issue_roofline(n, kern_ms_avg, clocks)},
+                         "integer_issue": integer_issue_roofline(n, kern_ms_avg, merge_clocks(cl_all))},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 128 * n * world, "d2h_bytes_per_step": (n if world == 1 else nbm * world) * world,
                     "steps": e2e_steps,
                     "how": ("kgv_schnorr_verify through the C ABI with pinned host buffers: H2D + kernel + D2H + sync inside the timed region (host clock)" if world == 1 else
                             "per rank and step: H2D of the rank's triples from pinned memory, kgv_schnorr_verify (device pointers), the bitmap exchange, D2H of the gathered bitmap, sync "
                             "(host clock, max over ranks)")},
-            "dag_replay": rep, "tx_validation": txv, "tx_validation_ecdsa_multisig": txv4, "ecdsa": ecd, "small_batches": small, "utxo_table": utx, "gpu_launches": int(launches), "clocks": clocks}
+            "dag_replay": rep, "dag_replay_ecdsa_multisig": rep4, "dag_replay_sharded": rep5, "tx_validation": txv, "ecdsa": ecd, "small_batches": small,
+            "utxo_table": utx, "gpu_launches": int(launches), "clocks": merge_clocks(cl_all)}
     emit_json_line(line)
 
 

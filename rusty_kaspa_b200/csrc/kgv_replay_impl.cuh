@@ -161,7 +161,8 @@ __device__ __forceinline__ void prefetch_range(const void* p, size_t bytes, uint
 // So each block is STAGED in shared memory first: all 1024 threads copy its transaction / input / output records, tx ids, script verdicts
 // and index maps with independent 8-byte loads (one memory latency for everything), then the output scripts the inserts will store; the
 // three phases then run out of shared memory and touch global memory only for the table itself (probe, claim, store) and for the results.
-// Table lines are prefetched into L2 one block ahead, record ranges two blocks ahead.  Blocks too large for the staging area take the
+// Record ranges are prefetched into L2 two blocks ahead (by address range only: a prefetch that itself needs dependent loads - e.g. the
+// table slots of the next block - was measured to cost more on the critical path than the miss it hides).  Blocks too large for the staging area take the
 // same code path with the pointers left on the global arrays.
 #define RP_MAXT 320u
 #define RP_MAXI 640u
@@ -175,8 +176,8 @@ struct ReplaySmem {
   kgv_tx_result pre[RP_MAXT];
   DevEntry dent[RP_MAXI];
   UtxoSlot* slot[RP_MAXI];
-  uint32_t itx[RP_MAXI];
-  uint32_t otx[RP_MAXO];
+  uint32_t itx[RP_MAXI + 2];  // staged from an 8-byte aligned start: one word of slack on either side
+  uint32_t otx[RP_MAXO + 2];
   uint32_t scr[RP_MAXO][RP_SCR / 4];
   uint8_t acc[RP_MAXT];
 };
@@ -212,36 +213,16 @@ __global__ void __launch_bounds__(1024, 1) k_replay_inorder(ReplayArgs a) {
     prefetch_range(a.itx + r.i0, (size_t)(r.i1 - r.i0) * 4, rtid, nth);
     prefetch_range(a.otx + r.o0, (size_t)(r.o1 - r.o0) * 4, rtid, nth);
   };
-  auto prefetch_slots = [&](uint32_t bi) {
-    if (bi >= a.n_blocks) return;
-    const ReplayRange r = a.ranges[bi];
-    for (uint32_t i = r.i0 + rtid; i < r.i1; i += nth) {
-      uint32_t k[9];
-      input_key(k, a.b.inputs[i]);
-      prefetch_l2(&a.t.slots[key_hash(k) & a.t.mask]);
-    }
-    if (!(r.flags & KGV_REPLAY_VERIFY_ONLY))
-      for (uint32_t o = r.o0 + rtid; o < r.o1; o += nth) {
-        const uint32_t ti = a.otx[o];
-        uint32_t k[9];
-#pragma unroll
-        for (int w = 0; w < 4; w++) { uint64_t q = a.ids[4 * (size_t)ti + w]; k[2 * w] = (uint32_t)q; k[2 * w + 1] = (uint32_t)(q >> 32); }
-        k[8] = o - a.b.txs[ti].first_output;
-        prefetch_l2(&a.t.slots[key_hash(k) & a.t.mask]);
-        prefetch_l2(a.b.bytes + a.b.outputs[o].script_off);
-      }
-  };
   prefetch_records(0);
   prefetch_records(1);
   __syncthreads();
-  prefetch_slots(0);
   long long tk[6] = {0, 0, 0, 0, 0, 0}, c0 = 0;  // KGV_DEBUG: cycles per phase, as seen by thread 0
 #define RP_TICK(k) do { if (a.timers && tid == 0) { long long c1 = clock64(); tk[k] += c1 - c0; c0 = c1; } } while (0)
   if (a.timers && tid == 0) c0 = clock64();
   for (uint32_t bi = 0; bi < a.n_blocks; bi++) {
     const ReplayRange bl = a.ranges[bi];
     prefetch_records(bi + 2);
-    if (bl.t1 == bl.t0) { prefetch_slots(bi + 1); continue; }
+    if (bl.t1 == bl.t0) continue;
     const uint32_t t0 = bl.t0, t1 = bl.t1, i0 = bl.i0, i1 = bl.i1, o0 = bl.o0, o1 = bl.o1;
     const bool staged = t1 - t0 <= RP_MAXT && i1 - i0 <= RP_MAXI && o1 - o0 <= RP_MAXO;
     // absolute-index views of this block's data: shared memory when staged, the global arrays otherwise
@@ -255,15 +236,38 @@ __global__ void __launch_bounds__(1024, 1) k_replay_inorder(ReplayArgs a) {
     UtxoSlot** p_slot = a.slotp;
     uint8_t* p_acc = a.accept;
     if (staged) {
-      copy8(S.txs, a.b.txs + t0, (size_t)(t1 - t0) * sizeof(kgv_tx), tid, nth);
-      copy8(S.inputs, a.b.inputs + i0, (size_t)(i1 - i0) * sizeof(kgv_input), tid, nth);
-      copy8(S.outputs, a.b.outputs + o0, (size_t)(o1 - o0) * sizeof(kgv_output), tid, nth);
-      copy8(S.ids, a.ids + 4 * (size_t)t0, (size_t)(t1 - t0) * 32, tid, nth);
-      copy8(S.pre, a.pre + t0, (size_t)(t1 - t0) * sizeof(kgv_tx_result), tid, nth);
-      copy4(S.itx, a.itx + i0, (size_t)(i1 - i0) * 4, tid, nth);
-      copy4(S.otx, a.otx + o0, (size_t)(o1 - o0) * 4, tid, nth);
+      // one flat list of 8-byte words over the seven record ranges; every thread issues ALL its loads before its first store, so the whole
+      // block arrives in one memory latency (copying range after range serialises ~10 dependent round trips: measured 4 us per block)
+      const uint64_t* src[7] = {(const uint64_t*)(a.b.txs + t0), (const uint64_t*)(a.b.inputs + i0), (const uint64_t*)(a.b.outputs + o0), a.ids + 4 * (size_t)t0,
+                                (const uint64_t*)(a.pre + t0), (const uint64_t*)(a.itx + (i0 & ~1u)), (const uint64_t*)(a.otx + (o0 & ~1u))};
+      uint64_t* dst[7] = {(uint64_t*)S.txs, (uint64_t*)S.inputs, (uint64_t*)S.outputs, S.ids, (uint64_t*)S.pre, (uint64_t*)S.itx, (uint64_t*)S.otx};
+      const uint32_t nw[7] = {(t1 - t0) * 9u, (i1 - i0) * 7u, (o1 - o0) * 3u, (t1 - t0) * 4u, (t1 - t0) * 2u, (i1 - (i0 & ~1u) + 1u) / 2u, (o1 - (o0 & ~1u) + 1u) / 2u};
+      uint32_t start[8];
+      start[0] = 0;
+#pragma unroll
+      for (int q = 0; q < 7; q++) start[q + 1] = start[q] + nw[q];
+      constexpr int RP_BATCH = 8;
+      for (uint32_t base = 0; base < start[7]; base += RP_BATCH * nth) {
+        uint64_t v[RP_BATCH];
+        uint64_t* d[RP_BATCH];
+#pragma unroll
+        for (int u = 0; u < RP_BATCH; u++) {
+          const uint32_t w = base + u * nth + tid;
+          d[u] = nullptr;
+          if (w < start[7]) {
+            int q = 0;
+#pragma unroll
+            for (int r = 1; r < 7; r++) q += w >= start[r];
+            const uint32_t off = w - start[q];
+            v[u] = __ldg(src[q] + off);
+            d[u] = dst[q] + off;
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < RP_BATCH; u++) if (d[u]) *d[u] = v[u];
+      }
       p_txs = S.txs - t0; p_in = S.inputs - i0; p_out = S.outputs - o0; p_ids = S.ids - 4 * (size_t)t0; p_pre = S.pre - t0;
-      p_itx = S.itx - i0; p_otx = S.otx - o0; p_dent = S.dent - i0; p_slot = S.slot - i0; p_acc = S.acc - t0;
+      p_itx = S.itx - (i0 & ~1u); p_otx = S.otx - (o0 & ~1u); p_dent = S.dent - i0; p_slot = S.slot - i0; p_acc = S.acc - t0;
       __syncthreads();
       RP_TICK(0);
       if (!(bl.flags & KGV_REPLAY_VERIFY_ONLY))  // scripts the inserts will store (consumed in phase C, two barriers from here)
@@ -300,7 +304,6 @@ __global__ void __launch_bounds__(1024, 1) k_replay_inorder(ReplayArgs a) {
       p_slot[i] = s;
       if (staged) a.dent[i] = d;  // the global copy feeds kgv_replay_muhash
     }
-    prefetch_slots(bi + 1);
     __syncthreads();
     RP_TICK(2);
     // ---- B: context rules and the acceptance decision

@@ -176,9 +176,13 @@ KGV_HD uint32_t resolve_input(const InputPlan& pl, const uint8_t* ss, const DevE
 
 // ---- per-transaction context rules (tx_validation_in_utxo_context.rs:75-155, mass/mod.rs:64-80,338-410)
 KGV_HD uint64_t utxo_plurality(uint32_t script_len) { return (63ull + script_len + 99ull) / 100ull; }
-KGV_HD bool ck_mul(uint64_t a, uint64_t b, uint64_t& r) {  // true on overflow
+KGV_HD bool ck_mul(uint64_t a, uint64_t b, uint64_t& r) {  // true on overflow (u64::checked_mul): the high half of the 128-bit product decides, no division
   r = a * b;
-  return a != 0 && r / a != b;
+#if defined(__CUDA_ARCH__)
+  return __umul64hi(a, b) != 0;
+#else
+  return (uint64_t)(((unsigned __int128)a * b) >> 64) != 0;
+#endif
 }
 KGV_HD bool ck_add(uint64_t a, uint64_t b, uint64_t& r) { r = a + b; return r < a; }
 KGV_HD uint64_t sat_add(uint64_t a, uint64_t b) { uint64_t r = a + b; return r < a ? ~0ull : r; }

@@ -234,7 +234,7 @@ def test_signature_cache_changes_speed_never_results(gpu_ctx, oracle):
     table (hits == lookups of that call, no inserts); a changed signature misses; parse errors are never cached; a tiny cache evicts but stays
     correct; the mempool -> block re-validation pattern hits."""
     from rusty_kaspa_b200.validator import SigCache
-    from rusty_kaspa_b200 import simgen
+    from rusty_kaspa_b200 import simgen, workload as W
     fk, fe, txs = simgen.funded_window(600, n_keys=64, n_nonces=128, mix=(0.4, 0.2, 0.2, 0.2))
     ents, k = [], 0
     for t in txs:
