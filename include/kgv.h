@@ -41,6 +41,7 @@ extern "C" {
 #define KGV_ERR_CUDA (-2)
 #define KGV_ERR_NOMEM (-3)
 #define KGV_ERR_NCCL (-4)
+#define KGV_ERR_LIMIT (-5) /* an internal iteration cap was hit (kgv_check_scripts_host); kgv_last_error says which */
 
 /* Per-signature verdicts.  The reference distinguishes these cases
  * (crypto/txscript/src/lib.rs:582-583, 593, 618-619, 628):
@@ -473,6 +474,22 @@ int kgv_script_execute(const kgv_tx_batch* batch, uint32_t tx, uint32_t input_in
  * hashed and verified on the GPU in batches (as many rounds as the scripts' control flow needs).
  * results[i] belongs to tx_indices[i]: status KGV_TX_OK / KGV_TX_SIGNATURE_INVALID / KGV_TX_SIGNATURE_EMPTY. */
 int kgv_check_scripts_host(kgv_ctx* ctx, const kgv_tx_batch* batch, const uint32_t* tx_indices, size_t n, kgv_tx_result* results);
+
+/* ------------------------------------------------------------------------------------------------
+ * Persistence formats either side of the path: the RocksDB rows of DbUtxoSetStore.  Host functions (the store lives on
+ * the host): what a shim runs between the database and kgv_utxo_apply_diff / kgv_utxo_lookup (write_diff_batch utxo_set.rs:107-112, the
+ * iterator feeding the pruning-point UTXO-set import processor.rs:1126-1200).
+ *   key row    txid(32) || index u32 LE with trailing zero bytes trimmed, at least one kept (UtxoKey, utxo_set.rs:31-62) - WITHOUT the store's
+ *              prefix bytes, which the caller prepends
+ *   value row  bincode::serialize(&UtxoEntry) (database/src/access.rs:139): amount u64 || spk version u16 || script length u64 || script ||
+ *              block_daa_score u64 || is_coinbase u8, all little-endian
+ * Rows are packed back to back; *_off has n + 1 entries.  encode: key_rows / value_rows may be NULL (with capacity 0) to size the buffers first.
+ * decode: scripts are appended to bytes_out and entries[i].script_off points there; malformed rows -> KGV_ERR_ARG.
+ * ------------------------------------------------------------------------------------------------ */
+int kgv_utxo_rows_encode(const uint8_t* keys36, const kgv_utxo_entry* entries, const uint8_t* bytes, size_t n_bytes, size_t n, uint8_t* key_rows, uint64_t* key_off,
+                         uint8_t* value_rows, uint64_t* value_off, size_t key_cap, size_t value_cap);
+int kgv_utxo_rows_decode(const uint8_t* key_rows, const uint64_t* key_off, const uint8_t* value_rows, const uint64_t* value_off, size_t n, uint8_t* keys36,
+                         kgv_utxo_entry* entries, uint8_t* bytes_out, size_t bytes_cap, size_t* bytes_used);
 
 /* Test / audit hook: affine coordinates (x||y, 32-byte big-endian each) of entry v (1..65535) of
  * generator table `which` (0: v*G, 1: v*2^128*G) as built on the device. */

@@ -333,7 +333,13 @@ class MuHash {
 class UtxoSet {
  public:
   UtxoSet(Context& c, uint64_t capacity_slots) : c_(c) { c_.check(kgv_utxo_create(c_.get(), capacity_slots, &h_)); }
+  // UtxoViewComposition::compose (consensus/core/src/utxo/utxo_view.rs:22-35,45-50): a diff layer over `base`; this object then IS base ∘ diff:
+  // reads fall through to the base, writes stay in the layer until commit() (write_diff_batch) or discard()
+  UtxoSet(Context& c, UtxoSet& base, uint64_t capacity_slots) : c_(c) { c_.check(kgv_utxo_view_create(c_.get(), base.get(), capacity_slots, &h_)); view_ = true; }
   ~UtxoSet() { if (h_) kgv_utxo_destroy(c_.get(), h_); }
+  void commit() { c_.check(kgv_utxo_view_commit(c_.get(), h_)); }
+  void discard() { c_.check(kgv_utxo_view_discard(c_.get(), h_)); }
+  bool is_view() const { return view_; }
   UtxoSet(const UtxoSet&) = delete;
   UtxoSet& operator=(const UtxoSet&) = delete;
   kgv_utxo_table* get() const { return h_; }
@@ -372,6 +378,23 @@ class UtxoSet {
   }
   Context& c_;
   kgv_utxo_table* h_ = nullptr;
+  bool view_ = false;
+};
+
+// ---- Cache<SigCacheKey, bool> (crypto/txscript/src/caches.rs:14-55): device-resident, attached to a context ----
+class SigCache {
+ public:
+  SigCache(Context& c, uint64_t size = 10000) : c_(c) { c_.check(kgv_sigcache_create(c_.get(), size, &h_)); c_.check(kgv_set_sigcache(c_.get(), h_)); }
+  ~SigCache() { if (h_) { kgv_set_sigcache(c_.get(), nullptr); kgv_sigcache_destroy(h_); } }
+  SigCache(const SigCache&) = delete;
+  SigCache& operator=(const SigCache&) = delete;
+  void clear() { c_.check(kgv_sigcache_clear(c_.get(), h_)); }
+  struct Counters { uint64_t get_counts, insert_counts, lookups, evictions; };  // caches.rs:57-93
+  Counters counters() { Counters k{}; c_.check(kgv_sigcache_counters(c_.get(), h_, &k.get_counts, &k.insert_counts, &k.lookups, &k.evictions)); return k; }
+
+ private:
+  Context& c_;
+  kgv_sigcache* h_ = nullptr;
 };
 
 // ---- transaction validation in UTXO context ----
@@ -395,6 +418,17 @@ class TransactionValidator {
     std::vector<kgv_tx_result> res(b.len());
     kgv_tx_batch v = b.view(false);
     c_.check(kgv_validate_txs(c_.get(), utxo_view.get(), &v, pov_daa_score, (uint32_t)flags, &p_, res.data()));
+    return res;
+  }
+  // calculate_utxo_state / verify_expected_utxo_state for a WINDOW of blocks as one call (utxo_validation.rs:110-228): block b = transactions
+  // [blocks[b].first_tx, +n_txs) of the batch (tx 0 = its coinbase); flags per block KGV_REPLAY_*.  Returns the per-transaction verdicts; `accept`
+  // (optional) receives which transactions were folded into the set.
+  std::vector<kgv_tx_result> replay_window(UtxoSet& utxo_view, const TxBatch& b, const std::vector<kgv_replay_block>& blocks, std::vector<uint8_t>* accept = nullptr,
+                                           kgv_replay_stats* stats = nullptr) {
+    std::vector<kgv_tx_result> res(b.len());
+    if (accept) accept->assign(b.len(), 0);
+    kgv_tx_batch v = b.view(false);
+    c_.check(kgv_replay_window(c_.get(), utxo_view.get(), &v, blocks.data(), blocks.size(), &p_, res.data(), accept ? accept->data() : nullptr, stats));
     return res;
   }
   // validate_mempool_transactions_in_parallel (consensus/src/pipeline/virtual_processor/processor.rs:853-878): same kernels, but every

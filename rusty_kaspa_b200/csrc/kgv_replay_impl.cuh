@@ -236,36 +236,15 @@ __global__ void __launch_bounds__(1024, 1) k_replay_inorder(ReplayArgs a) {
     UtxoSlot** p_slot = a.slotp;
     uint8_t* p_acc = a.accept;
     if (staged) {
-      // one flat list of 8-byte words over the seven record ranges; every thread issues ALL its loads before its first store, so the whole
-      // block arrives in one memory latency (copying range after range serialises ~10 dependent round trips: measured 4 us per block)
-      const uint64_t* src[7] = {(const uint64_t*)(a.b.txs + t0), (const uint64_t*)(a.b.inputs + i0), (const uint64_t*)(a.b.outputs + o0), a.ids + 4 * (size_t)t0,
-                                (const uint64_t*)(a.pre + t0), (const uint64_t*)(a.itx + (i0 & ~1u)), (const uint64_t*)(a.otx + (o0 & ~1u))};
-      uint64_t* dst[7] = {(uint64_t*)S.txs, (uint64_t*)S.inputs, (uint64_t*)S.outputs, S.ids, (uint64_t*)S.pre, (uint64_t*)S.itx, (uint64_t*)S.otx};
-      const uint32_t nw[7] = {(t1 - t0) * 9u, (i1 - i0) * 7u, (o1 - o0) * 3u, (t1 - t0) * 4u, (t1 - t0) * 2u, (i1 - (i0 & ~1u) + 1u) / 2u, (o1 - (o0 & ~1u) + 1u) / 2u};
-      uint32_t start[8];
-      start[0] = 0;
-#pragma unroll
-      for (int q = 0; q < 7; q++) start[q + 1] = start[q] + nw[q];
-      constexpr int RP_BATCH = 8;
-      for (uint32_t base = 0; base < start[7]; base += RP_BATCH * nth) {
-        uint64_t v[RP_BATCH];
-        uint64_t* d[RP_BATCH];
-#pragma unroll
-        for (int u = 0; u < RP_BATCH; u++) {
-          const uint32_t w = base + u * nth + tid;
-          d[u] = nullptr;
-          if (w < start[7]) {
-            int q = 0;
-#pragma unroll
-            for (int r = 1; r < 7; r++) q += w >= start[r];
-            const uint32_t off = w - start[q];
-            v[u] = __ldg(src[q] + off);
-            d[u] = dst[q] + off;
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < RP_BATCH; u++) if (d[u]) *d[u] = v[u];
-      }
+      // plain range-after-range copies: measured FASTER on the single SM than one flat, batched copy (the index arithmetic of the flat form costs
+      // more issue slots over 32 warps than the serialised latencies it removes: 13.6 k vs 8.0 k cycles per block)
+      copy8(S.txs, a.b.txs + t0, (size_t)(t1 - t0) * sizeof(kgv_tx), tid, nth);
+      copy8(S.inputs, a.b.inputs + i0, (size_t)(i1 - i0) * sizeof(kgv_input), tid, nth);
+      copy8(S.outputs, a.b.outputs + o0, (size_t)(o1 - o0) * sizeof(kgv_output), tid, nth);
+      copy8(S.ids, a.ids + 4 * (size_t)t0, (size_t)(t1 - t0) * 32, tid, nth);
+      copy8(S.pre, a.pre + t0, (size_t)(t1 - t0) * sizeof(kgv_tx_result), tid, nth);
+      copy8(S.itx, a.itx + (i0 & ~1u), (size_t)((i1 - (i0 & ~1u) + 1u) / 2u) * 8, tid, nth);
+      copy8(S.otx, a.otx + (o0 & ~1u), (size_t)((o1 - (o0 & ~1u) + 1u) / 2u) * 8, tid, nth);
       p_txs = S.txs - t0; p_in = S.inputs - i0; p_out = S.outputs - o0; p_ids = S.ids - 4 * (size_t)t0; p_pre = S.pre - t0;
       p_itx = S.itx - (i0 & ~1u); p_otx = S.otx - (o0 & ~1u); p_dent = S.dent - i0; p_slot = S.slot - i0; p_acc = S.acc - t0;
       __syncthreads();

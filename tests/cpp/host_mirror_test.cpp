@@ -104,6 +104,27 @@ int main(int argc, char** argv) {
     std::cout << "\n";
     std::cout << "tx_muhash_num " << hex(vm.second.numerator().data(), 384) << "\n";
     std::cout << "tx_muhash_den " << hex(vm.second.denominator().data(), 384) << "\n";
+    // --- composed view + SigCache: the same block through base ∘ (diff layer), twice with a cache attached (second pass answered from the cache);
+    //     applying it to the LAYER leaves the base untouched; discard drops the branch
+    {
+      kgv::UtxoSet view(ctx, us, 1 << 12);
+      kgv::SigCache cache(ctx, 1 << 12);
+      auto r1 = tv.validate_transactions_in_parallel(view, b, 10);
+      auto k1 = cache.counters();
+      auto r2 = tv.validate_transactions_in_parallel(view, b, 10);
+      auto k2 = cache.counters();
+      bool same = true;
+      for (size_t i = 0; i < r1.size(); i++) same = same && r1[i].status == vm.first[i].status && r2[i].status == vm.first[i].status && r1[i].script_err == vm.first[i].script_err;
+      view.add_transactions(b, accept, 10);
+      auto r3 = tv.validate_transactions_in_parallel(view, b, 10);  // everything accepted is now spent IN THE VIEW
+      size_t missing = 0;
+      for (size_t i = 0; i < r3.size(); i++) missing += (accept[i] && r3[i].status == KGV_TX_MISSING_OUTPOINTS);
+      size_t n_acc = 0;
+      for (uint8_t a : accept) n_acc += a;
+      std::cout << "view " << (same ? 1 : 0) << " " << us.count() << " " << (k2.get_counts - k1.get_counts) << " " << k1.insert_counts << " " << (k2.insert_counts - k1.insert_counts) << " "
+                << missing << " " << n_acc << "\n";
+      view.discard();
+    }
     us.add_transactions(b, accept, 10);
     before.combine(vm.second);
     std::cout << "commitment_matches " << (before.finalize() == us.muhash().finalize() ? 1 : 0) << "\n";
