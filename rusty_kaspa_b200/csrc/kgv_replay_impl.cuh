@@ -29,7 +29,7 @@
 __device__ __forceinline__ uint64_t wm_hash(const uint64_t* id) { return id[0] ^ (id[1] * 0x9E3779B97F4A7C15ull) ^ (id[2] >> 17) ^ (id[3] << 13); }
 __device__ __forceinline__ bool id_eq(const uint64_t* a, const uint64_t* b) { return a[0] == b[0] && a[1] == b[1] && a[2] == b[2] && a[3] == b[3]; }
 
-__global__ void k_wm_insert(const uint64_t* __restrict__ ids, uint32_t n_txs, uint32_t* __restrict__ wm, uint64_t wm_mask) {
+__global__ void k_wm_insert(const uint64_t* __restrict__ ids, uint32_t n_txs, uint32_t* __restrict__ wm, uint64_t wm_mask, uint8_t* __restrict__ has_sibling) {
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_txs) return;
   const uint64_t* id = ids + 4 * (size_t)t;
@@ -38,7 +38,7 @@ __global__ void k_wm_insert(const uint64_t* __restrict__ ids, uint32_t n_txs, ui
     uint32_t cur = atomicCAS(&wm[i], 0u, t + 1);
     if (cur == 0u) return;
     // the same transaction may sit in several parallel blocks of a DAG: one representative is enough (identical outputs)
-    if (id_eq(ids + 4 * (size_t)(cur - 1), id)) return;
+    if (id_eq(ids + 4 * (size_t)(cur - 1), id)) { has_sibling[cur - 1] = 1; return; }
   }
 }
 __device__ __forceinline__ int wm_find(const uint64_t* __restrict__ ids, const uint32_t* __restrict__ wm, uint64_t wm_mask, const uint64_t* id) {
@@ -373,44 +373,47 @@ __global__ void __launch_bounds__(1024, 1) k_replay_inorder(ReplayArgs a) {
 #define RS_NONE 0u
 #define RS_TABLE 1u
 #define RS_WINDOW 2u
-struct ReplaySrc {      // per input
-  uint32_t flag;        // index of the outpoint's spent flag: TABLE -> first input of the window probing the same slot; WINDOW -> global index of the creating output
+#define RS_FLAG_MASK 0x3FFFFFFFu
+struct ReplaySrc {      // per input (8 bytes: the walk stages these)
+  uint32_t flag;        // bits 30-31: RS_*; bits 0-29: index of the outpoint's spent flag - TABLE: first input of the window probing the same slot; WINDOW: global index of the creating output
   uint32_t src_tx;      // WINDOW: representative index of the creating transaction
 };
-struct ReplayTxInfo {   // per transaction
+struct __align__(16) ReplayTxInfo {   // per transaction (16 bytes)
   uint32_t first_input;
   uint32_t n_inputs;
-  uint8_t static_status;  // KGV_TX_OK or the first failing static rule (amounts / mass)
-  uint8_t bits;           // 1: coinbase (position 0 / subnetwork)  2: needs entry DAA scores  4: scripts ok (pre-check)  8: pre-check not applicable (skipped)
+  uint32_t rep;           // representative instance of this transaction id inside the window (itself unless a DAG sibling carries the same transaction)
+  uint8_t static_status;  // KGV_TX_OK or the first failing rule that does not depend on the walk
+  uint8_t bits;           // 1: coinbase (position 0 / subnetwork)  2: DAA-score rules depend on the walk (a window-created entry is involved)  4: scripts ok (pre-check)
   uint16_t pad_;
 };
+__device__ __forceinline__ uint32_t rs_kind(const ReplaySrc& r) { return r.flag >> 30; }
 
 // pointer map: table slot -> smallest input index of the window that found it (inputs spending one outpoint share one flag)
-__global__ void k_slotmap_insert(const uint8_t* __restrict__ kind, UtxoSlot* const* __restrict__ slot, size_t n_inputs, unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals,
+__device__ __forceinline__ uint64_t slotmap_hash(unsigned long long k) {
+  uint64_t h = (k >> 7) * 0x9E3779B97F4A7C15ull;
+  return h ^ (h >> 31);
+}
+__global__ void k_slotmap_insert(const ReplaySrc* __restrict__ src, UtxoSlot* const* __restrict__ slot, size_t n_inputs, unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals,
                                  uint64_t mask) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_inputs || kind[i] != RS_TABLE) return;
+  if (i >= n_inputs || rs_kind(src[i]) != RS_TABLE) return;
   const unsigned long long k = (unsigned long long)(uintptr_t)slot[i];
-  uint64_t h = (k >> 7) * 0x9E3779B97F4A7C15ull;
-  h ^= h >> 31;
-  for (uint64_t p = 0, j = h & mask; p <= mask; p++, j = (j + 1) & mask) {
+  for (uint64_t p = 0, j = slotmap_hash(k) & mask; p <= mask; p++, j = (j + 1) & mask) {
     unsigned long long cur = atomicCAS(&keys[j], 0ull, k);
     if (cur == 0ull || cur == k) { atomicMin(&vals[j], (uint32_t)i); return; }
   }
 }
-__global__ void k_slotmap_lookup(const uint8_t* __restrict__ kind, UtxoSlot* const* __restrict__ slot, size_t n_inputs, const unsigned long long* __restrict__ keys,
-                                 const uint32_t* __restrict__ vals, uint64_t mask, ReplaySrc* __restrict__ src) {
+__global__ void k_slotmap_lookup(UtxoSlot* const* __restrict__ slot, size_t n_inputs, const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ vals, uint64_t mask,
+                                 ReplaySrc* __restrict__ src) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_inputs || kind[i] != RS_TABLE) return;
+  if (i >= n_inputs || rs_kind(src[i]) != RS_TABLE) return;
   const unsigned long long k = (unsigned long long)(uintptr_t)slot[i];
-  uint64_t h = (k >> 7) * 0x9E3779B97F4A7C15ull;
-  h ^= h >> 31;
-  for (uint64_t p = 0, j = h & mask; p <= mask; p++, j = (j + 1) & mask)
-    if (keys[j] == k) { src[i].flag = vals[j]; return; }
+  for (uint64_t p = 0, j = slotmap_hash(k) & mask; p <= mask; p++, j = (j + 1) & mask)
+    if (keys[j] == k) { src[i].flag = (RS_TABLE << 30) | vals[j]; return; }
 }
 // sources of every input + the entry the pre-check (and the static rules) read
-__global__ void k_replay_sources(TableView t, BatchView b, size_t n_inputs, const uint64_t* __restrict__ ids, const uint32_t* __restrict__ wm, uint64_t wm_mask, DevEntry* __restrict__ dent,
-                                 uint8_t* __restrict__ kind, UtxoSlot** __restrict__ slot, ReplaySrc* __restrict__ src) {
+__global__ void k_replay_sources(TableView t, BatchView b, size_t n_inputs, const uint64_t* __restrict__ ids, const uint32_t* __restrict__ wm, uint64_t wm_mask, const uint32_t* __restrict__ tx_block,
+                                 const ReplayRange* __restrict__ ranges, DevEntry* __restrict__ dent, UtxoSlot** __restrict__ slot, ReplaySrc* __restrict__ src) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_inputs) return;
   const kgv_input& in = b.inputs[i];
@@ -420,9 +423,8 @@ __global__ void k_replay_sources(TableView t, BatchView b, size_t n_inputs, cons
   UtxoSlot* s = table_find(t, k, h);
   DevEntry d;
   ReplaySrc r;
-  r.flag = 0; r.src_tx = 0;
-  uint8_t kd = RS_NONE;
-  if (s) { head_to_entry(d, t, s, h); kd = RS_TABLE; }
+  r.flag = RS_NONE << 30; r.src_tx = 0;
+  if (s) { head_to_entry(d, t, s, h); r.flag = RS_TABLE << 30; }
   else {
     entry_absent(d);
     uint64_t id[4];
@@ -434,51 +436,58 @@ __global__ void k_replay_sources(TableView t, BatchView b, size_t n_inputs, cons
       if (in.prev_index < stx.n_outputs) {
         const kgv_output& o = b.outputs[stx.first_output + in.prev_index];
         d.amount = o.value; d.script = b.bytes + o.script_off; d.script_len = o.script_len; d.spk_version = o.spk_version;
-        d.is_coinbase = tx_is_coinbase(stx) ? 1 : 0;
+        d.is_coinbase = (tx_is_coinbase(stx) || ranges[tx_block[j]].t0 == (uint32_t)j) ? 1 : 0;  // the entry an accepted coinbase (position 0) leaves behind
         d.found = 1;
-        kd = RS_WINDOW;
-        r.flag = stx.first_output + in.prev_index;
+        r.flag = (RS_WINDOW << 30) | (stx.first_output + in.prev_index);
         r.src_tx = (uint32_t)j;
       }
     }
   }
   dent[i] = d;
-  kind[i] = kd;
   slot[i] = s;
   src[i] = r;
 }
-__global__ void k_replay_rep(const uint64_t* __restrict__ ids, const uint32_t* __restrict__ wm, uint64_t wm_mask, uint32_t n_txs, uint32_t* __restrict__ rep) {
-  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n_txs) return;
-  int j = wm_find(ids, wm, wm_mask, ids + 4 * (size_t)t);
-  rep[t] = j >= 0 ? (uint32_t)j : t;
-}
-// static rules per transaction (entries as populated for the pre-check) + the pre-check's script verdict folded into one record
+// static rules per transaction (entries as populated for the pre-check) + the pre-check's script verdict folded into one record.
+// A transaction whose DAA-score rules (coinbase maturity, relative locks) involve only entries whose DAA score is known up front is decided
+// here completely; one that involves an entry created by a transaction SEVERAL sibling blocks carry leaves those two rules to the walk (bits & 2), which then applies the rules in the
+// reference's order: maturity, [amounts, mass = static_status], sequence locks.
 __global__ void k_replay_static(BatchView b, uint32_t n_txs, kgv_params prm, const ReplayRange* __restrict__ ranges, const uint32_t* __restrict__ tx_block,
-                                const kgv_tx_result* __restrict__ pre, ReplayTxInfo* __restrict__ info, uint64_t* __restrict__ fee) {
+                                const kgv_tx_result* __restrict__ pre, const ReplaySrc* __restrict__ src, const uint64_t* __restrict__ ids, const uint32_t* __restrict__ wm, uint64_t wm_mask,
+                                const uint8_t* __restrict__ has_sibling, ReplayTxInfo* __restrict__ info, uint64_t* __restrict__ fee, uint32_t* __restrict__ sfail) {
   uint32_t ti = blockIdx.x * blockDim.x + threadIdx.x;
   if (ti >= n_txs) return;
   const kgv_tx& t = b.txs[ti];
   ReplayTxInfo o;
   o.first_input = t.first_input; o.n_inputs = t.n_inputs; o.static_status = KGV_TX_OK; o.bits = 0; o.pad_ = 0;
+  {
+    int j = wm_find(ids, wm, wm_mask, ids + 4 * (size_t)ti);
+    o.rep = j >= 0 ? (uint32_t)j : ti;
+  }
   const ReplayRange r = ranges[tx_block[ti]];
   const bool cb = ti == r.t0 || tx_is_coinbase(t);
   if (cb) o.bits |= 1;
-  const uint8_t ps = pre[ti].status;
-  if (ps == KGV_TX_OK) o.bits |= 4;
-  if (ps == KGV_PRE_SKIPPED) o.bits |= 8;
+  if (pre[ti].status == KGV_TX_OK) o.bits |= 4;
   uint64_t f = 0;
+  uint32_t fail = 0;
   if (!cb) {
     const DevEntry* ent = b.entries + t.first_input;
-    bool all = true, daa = false;
+    const ReplaySrc* sr = src + t.first_input;
+    // DAA score of the entry input i spends: the table's, or - created inside the window - the pov of the block that accepts the creator.  A creator
+    // with a single instance in the window can only be accepted in its own block; one that several sibling blocks carry is left to the walk.
+    auto entry_daa = [&](uint32_t i) -> uint64_t { return rs_kind(sr[i]) == RS_WINDOW ? ranges[tx_block[sr[i].src_tx]].pov : ent[i].block_daa_score; };
+    bool all = true, dyn = false;
     for (uint32_t i = 0; i < t.n_inputs; i++) {
       all = all && ent[i].found;
-      daa = daa || ent[i].is_coinbase || !(b.inputs[t.first_input + i].sequence & (1ull << 63));
+      const bool needs_daa = ent[i].is_coinbase || !(b.inputs[t.first_input + i].sequence & (1ull << 63));
+      dyn = dyn || (needs_daa && rs_kind(sr[i]) == RS_WINDOW && has_sibling[sr[i].src_tx]);
     }
-    if (daa) o.bits |= 2;
-    if (all) {  // amounts / spend / mass exactly as tx_context_rules orders them (maturity and sequence locks are the walk's: they read DAA scores)
-      uint64_t total_in = 0;
+    if (dyn) o.bits |= 2;
+    if (all) {  // the order of tx_context_rules (kgv_context.cuh)
       uint8_t st = KGV_TX_OK;
+      if (!dyn)
+        for (uint32_t i = 0; i < t.n_inputs; i++)
+          if (ent[i].is_coinbase && entry_daa(i) + prm.coinbase_maturity > r.pov) { st = KGV_TX_IMMATURE_COINBASE; fail = i; break; }
+      uint64_t total_in = 0;
       for (uint32_t i = 0; i < t.n_inputs && st == KGV_TX_OK; i++) {
         if (ck_add(total_in, ent[i].amount, total_in)) st = KGV_TX_INPUT_AMOUNT_OVERFLOW;
         else if (total_in > prm.max_sompi) st = KGV_TX_INPUT_AMOUNT_TOO_HIGH;
@@ -497,32 +506,45 @@ __global__ void k_replay_static(BatchView b, uint32_t n_txs, kgv_params prm, con
         if (!ok) st = KGV_TX_MASS_INCOMPUTABLE;
         else if (mass != t.mass) st = KGV_TX_WRONG_MASS;
       }
+      if (st == KGV_TX_OK && !dyn)
+        for (uint32_t i = 0; i < t.n_inputs; i++) {
+          const uint64_t seq = b.inputs[t.first_input + i].sequence;
+          if (seq & (1ull << 63)) continue;
+          const long long lock = (long long)entry_daa(i) + (long long)(seq & 0xFFFFFFFFull) - 1;
+          if (lock >= (long long)r.pov) { st = KGV_TX_SEQUENCE_LOCK; break; }
+        }
       o.static_status = st;
     }
   }
   info[ti] = o;
   fee[ti] = f;
+  sfail[ti] = fail;
 }
 
+// The walk.  Each block's records (16 bytes per transaction, 8 per input) are STAGED in shared memory one block ahead: at the top of iteration
+// b every thread issues its share of the loads for block b+1 into registers, block b is decided and committed out of shared memory, then the
+// registers are stored for the next iteration - the global-memory latency hides behind the current block's two barriers.
+#define RW_MAXT 512u
+#define RW_MAXI 1024u
+#define RW_WORDS ((RW_MAXT * 16u + RW_MAXI * 8u) / 8u)  // 8-byte words per staging buffer (2 per thread)
 struct WalkArgs {
   const ReplayRange* ranges;
   uint32_t n_blocks;
   const ReplayTxInfo* info;
-  const uint8_t* kind;
   const ReplaySrc* src;
-  const uint32_t* rep;
-  const DevEntry* dent;       // entries of the pre-check (DAA score / coinbase flag of table entries)
-  const kgv_input* inputs;    // sequence numbers (rare path)
-  volatile unsigned long long* acc_pov;  // per representative tx: pov of the block that accepted it (written here, read on the rare DAA path and by the finish kernels)
-  uint8_t* w_status;          // dynamic verdict per tx: 0 = passed the dynamic rules
-  uint32_t* w_fail;           // failing input for ImmatureCoinbaseSpend
+  const DevEntry* dent;       // entries of the pre-check (DAA score / coinbase flag), rare path only
+  const kgv_input* inputs;    // sequence numbers, rare path only
+  volatile unsigned long long* acc_pov;  // per representative tx: pov of the block that accepted it
+  uint8_t* w_status;          // dynamic verdict per tx
+  uint32_t* w_fail;           // failing input for a dynamic ImmatureCoinbaseSpend
   uint8_t* accept;
-  uint32_t* bm_spent_in;      // global copies of the bitmaps (written at the end; the walk itself uses them directly when they do not fit shared memory)
+  uint32_t* bm_spent_in;      // global copies of the bitmaps (written at the end; used directly when they do not fit shared memory)
   uint32_t* bm_spent_out;
   uint32_t* bm_accepted;
   uint32_t words_in, words_out, words_tx;
   uint64_t coinbase_maturity;
   unsigned long long* stats;
+  unsigned long long* timers;
   int use_smem;
 };
 __device__ __forceinline__ bool bm_get(const uint32_t* bm, uint32_t i) { return (*(const volatile uint32_t*)&bm[i >> 5] >> (i & 31)) & 1u; }
@@ -531,51 +553,74 @@ __device__ __forceinline__ void bm_set(uint32_t* bm, uint32_t i) { atomicOr(&bm[
 __global__ void __launch_bounds__(1024, 1) k_replay_walk(WalkArgs a) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const uint32_t tid = threadIdx.x, nth = blockDim.x;
+  unsigned long long* stage[2] = {(unsigned long long*)smem_raw, (unsigned long long*)smem_raw + RW_WORDS};
   uint32_t *spent_in = a.bm_spent_in, *spent_out = a.bm_spent_out, *accepted = a.bm_accepted;
   if (a.use_smem) {
-    spent_in = (uint32_t*)smem_raw; spent_out = spent_in + a.words_in; accepted = spent_out + a.words_out;
+    spent_in = (uint32_t*)(smem_raw + 2 * RW_WORDS * 8); spent_out = spent_in + a.words_in; accepted = spent_out + a.words_out;
     for (uint32_t w = tid; w < a.words_in + a.words_out + a.words_tx; w += nth) spent_in[w] = 0;
   }
-  __shared__ unsigned long long s_acc;
+  __shared__ unsigned int s_acc;
   if (tid == 0) s_acc = 0;
+  uint32_t n_acc = 0;  // per thread, reduced once at the end
+  const unsigned long long* info64 = (const unsigned long long*)a.info;
+  const unsigned long long* src64 = (const unsigned long long*)a.src;
+  auto fits = [](const ReplayRange& r) { return r.t1 - r.t0 <= RW_MAXT && r.i1 - r.i0 <= RW_MAXI; };
+  // word w of a block's staging image: info words first, then the inputs' source words
+  auto load_word = [&](const ReplayRange& r, uint32_t w, unsigned long long& v) -> bool {
+    const uint32_t n_info = 2 * (r.t1 - r.t0), n_src = r.i1 - r.i0;
+    if (w < n_info) { v = __ldcg(info64 + 2 * (size_t)r.t0 + w); return true; }
+    if (w - n_info < n_src) { v = __ldcg(src64 + (size_t)r.i0 + (w - n_info)); return true; }
+    return false;
+  };
+  ReplayRange cur = a.ranges[0], nxt = a.n_blocks > 1 ? a.ranges[1] : cur;
+  if (fits(cur)) {
+    unsigned long long v;
+    if (load_word(cur, tid, v)) stage[0][tid] = v;
+    if (load_word(cur, tid + nth, v)) stage[0][tid + nth] = v;
+  }
   __syncthreads();
+  long long tk[4] = {0, 0, 0, 0}, c0 = 0;
+#define RW_TICK(k) do { if (a.timers && tid == 0) { long long c1 = clock64(); tk[k] += c1 - c0; c0 = c1; } } while (0)
+  if (a.timers && tid == 0) c0 = clock64();
   for (uint32_t bi = 0; bi < a.n_blocks; bi++) {
-    const ReplayRange bl = a.ranges[bi];
-    if (bi + 2 < a.n_blocks) {  // L2 prefetch of the records two blocks ahead (plain address ranges)
-      const ReplayRange nx = a.ranges[bi + 2];
-      const uint32_t rtid = nth - 1 - tid;
-      prefetch_range(a.info + nx.t0, (size_t)(nx.t1 - nx.t0) * sizeof(ReplayTxInfo), rtid, nth);
-      prefetch_range(a.kind + nx.i0, (size_t)(nx.i1 - nx.i0), rtid, nth);
-      prefetch_range(a.src + nx.i0, (size_t)(nx.i1 - nx.i0) * sizeof(ReplaySrc), rtid, nth);
-      prefetch_range(a.rep + nx.t0, (size_t)(nx.t1 - nx.t0) * 4, rtid, nth);
-    }
-    if (bl.t1 == bl.t0) continue;
+    const ReplayRange bl = cur;
+    // ---- issue the loads of the next block's records (consumed after this block's commit)
+    const bool have_next = bi + 1 < a.n_blocks;
+    const bool stage_next = have_next && fits(nxt);
+    unsigned long long v0 = 0, v1 = 0;
+    bool h0 = false, h1 = false;
+    if (stage_next) { h0 = load_word(nxt, tid, v0); h1 = load_word(nxt, tid + nth, v1); }
+    ReplayRange nn = nxt;
+    if (bi + 2 < a.n_blocks) nn = a.ranges[bi + 2];
+    const bool staged = fits(bl);
+    const ReplayTxInfo* p_info = staged ? (const ReplayTxInfo*)stage[bi & 1] - bl.t0 : a.info;
+    const ReplaySrc* p_src = staged ? (const ReplaySrc*)(stage[bi & 1] + 2 * (size_t)(bl.t1 - bl.t0)) - bl.i0 : a.src;
     const bool verify_only = (bl.flags & KGV_REPLAY_VERIFY_ONLY) != 0;
     // ---- decide: every transaction reads the flags of its inputs (state as of the previous block)
+    bool acc_first = false;  // the verdict of this thread's first transaction stays in a register (blocks beyond 1024 transactions re-read the others)
     for (uint32_t ti = bl.t0 + tid; ti < bl.t1; ti += nth) {
-      const ReplayTxInfo o = a.info[ti];
+      const ReplayTxInfo o = p_info[ti];
       uint8_t st = KGV_TX_OK;
-      uint32_t fail = 0;
       bool acc;
       if (o.bits & 1) {
         st = KGV_TX_SKIPPED_COINBASE;
         acc = (ti == bl.t0) && (bl.flags & KGV_REPLAY_ACCEPT_COINBASE);
       } else {
         for (uint32_t i = 0; i < o.n_inputs; i++) {
-          const uint32_t gi = o.first_input + i;
-          const uint8_t kd = a.kind[gi];
-          const ReplaySrc sr = a.src[gi];
+          const ReplaySrc sr = p_src[o.first_input + i];
+          const uint32_t kd = rs_kind(sr), fl = sr.flag & RS_FLAG_MASK;
           bool ex = false;
-          if (kd == RS_TABLE) ex = !bm_get(spent_in, sr.flag);
-          else if (kd == RS_WINDOW) ex = bm_get(accepted, sr.src_tx) && !bm_get(spent_out, sr.flag);
+          if (kd == RS_TABLE) ex = !bm_get(spent_in, fl);
+          else if (kd == RS_WINDOW) ex = bm_get(accepted, sr.src_tx) && !bm_get(spent_out, fl);
           if (!ex) { st = KGV_TX_MISSING_OUTPOINTS; break; }
         }
-        if (st == KGV_TX_OK && (o.bits & 2)) {  // rare: coinbase maturity (tx_validation_in_utxo_context.rs:75-91) needs the entries' DAA scores
+        if (st == KGV_TX_OK && (o.bits & 2)) {  // rare: coinbase maturity (tx_validation_in_utxo_context.rs:75-91) on a window-created entry
           for (uint32_t i = 0; i < o.n_inputs; i++) {
             const uint32_t gi = o.first_input + i;
             const DevEntry& e = a.dent[gi];
-            const uint64_t daa = a.kind[gi] == RS_TABLE ? e.block_daa_score : a.acc_pov[a.src[gi].src_tx];
-            if (e.is_coinbase && daa + a.coinbase_maturity > bl.pov) { st = KGV_TX_IMMATURE_COINBASE; fail = i; break; }
+            const ReplaySrc sr = p_src[gi];
+            const uint64_t daa = rs_kind(sr) == RS_TABLE ? e.block_daa_score : a.acc_pov[sr.src_tx];
+            if (e.is_coinbase && daa + a.coinbase_maturity > bl.pov) { st = KGV_TX_IMMATURE_COINBASE; a.w_fail[ti] = i; break; }
           }
         }
         if (st == KGV_TX_OK) st = o.static_status;
@@ -584,7 +629,8 @@ __global__ void __launch_bounds__(1024, 1) k_replay_walk(WalkArgs a) {
             const uint32_t gi = o.first_input + i;
             const uint64_t seq = a.inputs[gi].sequence;
             if (seq & (1ull << 63)) continue;
-            const uint64_t daa = a.kind[gi] == RS_TABLE ? a.dent[gi].block_daa_score : a.acc_pov[a.src[gi].src_tx];
+            const ReplaySrc sr = p_src[gi];
+            const uint64_t daa = rs_kind(sr) == RS_TABLE ? a.dent[gi].block_daa_score : a.acc_pov[sr.src_tx];
             const long long lock = (long long)daa + (long long)(seq & 0xFFFFFFFFull) - 1;
             if (lock >= (long long)bl.pov) { st = KGV_TX_SEQUENCE_LOCK; break; }
           }
@@ -593,39 +639,47 @@ __global__ void __launch_bounds__(1024, 1) k_replay_walk(WalkArgs a) {
       }
       if (verify_only) acc = false;
       a.w_status[ti] = st;
-      a.w_fail[ti] = fail;
       a.accept[ti] = acc ? 1 : 0;
-      if (acc && !(o.bits & 1)) atomicAdd(&s_acc, 1ull);
+      if (ti == bl.t0 + tid) acc_first = acc;
+      if (acc && !(o.bits & 1)) n_acc++;
     }
     __syncthreads();
+    RW_TICK(0);
     // ---- commit: accepted transactions spend their inputs and become visible to later blocks (UtxoDiff::add_transaction, utxo_diff.rs:233-247)
     if (!verify_only) {
       for (uint32_t ti = bl.t0 + tid; ti < bl.t1; ti += nth) {
-        if (!a.accept[ti]) continue;
-        const ReplayTxInfo o = a.info[ti];
+        if (ti == bl.t0 + tid ? !acc_first : !a.accept[ti]) continue;  // (written by this very thread above)
+        const ReplayTxInfo o = p_info[ti];
         for (uint32_t i = 0; i < o.n_inputs; i++) {
-          const uint32_t gi = o.first_input + i;
-          if (a.kind[gi] == RS_TABLE) bm_set(spent_in, a.src[gi].flag);
-          else bm_set(spent_out, a.src[gi].flag);
+          const ReplaySrc sr = p_src[o.first_input + i];
+          if (rs_kind(sr) == RS_TABLE) bm_set(spent_in, sr.flag & RS_FLAG_MASK);
+          else bm_set(spent_out, sr.flag & RS_FLAG_MASK);
         }
-        const uint32_t r = a.rep[ti];
-        bm_set(accepted, r);
-        a.acc_pov[r] = bl.pov;
+        bm_set(accepted, o.rep);
+        a.acc_pov[o.rep] = bl.pov;
       }
-      __syncthreads();
     }
+    RW_TICK(1);
+    if (h0) stage[(bi + 1) & 1][tid] = v0;
+    if (h1) stage[(bi + 1) & 1][tid + nth] = v1;
+    cur = nxt; nxt = nn;
+    __syncthreads();
+    RW_TICK(2);
   }
-  __syncthreads();
   if (a.use_smem)
     for (uint32_t w = tid; w < a.words_in + a.words_out + a.words_tx; w += nth) {
       uint32_t* dst = w < a.words_in ? a.bm_spent_in + w : (w < a.words_in + a.words_out ? a.bm_spent_out + (w - a.words_in) : a.bm_accepted + (w - a.words_in - a.words_out));
       *dst = spent_in[w];
     }
+  for (int off = 16; off; off >>= 1) n_acc += __shfl_down_sync(0xFFFFFFFFu, n_acc, off);
+  if ((tid & 31) == 0 && n_acc) atomicAdd(&s_acc, n_acc);
+  __syncthreads();
   if (tid == 0) a.stats[0] = s_acc;
+  if (a.timers && tid == 0) for (int q = 0; q < 3; q++) a.timers[q] = (unsigned long long)tk[q];
 }
 
 // spent entries: captured for the MuHash consumers (entry as it was when spent), then erased from the table
-__global__ void k_replay_finish_inputs(TableView t, BatchView b, size_t n_inputs, const uint32_t* __restrict__ itx, const uint8_t* __restrict__ accept, const uint8_t* __restrict__ kind,
+__global__ void k_replay_finish_inputs(TableView t, BatchView b, size_t n_inputs, const uint32_t* __restrict__ itx, const uint8_t* __restrict__ accept,
                                        UtxoSlot* const* __restrict__ slot, const ReplaySrc* __restrict__ src, const unsigned long long* __restrict__ acc_pov, DevEntry* __restrict__ dent,
                                        uint8_t* __restrict__ spent_scripts) {
   __shared__ int s_live, s_tomb;
@@ -634,7 +688,8 @@ __global__ void k_replay_finish_inputs(TableView t, BatchView b, size_t n_inputs
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n_inputs && accept[itx[i]]) {
   DevEntry d = dent[i];
-  if (kind[i] == RS_TABLE) {
+  const uint32_t kd = rs_kind(src[i]);
+  if (kd == RS_TABLE) {
     UtxoSlot* s = slot[i];
     if (d.script_len <= INLINE_SCRIPT) {  // the slot is about to be tombstoned (and may be reused): keep the script bytes
       uint32_t* dst = (uint32_t*)(spent_scripts + 72 * i);
@@ -647,7 +702,7 @@ __global__ void k_replay_finish_inputs(TableView t, BatchView b, size_t n_inputs
     uint32_t k[9];
     input_key(k, b.inputs[i]);
     table_erase_found(t, k, s, s >= t.slots && s <= t.slots + t.mask, &s_live, &s_tomb);
-  } else if (kind[i] == RS_WINDOW) {
+  } else if (kd == RS_WINDOW) {
     d.block_daa_score = acc_pov[src[i].src_tx];  // the entry existed with the accepting block's DAA score (utxo_diff.rs:240-245)
     dent[i] = d;
   }
@@ -659,7 +714,7 @@ __global__ void k_replay_finish_inputs(TableView t, BatchView b, size_t n_inputs
   }
 }
 // outputs of accepted transactions that nobody spent inside the window
-__global__ void k_replay_finish_outputs(TableView t, BatchView b, size_t n_outputs, const uint32_t* __restrict__ otx, const uint8_t* __restrict__ accept, const uint32_t* __restrict__ rep,
+__global__ void k_replay_finish_outputs(TableView t, BatchView b, size_t n_outputs, const uint32_t* __restrict__ otx, const uint8_t* __restrict__ accept,
                                         const uint32_t* __restrict__ bm_spent_out, const uint64_t* __restrict__ ids, const unsigned long long* __restrict__ acc_pov,
                                         const ReplayTxInfo* __restrict__ info) {
   __shared__ int s_live, s_tomb;
@@ -668,7 +723,7 @@ __global__ void k_replay_finish_outputs(TableView t, BatchView b, size_t n_outpu
   size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (o < n_outputs) {
     const uint32_t ti = otx[o];
-    const uint32_t r = rep[ti];
+    const uint32_t r = info[ti].rep;
     // the representative instance stores the outputs (several accepted instances of one id would store the same entries)
     if (accept[ti] && (r == ti || !accept[r])) {
       const kgv_tx& tx = b.txs[ti];
@@ -690,13 +745,13 @@ __global__ void k_replay_finish_outputs(TableView t, BatchView b, size_t n_outpu
   }
 }
 __global__ void k_replay_finish_results(uint32_t n_txs, const ReplayRange* __restrict__ ranges, const uint32_t* __restrict__ tx_block, const ReplayTxInfo* __restrict__ info,
-                                        const uint8_t* __restrict__ w_status, const uint32_t* __restrict__ w_fail, const uint64_t* __restrict__ fee,
-                                        const kgv_tx_result* __restrict__ pre, kgv_tx_result* __restrict__ res) {
+                                        const uint8_t* __restrict__ w_status, const uint32_t* __restrict__ w_fail, const uint32_t* __restrict__ sfail,
+                                        const uint64_t* __restrict__ fee, const kgv_tx_result* __restrict__ pre, kgv_tx_result* __restrict__ res) {
   uint32_t ti = blockIdx.x * blockDim.x + threadIdx.x;
   if (ti >= n_txs) return;
   kgv_tx_result r;
   r.fee = 0; r.fail_input = 0; r.status = w_status[ti]; r.script_err = 0; r.pad_[0] = r.pad_[1] = 0;
-  if (r.status == KGV_TX_IMMATURE_COINBASE) r.fail_input = w_fail[ti];
+  if (r.status == KGV_TX_IMMATURE_COINBASE) r.fail_input = (info[ti].bits & 2) ? w_fail[ti] : sfail[ti];
   const uint8_t st = r.status;
   // the fee is known once the amounts passed (tx_context_rules sets it before the mass / sequence-lock rules)
   if (st == KGV_TX_OK || st == KGV_TX_MASS_INCOMPUTABLE || st == KGV_TX_WRONG_MASS || st == KGV_TX_SEQUENCE_LOCK) r.fee = fee[ti];
@@ -718,6 +773,7 @@ extern "C" int kgv_replay_window(kgv_ctx* ctx, kgv_utxo_table* table, const kgv_
   if (stats) { stats->n_accepted = 0; stats->n_sig_checks = 0; stats->n_host_vm = 0; stats->pre_check_ms = 0; stats->in_order_ms = 0; }
   if (batch->n_txs == 0 || n_blocks == 0) return KGV_OK;
   if (n_blocks > 0xFFFFFFFFull) { ctx->err = "too many blocks"; return KGV_ERR_ARG; }
+  if (batch->n_inputs > RS_FLAG_MASK || batch->n_outputs > RS_FLAG_MASK) { ctx->err = "a replay window holds at most 2^30 - 1 inputs / outputs"; return KGV_ERR_LIMIT; }
   // the blocks must tile the batch in order (block b = transactions [first_tx, first_tx + n_txs))
   {
     uint64_t at = 0;
@@ -754,10 +810,10 @@ extern "C" int kgv_replay_window(kgv_ctx* ctx, kgv_utxo_table* table, const kgv_
   uint64_t sm_cap = 1024;
   while (sm_cap < 2 * ni) sm_cap <<= 1;
   const uint32_t words_in = (uint32_t)((ni + 31) / 32), words_out = (uint32_t)((no + 31) / 32), words_tx = (uint32_t)((nt + 31) / 32);
-  size_t o_knd = al256(o_cnt + 64);
-  size_t o_src = al256(o_knd + ni);
-  size_t o_rep = al256(o_src + ni * sizeof(ReplaySrc));
-  size_t o_inf = al256(o_rep + nt * 4);
+  size_t o_sib = al256(o_cnt + 64);
+  size_t o_src = al256(o_sib + nt);
+  size_t o_sfl = al256(o_src + ni * sizeof(ReplaySrc));
+  size_t o_inf = al256(o_sfl + nt * 4);
   size_t o_fee = al256(o_inf + nt * sizeof(ReplayTxInfo));
   size_t o_wst = al256(o_fee + nt * 8);
   size_t o_wfl = al256(o_wst + nt);
@@ -765,7 +821,7 @@ extern "C" int kgv_replay_window(kgv_ctx* ctx, kgv_utxo_table* table, const kgv_
   size_t o_bm = al256(o_apv + nt * 8);
   size_t o_smk = al256(o_bm + ((size_t)words_in + words_out + words_tx) * 4);
   size_t o_smv = al256(o_smk + sm_cap * 8);
-  size_t total = legacy_walk ? al256(o_cnt + 64) : al256(o_smv + sm_cap * 4);
+  size_t total = legacy_walk ? al256(o_sib + nt) : al256(o_smv + sm_cap * 4);
   rc = kgv_reserve(ctx, &ctx->d_replay, &ctx->d_replay_cap, total);
   if (rc) return rc;
   uint8_t* R = ctx->d_replay;
@@ -782,13 +838,24 @@ extern "C" int kgv_replay_window(kgv_ctx* ctx, kgv_utxo_table* table, const kgv_
     for (cudaEvent_t& e : ctx->ev_time) if (!e) CK(cudaEventCreate(&e));
     CK(cudaEventRecord(ctx->ev_time[0], st));
   }
+  // KGV_DEBUG: device time between marks, printed at the end of the call
+  std::vector<std::pair<const char*, cudaEvent_t>> marks;
+  auto mark = [&](const char* name) {
+    if (!kgv_debug_on()) return;
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, st);
+    marks.push_back({name, e});
+  };
+  mark("start");
   CK(cudaMemcpyAsync(dblk, blocks, n_blocks * sizeof(kgv_replay_block), cudaMemcpyHostToDevice, st));
   CK(cudaMemsetAsync(wm, 0, wm_cap * 4, st));
   CK(cudaMemsetAsync(cnt, 0, 64, st));
   BatchView v0{d.txs, d.inputs, d.outputs, nullptr, d.bytes};
   k_tx_ids_dev<<<nblk(nt, 128), 128, 0, st>>>(v0, (uint32_t)nt, ids);
   CK(cudaGetLastError());
-  k_wm_insert<<<nblk(nt, 128), 128, 0, st>>>(ids, (uint32_t)nt, wm, wm_cap - 1);
+  CK(cudaMemsetAsync(R + o_sib, 0, nt, st));
+  k_wm_insert<<<nblk(nt, 128), 128, 0, st>>>(ids, (uint32_t)nt, wm, wm_cap - 1, R + o_sib);
   CK(cudaGetLastError());
   k_input_tx_index<<<nblk(nt, 128), 128, 0, st>>>(d.txs, (uint32_t)nt, itx);
   CK(cudaGetLastError());
@@ -801,7 +868,6 @@ extern "C" int kgv_replay_window(kgv_ctx* ctx, kgv_utxo_table* table, const kgv_
   ctx->launches += 6;
   // ---- pre-check of every script of the window
   BatchView v{d.txs, d.inputs, d.outputs, dent, d.bytes};
-  uint8_t* kind = R + o_knd;
   ReplaySrc* src = (ReplaySrc*)(R + o_src);
   UtxoSlot** slotp = (UtxoSlot**)(R + o_slp);
   auto find_sources = [&]() -> int {
@@ -812,13 +878,15 @@ extern "C" int kgv_replay_window(kgv_ctx* ctx, kgv_utxo_table* table, const kgv_
       ctx->launches++;
       return KGV_OK;
     }
-    k_replay_sources<<<nblk(ni, 128), 128, 0, st>>>(view_of(table), v, ni, ids, wm, wm_cap - 1, dent, kind, slotp, src);
+    k_replay_sources<<<nblk(ni, 128), 128, 0, st>>>(view_of(table), v, ni, ids, wm, wm_cap - 1, txb, (const ReplayRange*)(R + o_rng), dent, slotp, src);
     CK(cudaGetLastError());
     ctx->launches++;
     return KGV_OK;
   };
+  mark("ids+window map+ranges");
   rc = find_sources();
   if (rc) return rc;
+  mark("sources");
   k_replay_pre_status<<<nblk(nt, 128), 128, 0, st>>>(v, (uint32_t)nt, dblk, txb, pre);
   CK(cudaGetLastError());
   ctx->launches++;
@@ -826,6 +894,7 @@ extern "C" int kgv_replay_window(kgv_ctx* ctx, kgv_utxo_table* table, const kgv_
   uint64_t n_items = 0;
   rc = kgv_scripts_phase(ctx, v, nt, ni, itx, pre, &n_items);
   if (rc) return rc;
+  mark("scripts phase");
   k_count_status<<<nblk(nt, 256), 256, 0, st>>>(pre, (uint32_t)nt, KGV_TX_NEEDS_HOST_VM, cnt + 1);
   CK(cudaGetLastError());
   ctx->launches++;
@@ -846,11 +915,12 @@ extern "C" int kgv_replay_window(kgv_ctx* ctx, kgv_utxo_table* table, const kgv_
       if (rc) return rc;
     }
   }
+  mark("host vm");
   if (stats) CK(cudaEventRecord(ctx->ev_time[1], st));
   if (!legacy_walk) {
     // ---- the resolving walk
     const ReplayRange* ranges = (const ReplayRange*)(R + o_rng);
-    uint32_t* rep = (uint32_t*)(R + o_rep);
+    uint32_t* sfail = (uint32_t*)(R + o_sfl);
     ReplayTxInfo* info = (ReplayTxInfo*)(R + o_inf);
     uint64_t* fee = (uint64_t*)(R + o_fee);
     uint8_t* wst = R + o_wst;
@@ -865,44 +935,54 @@ extern "C" int kgv_replay_window(kgv_ctx* ctx, kgv_utxo_table* table, const kgv_
     if (ni) {
       CK(cudaMemsetAsync(smk, 0, sm_cap * 8, st));
       CK(cudaMemsetAsync(smv, 0xFF, sm_cap * 4, st));
-      k_slotmap_insert<<<nblk(ni, 256), 256, 0, st>>>(kind, slotp, ni, smk, smv, sm_cap - 1);
+      k_slotmap_insert<<<nblk(ni, 256), 256, 0, st>>>(src, slotp, ni, smk, smv, sm_cap - 1);
       CK(cudaGetLastError());
-      k_slotmap_lookup<<<nblk(ni, 256), 256, 0, st>>>(kind, slotp, ni, smk, smv, sm_cap - 1, src);
+      k_slotmap_lookup<<<nblk(ni, 256), 256, 0, st>>>(slotp, ni, smk, smv, sm_cap - 1, src);
       CK(cudaGetLastError());
       ctx->launches += 2;
     }
-    k_replay_rep<<<nblk(nt, 256), 256, 0, st>>>(ids, wm, wm_cap - 1, (uint32_t)nt, rep);
+    mark("slot map");
+    k_replay_static<<<nblk(nt, 128), 128, 0, st>>>(v, (uint32_t)nt, *prm, ranges, txb, pre, src, ids, wm, wm_cap - 1, R + o_sib, info, fee, sfail);
     CK(cudaGetLastError());
-    k_replay_static<<<nblk(nt, 128), 128, 0, st>>>(v, (uint32_t)nt, *prm, ranges, txb, pre, info, fee);
-    CK(cudaGetLastError());
-    ctx->launches += 2;
+    ctx->launches++;
+    mark("static rules");
     WalkArgs w;
-    w.ranges = ranges; w.n_blocks = (uint32_t)n_blocks; w.info = info; w.kind = kind; w.src = src; w.rep = rep; w.dent = dent; w.inputs = d.inputs;
+    w.ranges = ranges; w.n_blocks = (uint32_t)n_blocks; w.info = info; w.src = src; w.dent = dent; w.inputs = d.inputs;
     w.acc_pov = apov; w.w_status = wst; w.w_fail = wfl; w.accept = dacc;
     w.bm_spent_in = bm; w.bm_spent_out = bm + words_in; w.bm_accepted = bm + words_in + words_out;
     w.words_in = words_in; w.words_out = words_out; w.words_tx = words_tx;
     w.coinbase_maturity = prm->coinbase_maturity; w.stats = cnt;
-    const size_t walk_smem = bm_words * 4;
+    w.timers = kgv_debug_on() ? cnt + 2 : nullptr;
+    const size_t stage_bytes = 2 * (size_t)RW_WORDS * 8, walk_smem = stage_bytes + bm_words * 4;
     w.use_smem = walk_smem <= 200 * 1024;
     static bool walk_set = false;
     if (!walk_set) { CK(cudaFuncSetAttribute(k_replay_walk, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); walk_set = true; }
-    k_replay_walk<<<1, 1024, w.use_smem ? walk_smem : 0, st>>>(w);
+    k_replay_walk<<<1, 1024, w.use_smem ? walk_smem : stage_bytes, st>>>(w);
     CK(cudaGetLastError());
     ctx->launches++;
+    mark("walk");
     const TableView tv = view_of(table);
     if (ni) {
-      k_replay_finish_inputs<<<nblk(ni, 128), 128, 0, st>>>(tv, v, ni, itx, dacc, kind, slotp, src, apov, dent, R + o_scr);
+      k_replay_finish_inputs<<<nblk(ni, 128), 128, 0, st>>>(tv, v, ni, itx, dacc, slotp, src, apov, dent, R + o_scr);
       CK(cudaGetLastError());
       ctx->launches++;
     }
     if (no) {
-      k_replay_finish_outputs<<<nblk(no, 128), 128, 0, st>>>(tv, v, no, otx, dacc, rep, bm + words_in, ids, apov, info);
+      k_replay_finish_outputs<<<nblk(no, 128), 128, 0, st>>>(tv, v, no, otx, dacc, bm + words_in, ids, apov, info);
       CK(cudaGetLastError());
       ctx->launches++;
     }
-    k_replay_finish_results<<<nblk(nt, 256), 256, 0, st>>>((uint32_t)nt, ranges, txb, info, wst, wfl, fee, pre, res);
+    mark("finish inputs+outputs");
+    k_replay_finish_results<<<nblk(nt, 256), 256, 0, st>>>((uint32_t)nt, ranges, txb, info, wst, wfl, sfail, fee, pre, res);
     CK(cudaGetLastError());
     ctx->launches++;
+    mark("finish results");
+    if (kgv_debug_on()) {
+      unsigned long long tk[3];
+      CK(cudaMemcpyAsync(tk, cnt + 2, sizeof tk, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      fprintf(stderr, "[kgv] walk cycles per block: decide %.0f  commit %.0f  refill %.0f\n", (double)tk[0] / n_blocks, (double)tk[1] / n_blocks, (double)tk[2] / n_blocks);
+    }
     if (stats) CK(cudaEventRecord(ctx->ev_time[2], st));
   } else {
   // ---- in-order pass over the table itself (KGV_REPLAY_WALK=table: the round-2a form, kept as a cross-check of the resolving walk)
@@ -932,6 +1012,17 @@ extern "C" int kgv_replay_window(kgv_ctx* ctx, kgv_utxo_table* table, const kgv_
   }
   }
   STAGE("replay in-order");
+  if (!marks.empty()) {
+    cudaStreamSynchronize(st);
+    fprintf(stderr, "[kgv] replay window, device ms:");
+    for (size_t i = 1; i < marks.size(); i++) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, marks[i - 1].second, marks[i].second);
+      fprintf(stderr, "  %s %.3f", marks[i].first, ms);
+    }
+    fprintf(stderr, "\n");
+    for (auto& m : marks) cudaEventDestroy(m.second);
+  }
   const bool dev_out = kgv_ptr_is_device(results);
   CK(cudaMemcpyAsync(results, res, nt * sizeof(kgv_tx_result), dev_out ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
   if (accept) CK(cudaMemcpyAsync(accept, dacc, nt, kgv_ptr_is_device(accept) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));

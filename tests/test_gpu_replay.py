@@ -183,6 +183,79 @@ def test_replay_block_flags_follow_the_reference_semantics(gpu_ctx, oracle):
     r.close(); ost.close(); g.close()
 
 
+def test_window_with_sibling_duplicates_double_spends_and_rejected_creators(gpu_ctx, oracle):
+    """What a DAG window can hold and a chain cannot, against the oracle's block-by-block composed view: the SAME transaction in several sibling
+    blocks (only its first instance is accepted, the others find their inputs spent), a different transaction double-spending an outpoint an
+    earlier block of the window consumed, a transaction placed BEFORE the block that creates what it spends, and creators whose signature is
+    broken after their descendants were built (txids do not cover signature scripts: the whole subtree must come out MissingTxOutpoints).
+    One window, so every dependency is resolved inside kgv_replay_window's walk; then the window is replayed again in 7-block pieces."""
+    import copy
+    from rusty_kaspa_b200.simgen import tx_id
+    dag = SimDag(seed=77, n_keys=64, n_nonces=128, mix=(0.6, 0.2, 0.1, 0.1), frac_invalid=0.0, coinbase_maturity=2, coinbase_outputs=6)
+    rng = np.random.default_rng(3)
+    blocks, n_respent = [], 0
+    for bi in range(42):
+        before = {(u["txid"], u["index"]): u for u in dag.utxos}
+        txs, pov = dag.make_block(14)
+        blocks.append((list(txs), pov))
+        if bi in (10, 20, 30):
+            # a double spend by a DIFFERENT transaction: the generator is handed back an outpoint this block just spent
+            left = {(u["txid"], u["index"]) for u in dag.utxos}
+            gone = [u for k, u in before.items() if k not in left]
+            cand = [u for u in gone if not u["coinbase"] and u["amount"] >= 4]
+            assert cand
+            saved, dag.utxos = dag.utxos, [cand[0]]
+            txs2, pov2 = dag.make_block(1)  # coinbase + ONE transaction, which can only pick the outpoint that is already spent
+            assert len(txs2) == 2 and (txs2[1]["inputs"][0]["txid"], txs2[1]["inputs"][0]["index"]) == (cand[0]["txid"], cand[0]["index"])
+            blocks.append((list(txs2), pov2))
+            dag.utxos = saved + dag.utxos
+            n_respent += 1
+    # sibling duplicates: copies of earlier transactions in later blocks (and one copy EARLIER than its original)
+    n_dup = 0
+    for src_b, dst_b, k in ((5, 6, 2), (5, 9, 2), (12, 13, 4), (17, 25, 1), (31, 28, 3), (34, 35, 5), (34, 36, 5)):
+        blocks[dst_b][0].append(copy.deepcopy(blocks[src_b][0][k]))
+        n_dup += 1
+    # rejected creators: break the signature of a transaction some later transaction depends on
+    ids = {}
+    for bi, (txs, _) in enumerate(blocks):
+        for ti, t in enumerate(txs):
+            ids.setdefault(tx_id(t), (bi, ti))
+    broken = 0
+    for bi in range(len(blocks) - 1, 0, -1):
+        for t in blocks[bi][0][1:]:
+            src = ids.get(t["inputs"][0]["txid"])
+            if src and src[1] > 0 and broken < 5 and rng.random() < 0.5:
+                c = blocks[src[0]][0][src[1]]
+                ss = bytearray(c["inputs"][0]["sigscript"])
+                if len(ss) > 20 and ss[10] == c["inputs"][0]["sigscript"][10]:
+                    ss[10] ^= 0x40
+                    c["inputs"][0]["sigscript"] = bytes(ss)
+                    broken += 1
+    assert broken >= 3 and n_dup == 7 and n_respent == 3
+    prm = Params(coinbase_maturity=2, storage_mass_parameter=dag.C)
+    op = oracle_tx.params(coinbase_maturity=2, storage_mass_parameter=dag.C)
+    ost = oracle_tx.State(oracle)
+    exp = []
+    for txs, pov in blocks:
+        b = build_batch(txs)
+        r = ost.validate(b, pov, 0, op, threads=2)
+        exp.append(r)
+        ost.accept(b, ((r["status"] == 0) | (r["status"] == 12)).astype(np.uint8), pov)
+        ost.commit()
+    statuses = np.concatenate([e["status"] for e in exp])
+    assert (statuses == 1).sum() >= n_dup + broken and (statuses == 9).sum() + (statuses == 10).sum() >= 3, np.bincount(statuses)
+    for piece in (len(blocks), 7):
+        r2 = DagReplayer(gpu_ctx, prm, 1 << 14)
+        got = []
+        for w in range(0, len(blocks), piece):
+            got += r2.replay_windowed(blocks[w:w + piece])
+        for bi, (e, c) in enumerate(zip(exp, got)):
+            assert (c["status"] == e["status"]).all() and (c["script_err"] == e["script_err"]).all(), (piece, bi, c["status"], e["status"])
+        assert r2.us.count() == ost.count() and r2.us.digest() == ost.digest()
+        r2.close()
+    ost.close()
+
+
 @pytest.mark.parametrize("fixture", ["simpa_goref_1060.json.gz", "simpa_goref_pruning_5000.json.gz"])
 def test_whole_virtual_chain_as_one_replay_window_reproduces_every_header_commitment(gpu_ctx, fixture):
     """The reference's simpa DAG fixtures, their whole virtual chain as ONE kgv_replay_window call: per chain block the merged blocks in consensus
