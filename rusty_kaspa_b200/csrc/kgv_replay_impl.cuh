@@ -110,16 +110,18 @@ __global__ void k_replay_pre_status(BatchView b, uint32_t n_txs, const kgv_repla
 // the in-order pass: ONE CTA, blocks in sequence
 // ---------------------------------------------------------------------------------------------
 // per-block ranges, computed in parallel before the walk so that the in-order kernel never chases tx records to find them
-struct ReplayRange {
+struct __align__(16) ReplayRange {  // 48 bytes: a whole number of 16-byte units (the walk fetches these with bulk copies)
   uint32_t t0, t1, i0, i1, o0, o1, flags, pad_;
   uint64_t pov;
+  uint64_t pad2_;
 };
+static_assert(sizeof(ReplayRange) == 48, "ReplayRange layout");
 __global__ void k_replay_ranges(const kgv_replay_block* __restrict__ blocks, uint32_t n_blocks, const kgv_tx* __restrict__ txs, ReplayRange* __restrict__ out) {
   uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= n_blocks) return;
   kgv_replay_block bl = blocks[b];
   ReplayRange r;
-  r.t0 = bl.first_tx; r.t1 = bl.first_tx + bl.n_txs; r.flags = bl.flags; r.pad_ = 0; r.pov = bl.pov_daa_score;
+  r.t0 = bl.first_tx; r.t1 = bl.first_tx + bl.n_txs; r.flags = bl.flags; r.pad_ = 0; r.pov = bl.pov_daa_score; r.pad2_ = 0;
   r.i0 = r.i1 = r.o0 = r.o1 = 0;
   if (bl.n_txs) {
     const kgv_tx& tf = txs[r.t0];
@@ -383,7 +385,7 @@ struct __align__(16) ReplayTxInfo {   // per transaction (16 bytes)
   uint32_t n_inputs;
   uint32_t rep;           // representative instance of this transaction id inside the window (itself unless a DAG sibling carries the same transaction)
   uint8_t static_status;  // KGV_TX_OK or the first failing rule that does not depend on the walk
-  uint8_t bits;           // 1: coinbase (position 0 / subnetwork)  2: DAA-score rules depend on the walk (a window-created entry is involved)  4: scripts ok (pre-check)
+  uint8_t bits;           // 1: coinbase (position 0 / subnetwork)  2: DAA-score rules depend on the walk  4: scripts ok (pre-check)  8: sibling blocks carry this transaction too
   uint16_t pad_;
 };
 __device__ __forceinline__ uint32_t rs_kind(const ReplaySrc& r) { return r.flag >> 30; }
@@ -462,6 +464,7 @@ __global__ void k_replay_static(BatchView b, uint32_t n_txs, kgv_params prm, con
   {
     int j = wm_find(ids, wm, wm_mask, ids + 4 * (size_t)ti);
     o.rep = j >= 0 ? (uint32_t)j : ti;
+    if (has_sibling[o.rep]) o.bits |= 8;
   }
   const ReplayRange r = ranges[tx_block[ti]];
   const bool cb = ti == r.t0 || tx_is_coinbase(t);
@@ -521,12 +524,15 @@ __global__ void k_replay_static(BatchView b, uint32_t n_txs, kgv_params prm, con
   sfail[ti] = fail;
 }
 
-// The walk.  Each block's records (16 bytes per transaction, 8 per input) are STAGED in shared memory one block ahead: at the top of iteration
-// b every thread issues its share of the loads for block b+1 into registers, block b is decided and committed out of shared memory, then the
-// registers are stored for the next iteration - the global-memory latency hides behind the current block's two barriers.
+// The walk.  One CTA of 256 threads (a 10-BPS block carries ~150 transactions; every extra warp only adds issue pressure to the one SM).  Each
+// block's records (16 bytes per transaction, 8 per input) and the range record two blocks ahead are fetched into shared memory by the copy
+// engine - cp.async.bulk issued by thread 0, completion on an mbarrier - ONE block ahead of their use: no thread spends instructions or
+// registers on staging, and the global-memory latency hides behind the current block's decide / commit.
+#define RW_THREADS 256u
 #define RW_MAXT 512u
 #define RW_MAXI 1024u
-#define RW_WORDS ((RW_MAXT * 16u + RW_MAXI * 8u) / 8u)  // 8-byte words per staging buffer (2 per thread)
+#define RW_STAGE_BYTES (RW_MAXT * 16u + (RW_MAXI + 2u) * 8u)  // one staging buffer (inputs are copied from an even index: one entry of slack either side)
+#define RW_FIXED_BYTES (2u * RW_STAGE_BYTES + 3u * 48u + 16u) // two staging buffers, a ring of three range records, two mbarriers
 struct WalkArgs {
   const ReplayRange* ranges;
   uint32_t n_blocks;
@@ -535,147 +541,213 @@ struct WalkArgs {
   const DevEntry* dent;       // entries of the pre-check (DAA score / coinbase flag), rare path only
   const kgv_input* inputs;    // sequence numbers, rare path only
   volatile unsigned long long* acc_pov;  // per representative tx: pov of the block that accepted it
-  uint8_t* w_status;          // dynamic verdict per tx
-  uint32_t* w_fail;           // failing input for a dynamic ImmatureCoinbaseSpend
-  uint8_t* accept;
+  uint8_t* w_status;          // verdict of the transactions whose DAA-score rules the walk decides (bits & 2)
+  uint32_t* w_fail;           // failing input for such an ImmatureCoinbaseSpend
+  uint8_t* accept;            // scratch for blocks beyond 256 transactions
   uint32_t* bm_spent_in;      // global copies of the bitmaps (written at the end; used directly when they do not fit shared memory)
   uint32_t* bm_spent_out;
-  uint32_t* bm_accepted;
+  uint32_t* bm_accepted;      // per representative transaction
+  uint32_t* bm_exists;        // per transaction: every input existed at its block's position
   uint32_t words_in, words_out, words_tx;
   uint64_t coinbase_maturity;
   unsigned long long* stats;
-  unsigned long long* timers;
   int use_smem;
 };
 __device__ __forceinline__ bool bm_get(const uint32_t* bm, uint32_t i) { return (*(const volatile uint32_t*)&bm[i >> 5] >> (i & 31)) & 1u; }
 __device__ __forceinline__ void bm_set(uint32_t* bm, uint32_t i) { atomicOr(&bm[i >> 5], 1u << (i & 31)); }
 
-__global__ void __launch_bounds__(1024, 1) k_replay_walk(WalkArgs a) {
-  extern __shared__ __align__(16) uint8_t smem_raw[];
-  const uint32_t tid = threadIdx.x, nth = blockDim.x;
-  unsigned long long* stage[2] = {(unsigned long long*)smem_raw, (unsigned long long*)smem_raw + RW_WORDS};
-  uint32_t *spent_in = a.bm_spent_in, *spent_out = a.bm_spent_out, *accepted = a.bm_accepted;
-  if (a.use_smem) {
-    spent_in = (uint32_t*)(smem_raw + 2 * RW_WORDS * 8); spent_out = spent_in + a.words_in; accepted = spent_out + a.words_out;
-    for (uint32_t w = tid; w < a.words_in + a.words_out + a.words_tx; w += nth) spent_in[w] = 0;
+// decide / commit of one block.  Force-inlined into call sites whose pointer arguments have a KNOWN address space (shared staging + shared bitmaps
+// on the common path): with pointers selected at run time the compiler falls back to generic loads and to a compare-and-swap loop per atomicOr,
+// which cost 3x the whole walk (measured: 3.7 k -> cycles per block).
+__device__ __forceinline__ bool walk_decide(const WalkArgs& a, const ReplayRange& bl, const ReplayTxInfo* p_info, const ReplaySrc* p_src, const uint32_t* spent_in,
+                                            const uint32_t* spent_out, const uint32_t* accepted, uint32_t* exists, uint32_t tid, uint32_t nth, uint32_t& n_acc) {
+  const bool verify_only = (bl.flags & KGV_REPLAY_VERIFY_ONLY) != 0;
+  bool acc_first = false;  // the verdict of this thread's first transaction stays in a register (blocks beyond 256 transactions re-read the others)
+  for (uint32_t ti = bl.t0 + tid; ti < bl.t1; ti += nth) {
+    const ReplayTxInfo o = p_info[ti];
+    uint8_t st = KGV_TX_OK;
+    bool acc;
+    if (o.bits & 1) {
+      acc = (ti == bl.t0) && (bl.flags & KGV_REPLAY_ACCEPT_COINBASE);
+    } else {
+      for (uint32_t i = 0; i < o.n_inputs; i++) {
+        const ReplaySrc sr = p_src[o.first_input + i];
+        const uint32_t kd = rs_kind(sr), fl = sr.flag & RS_FLAG_MASK;
+        bool ex = false;
+        if (kd == RS_TABLE) ex = !bm_get(spent_in, fl);
+        else if (kd == RS_WINDOW) ex = bm_get(accepted, sr.src_tx) && !bm_get(spent_out, fl);
+        if (!ex) { st = KGV_TX_MISSING_OUTPOINTS; break; }
+      }
+      if (st == KGV_TX_OK && (o.bits & 2)) {  // rare: coinbase maturity (tx_validation_in_utxo_context.rs:75-91) on an entry whose creator sibling blocks share
+        for (uint32_t i = 0; i < o.n_inputs; i++) {
+          const uint32_t gi = o.first_input + i;
+          const DevEntry& e = a.dent[gi];
+          const ReplaySrc sr = p_src[gi];
+          const uint64_t daa = rs_kind(sr) == RS_TABLE ? e.block_daa_score : a.acc_pov[sr.src_tx];
+          if (e.is_coinbase && daa + a.coinbase_maturity > bl.pov) { st = KGV_TX_IMMATURE_COINBASE; a.w_fail[ti] = i; break; }
+        }
+      }
+      if (st == KGV_TX_OK) st = o.static_status;
+      if (st == KGV_TX_OK && (o.bits & 2)) {  // rare: relative sequence locks (:130-155)
+        for (uint32_t i = 0; i < o.n_inputs; i++) {
+          const uint32_t gi = o.first_input + i;
+          const uint64_t seq = a.inputs[gi].sequence;
+          if (seq & (1ull << 63)) continue;
+          const ReplaySrc sr = p_src[gi];
+          const uint64_t daa = rs_kind(sr) == RS_TABLE ? a.dent[gi].block_daa_score : a.acc_pov[sr.src_tx];
+          const long long lock = (long long)daa + (long long)(seq & 0xFFFFFFFFull) - 1;
+          if (lock >= (long long)bl.pov) { st = KGV_TX_SEQUENCE_LOCK; break; }
+        }
+      }
+      if (st != KGV_TX_MISSING_OUTPOINTS) bm_set(exists, ti);
+      if (o.bits & 2) a.w_status[ti] = st;  // rare
+      acc = st == KGV_TX_OK && ((bl.flags & KGV_REPLAY_SKIP_SCRIPTS) || (o.bits & 4));
+    }
+    if (verify_only) acc = false;
+    if (ti == bl.t0 + tid) acc_first = acc;
+    else a.accept[ti] = acc ? 1 : 0;        // blocks beyond 256 transactions only
+    if (acc && !(o.bits & 1)) n_acc++;
   }
+  return acc_first;
+}
+// accepted transactions spend their inputs and become visible to later blocks (UtxoDiff::add_transaction, utxo_diff.rs:233-247)
+__device__ __forceinline__ void walk_commit(const WalkArgs& a, const ReplayRange& bl, const ReplayTxInfo* p_info, const ReplaySrc* p_src, uint32_t* spent_in, uint32_t* spent_out,
+                                            uint32_t* accepted, uint32_t tid, uint32_t nth, bool acc_first) {
+  if (bl.flags & KGV_REPLAY_VERIFY_ONLY) return;
+  for (uint32_t ti = bl.t0 + tid; ti < bl.t1; ti += nth) {
+    if (ti == bl.t0 + tid ? !acc_first : !a.accept[ti]) continue;  // (written by this very thread in walk_decide)
+    const ReplayTxInfo o = p_info[ti];
+    for (uint32_t i = 0; i < o.n_inputs; i++) {
+      const ReplaySrc sr = p_src[o.first_input + i];
+      if (rs_kind(sr) == RS_TABLE) bm_set(spent_in, sr.flag & RS_FLAG_MASK);
+      else bm_set(spent_out, sr.flag & RS_FLAG_MASK);
+    }
+    bm_set(accepted, o.rep);
+    if (o.bits & 8) a.acc_pov[o.rep] = bl.pov;  // rare: which sibling's block accepted it is only known here
+  }
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count)); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {  // 16-byte aligned addresses and size
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+
+// BM_SHARED: the four bitmaps live in shared memory (windows up to ~1.4 M flags); otherwise they are the global copies.
+template <bool BM_SHARED>
+__global__ void __launch_bounds__(RW_THREADS, 1) k_replay_walk(WalkArgs a) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  const uint32_t tid = threadIdx.x, nth = blockDim.x;
+  uint8_t* const stage0 = smem_raw;
+  uint8_t* const stage1 = smem_raw + RW_STAGE_BYTES;
+  ReplayRange* const ring = (ReplayRange*)(smem_raw + 2 * RW_STAGE_BYTES);
+  uint64_t* const mbar = (uint64_t*)(smem_raw + 2 * RW_STAGE_BYTES + 3 * 48);
+  // The loop below issues NO global store on its common path: its whole output is the four bitmaps, written out once at the end;
+  // k_replay_verdicts turns them into per-transaction verdicts.
+  const uint32_t bm_words = a.words_in + a.words_out + 2 * a.words_tx;
+  uint32_t* const sm_bm = (uint32_t*)(smem_raw + RW_FIXED_BYTES);
+  if (BM_SHARED)
+    for (uint32_t w = tid; w < bm_words; w += nth) sm_bm[w] = 0;
   __shared__ unsigned int s_acc;
-  if (tid == 0) s_acc = 0;
   uint32_t n_acc = 0;  // per thread, reduced once at the end
-  const unsigned long long* info64 = (const unsigned long long*)a.info;
-  const unsigned long long* src64 = (const unsigned long long*)a.src;
   auto fits = [](const ReplayRange& r) { return r.t1 - r.t0 <= RW_MAXT && r.i1 - r.i0 <= RW_MAXI; };
-  // word w of a block's staging image: info words first, then the inputs' source words
-  auto load_word = [&](const ReplayRange& r, uint32_t w, unsigned long long& v) -> bool {
-    const uint32_t n_info = 2 * (r.t1 - r.t0), n_src = r.i1 - r.i0;
-    if (w < n_info) { v = __ldcg(info64 + 2 * (size_t)r.t0 + w); return true; }
-    if (w - n_info < n_src) { v = __ldcg(src64 + (size_t)r.i0 + (w - n_info)); return true; }
-    return false;
+  // copy group G(b) = { records of block b, range record of block b+1 }, completing on mbar[b & 1]; issued by thread 0 with range(b) in hand
+  auto issue_group = [&](uint32_t b, const ReplayRange& r) {
+    uint8_t* st = (b & 1) ? stage1 : stage0;
+    uint64_t* bar = &mbar[b & 1];
+    const uint32_t nt = r.t1 - r.t0, ie = r.i0 & ~1u, ni2 = (r.i1 - ie + 1u) & ~1u;
+    const bool data = fits(r) && nt;
+    const bool next = b + 1 < a.n_blocks;
+    const uint32_t bytes = (data ? nt * 16u + ni2 * 8u : 0u) + (next ? 48u : 0u);
+    mbar_expect_tx(bar, bytes);
+    if (data) {
+      bulk_g2s(st, a.info + r.t0, nt * 16u, bar);
+      if (ni2) bulk_g2s(st + RW_MAXT * 16u, a.src + ie, ni2 * 8u, bar);
+    }
+    if (next) bulk_g2s(&ring[(b + 1) % 3], a.ranges + b + 1, 48u, bar);
   };
-  ReplayRange cur = a.ranges[0], nxt = a.n_blocks > 1 ? a.ranges[1] : cur;
-  if (fits(cur)) {
-    unsigned long long v;
-    if (load_word(cur, tid, v)) stage[0][tid] = v;
-    if (load_word(cur, tid + nth, v)) stage[0][tid + nth] = v;
+  if (tid == 0) {
+    s_acc = 0;
+    mbar_init(&mbar[0], 1);
+    mbar_init(&mbar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    ring[0] = a.ranges[0];
   }
   __syncthreads();
-  long long tk[4] = {0, 0, 0, 0}, c0 = 0;
-#define RW_TICK(k) do { if (a.timers && tid == 0) { long long c1 = clock64(); tk[k] += c1 - c0; c0 = c1; } } while (0)
-  if (a.timers && tid == 0) c0 = clock64();
+  if (tid == 0) issue_group(0, ring[0]);
   for (uint32_t bi = 0; bi < a.n_blocks; bi++) {
-    const ReplayRange bl = cur;
-    // ---- issue the loads of the next block's records (consumed after this block's commit)
-    const bool have_next = bi + 1 < a.n_blocks;
-    const bool stage_next = have_next && fits(nxt);
-    unsigned long long v0 = 0, v1 = 0;
-    bool h0 = false, h1 = false;
-    if (stage_next) { h0 = load_word(nxt, tid, v0); h1 = load_word(nxt, tid + nth, v1); }
-    ReplayRange nn = nxt;
-    if (bi + 2 < a.n_blocks) nn = a.ranges[bi + 2];
+    mbar_wait(&mbar[bi & 1], (bi >> 1) & 1);  // records of this block + range of the next one have landed
+    const ReplayRange bl = ring[bi % 3];
+    if (tid == 0 && bi + 1 < a.n_blocks) issue_group(bi + 1, ring[(bi + 1) % 3]);  // its buffers were last read before the barrier that ended iteration bi-1
     const bool staged = fits(bl);
-    const ReplayTxInfo* p_info = staged ? (const ReplayTxInfo*)stage[bi & 1] - bl.t0 : a.info;
-    const ReplaySrc* p_src = staged ? (const ReplaySrc*)(stage[bi & 1] + 2 * (size_t)(bl.t1 - bl.t0)) - bl.i0 : a.src;
-    const bool verify_only = (bl.flags & KGV_REPLAY_VERIFY_ONLY) != 0;
-    // ---- decide: every transaction reads the flags of its inputs (state as of the previous block)
-    bool acc_first = false;  // the verdict of this thread's first transaction stays in a register (blocks beyond 1024 transactions re-read the others)
-    for (uint32_t ti = bl.t0 + tid; ti < bl.t1; ti += nth) {
-      const ReplayTxInfo o = p_info[ti];
-      uint8_t st = KGV_TX_OK;
-      bool acc;
-      if (o.bits & 1) {
-        st = KGV_TX_SKIPPED_COINBASE;
-        acc = (ti == bl.t0) && (bl.flags & KGV_REPLAY_ACCEPT_COINBASE);
-      } else {
-        for (uint32_t i = 0; i < o.n_inputs; i++) {
-          const ReplaySrc sr = p_src[o.first_input + i];
-          const uint32_t kd = rs_kind(sr), fl = sr.flag & RS_FLAG_MASK;
-          bool ex = false;
-          if (kd == RS_TABLE) ex = !bm_get(spent_in, fl);
-          else if (kd == RS_WINDOW) ex = bm_get(accepted, sr.src_tx) && !bm_get(spent_out, fl);
-          if (!ex) { st = KGV_TX_MISSING_OUTPOINTS; break; }
-        }
-        if (st == KGV_TX_OK && (o.bits & 2)) {  // rare: coinbase maturity (tx_validation_in_utxo_context.rs:75-91) on a window-created entry
-          for (uint32_t i = 0; i < o.n_inputs; i++) {
-            const uint32_t gi = o.first_input + i;
-            const DevEntry& e = a.dent[gi];
-            const ReplaySrc sr = p_src[gi];
-            const uint64_t daa = rs_kind(sr) == RS_TABLE ? e.block_daa_score : a.acc_pov[sr.src_tx];
-            if (e.is_coinbase && daa + a.coinbase_maturity > bl.pov) { st = KGV_TX_IMMATURE_COINBASE; a.w_fail[ti] = i; break; }
-          }
-        }
-        if (st == KGV_TX_OK) st = o.static_status;
-        if (st == KGV_TX_OK && (o.bits & 2)) {  // rare: relative sequence locks (:130-155)
-          for (uint32_t i = 0; i < o.n_inputs; i++) {
-            const uint32_t gi = o.first_input + i;
-            const uint64_t seq = a.inputs[gi].sequence;
-            if (seq & (1ull << 63)) continue;
-            const ReplaySrc sr = p_src[gi];
-            const uint64_t daa = rs_kind(sr) == RS_TABLE ? a.dent[gi].block_daa_score : a.acc_pov[sr.src_tx];
-            const long long lock = (long long)daa + (long long)(seq & 0xFFFFFFFFull) - 1;
-            if (lock >= (long long)bl.pov) { st = KGV_TX_SEQUENCE_LOCK; break; }
-          }
-        }
-        acc = st == KGV_TX_OK && ((bl.flags & KGV_REPLAY_SKIP_SCRIPTS) || (o.bits & 4));
-      }
-      if (verify_only) acc = false;
-      a.w_status[ti] = st;
-      a.accept[ti] = acc ? 1 : 0;
-      if (ti == bl.t0 + tid) acc_first = acc;
-      if (acc && !(o.bits & 1)) n_acc++;
+    const uint8_t* sp = (bi & 1) ? stage1 : stage0;
+    bool acc_first;
+    // ---- decide: every transaction reads the flags of its inputs (state as of the previous block); barrier; commit
+    if (BM_SHARED && staged) {
+      uint32_t *spent_in = sm_bm, *spent_out = sm_bm + a.words_in, *accepted = spent_out + a.words_out, *exists = accepted + a.words_tx;
+      const ReplayTxInfo* p_info = (const ReplayTxInfo*)sp - bl.t0;
+      const ReplaySrc* p_src = (const ReplaySrc*)(sp + RW_MAXT * 16u) - (bl.i0 & ~1u);
+      acc_first = walk_decide(a, bl, p_info, p_src, spent_in, spent_out, accepted, exists, tid, nth, n_acc);
+      __syncthreads();
+      walk_commit(a, bl, p_info, p_src, spent_in, spent_out, accepted, tid, nth, acc_first);
+    } else if (BM_SHARED) {  // a block too large for the staging area: records straight from global memory
+      uint32_t *spent_in = sm_bm, *spent_out = sm_bm + a.words_in, *accepted = spent_out + a.words_out, *exists = accepted + a.words_tx;
+      acc_first = walk_decide(a, bl, a.info, a.src, spent_in, spent_out, accepted, exists, tid, nth, n_acc);
+      __syncthreads();
+      walk_commit(a, bl, a.info, a.src, spent_in, spent_out, accepted, tid, nth, acc_first);
+    } else {                 // a window too large for shared-memory bitmaps
+      const ReplayTxInfo* p_info = staged ? (const ReplayTxInfo*)sp - bl.t0 : a.info;
+      const ReplaySrc* p_src = staged ? (const ReplaySrc*)(sp + RW_MAXT * 16u) - (bl.i0 & ~1u) : a.src;
+      acc_first = walk_decide(a, bl, p_info, p_src, a.bm_spent_in, a.bm_spent_out, a.bm_accepted, a.bm_exists, tid, nth, n_acc);
+      __syncthreads();
+      walk_commit(a, bl, p_info, p_src, a.bm_spent_in, a.bm_spent_out, a.bm_accepted, tid, nth, acc_first);
     }
     __syncthreads();
-    RW_TICK(0);
-    // ---- commit: accepted transactions spend their inputs and become visible to later blocks (UtxoDiff::add_transaction, utxo_diff.rs:233-247)
-    if (!verify_only) {
-      for (uint32_t ti = bl.t0 + tid; ti < bl.t1; ti += nth) {
-        if (ti == bl.t0 + tid ? !acc_first : !a.accept[ti]) continue;  // (written by this very thread above)
-        const ReplayTxInfo o = p_info[ti];
-        for (uint32_t i = 0; i < o.n_inputs; i++) {
-          const ReplaySrc sr = p_src[o.first_input + i];
-          if (rs_kind(sr) == RS_TABLE) bm_set(spent_in, sr.flag & RS_FLAG_MASK);
-          else bm_set(spent_out, sr.flag & RS_FLAG_MASK);
-        }
-        bm_set(accepted, o.rep);
-        a.acc_pov[o.rep] = bl.pov;
-      }
-    }
-    RW_TICK(1);
-    if (h0) stage[(bi + 1) & 1][tid] = v0;
-    if (h1) stage[(bi + 1) & 1][tid + nth] = v1;
-    cur = nxt; nxt = nn;
-    __syncthreads();
-    RW_TICK(2);
   }
-  if (a.use_smem)
-    for (uint32_t w = tid; w < a.words_in + a.words_out + a.words_tx; w += nth) {
-      uint32_t* dst = w < a.words_in ? a.bm_spent_in + w : (w < a.words_in + a.words_out ? a.bm_spent_out + (w - a.words_in) : a.bm_accepted + (w - a.words_in - a.words_out));
-      *dst = spent_in[w];
-    }
+  if (BM_SHARED)
+    for (uint32_t w = tid; w < bm_words; w += nth) a.bm_spent_in[w] = sm_bm[w];  // the global copies are laid out back to back like the shared ones
   for (int off = 16; off; off >>= 1) n_acc += __shfl_down_sync(0xFFFFFFFFu, n_acc, off);
   if ((tid & 31) == 0 && n_acc) atomicAdd(&s_acc, n_acc);
   __syncthreads();
   if (tid == 0) a.stats[0] = s_acc;
-  if (a.timers && tid == 0) for (int q = 0; q < 3; q++) a.timers[q] = (unsigned long long)tk[q];
+}
+
+// bitmaps of the walk -> per-transaction verdict of the UTXO-context rules, the acceptance flag, and the DAA score accepted outputs carry
+__global__ void k_replay_verdicts(uint32_t n_txs, const ReplayRange* __restrict__ ranges, const uint32_t* __restrict__ tx_block, const ReplayTxInfo* __restrict__ info,
+                                  const uint32_t* __restrict__ bm_exists, uint8_t* __restrict__ w_status, uint8_t* __restrict__ accept, unsigned long long* __restrict__ acc_pov) {
+  uint32_t ti = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ti >= n_txs) return;
+  const ReplayTxInfo o = info[ti];
+  const ReplayRange bl = ranges[tx_block[ti]];
+  uint8_t st;
+  bool acc;
+  if (o.bits & 1) {
+    st = KGV_TX_SKIPPED_COINBASE;
+    acc = (ti == bl.t0) && (bl.flags & KGV_REPLAY_ACCEPT_COINBASE);
+  } else {
+    st = !bm_get(bm_exists, ti) ? KGV_TX_MISSING_OUTPOINTS : ((o.bits & 2) ? w_status[ti] : o.static_status);
+    acc = st == KGV_TX_OK && ((bl.flags & KGV_REPLAY_SKIP_SCRIPTS) || (o.bits & 4));
+  }
+  if (bl.flags & KGV_REPLAY_VERIFY_ONLY) acc = false;
+  w_status[ti] = st;
+  accept[ti] = acc ? 1 : 0;
+  if (acc && !(o.bits & 8)) acc_pov[o.rep] = bl.pov;  // (a transaction sibling blocks share: written by the walk)
 }
 
 // spent entries: captured for the MuHash consumers (entry as it was when spent), then erased from the table
@@ -819,7 +891,7 @@ extern "C" int kgv_replay_window(kgv_ctx* ctx, kgv_utxo_table* table, const kgv_
   size_t o_wfl = al256(o_wst + nt);
   size_t o_apv = al256(o_wfl + nt * 4);
   size_t o_bm = al256(o_apv + nt * 8);
-  size_t o_smk = al256(o_bm + ((size_t)words_in + words_out + words_tx) * 4);
+  size_t o_smk = al256(o_bm + ((size_t)words_in + words_out + 2 * (size_t)words_tx) * 4);
   size_t o_smv = al256(o_smk + sm_cap * 8);
   size_t total = legacy_walk ? al256(o_sib + nt) : al256(o_smv + sm_cap * 4);
   rc = kgv_reserve(ctx, &ctx->d_replay, &ctx->d_replay_cap, total);
@@ -929,7 +1001,7 @@ extern "C" int kgv_replay_window(kgv_ctx* ctx, kgv_utxo_table* table, const kgv_
     uint32_t* bm = (uint32_t*)(R + o_bm);
     unsigned long long* smk = (unsigned long long*)(R + o_smk);
     uint32_t* smv = (uint32_t*)(R + o_smv);
-    const size_t bm_words = (size_t)words_in + words_out + words_tx;
+    const size_t bm_words = (size_t)words_in + words_out + 2 * (size_t)words_tx;
     CK(cudaMemsetAsync(bm, 0, bm_words * 4, st));
     CK(cudaMemsetAsync(apov, 0, nt * 8, st));
     if (ni) {
@@ -949,18 +1021,21 @@ extern "C" int kgv_replay_window(kgv_ctx* ctx, kgv_utxo_table* table, const kgv_
     WalkArgs w;
     w.ranges = ranges; w.n_blocks = (uint32_t)n_blocks; w.info = info; w.src = src; w.dent = dent; w.inputs = d.inputs;
     w.acc_pov = apov; w.w_status = wst; w.w_fail = wfl; w.accept = dacc;
-    w.bm_spent_in = bm; w.bm_spent_out = bm + words_in; w.bm_accepted = bm + words_in + words_out;
+    w.bm_spent_in = bm; w.bm_spent_out = bm + words_in; w.bm_accepted = bm + words_in + words_out; w.bm_exists = bm + words_in + words_out + words_tx;
     w.words_in = words_in; w.words_out = words_out; w.words_tx = words_tx;
     w.coinbase_maturity = prm->coinbase_maturity; w.stats = cnt;
-    w.timers = kgv_debug_on() ? cnt + 2 : nullptr;
-    const size_t stage_bytes = 2 * (size_t)RW_WORDS * 8, walk_smem = stage_bytes + bm_words * 4;
+    const size_t stage_bytes = RW_FIXED_BYTES, walk_smem = stage_bytes + bm_words * 4;
     w.use_smem = walk_smem <= 200 * 1024;
     static bool walk_set = false;
-    if (!walk_set) { CK(cudaFuncSetAttribute(k_replay_walk, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); walk_set = true; }
-    k_replay_walk<<<1, 1024, w.use_smem ? walk_smem : stage_bytes, st>>>(w);
+    if (!walk_set) { CK(cudaFuncSetAttribute(k_replay_walk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); walk_set = true; }
+    if (w.use_smem) k_replay_walk<true><<<1, RW_THREADS, walk_smem, st>>>(w);
+    else k_replay_walk<false><<<1, RW_THREADS, stage_bytes, st>>>(w);
     CK(cudaGetLastError());
     ctx->launches++;
     mark("walk");
+    k_replay_verdicts<<<nblk(nt, 256), 256, 0, st>>>((uint32_t)nt, ranges, txb, info, w.bm_exists, wst, dacc, apov);
+    CK(cudaGetLastError());
+    ctx->launches++;
     const TableView tv = view_of(table);
     if (ni) {
       k_replay_finish_inputs<<<nblk(ni, 128), 128, 0, st>>>(tv, v, ni, itx, dacc, slotp, src, apov, dent, R + o_scr);
@@ -977,12 +1052,6 @@ extern "C" int kgv_replay_window(kgv_ctx* ctx, kgv_utxo_table* table, const kgv_
     CK(cudaGetLastError());
     ctx->launches++;
     mark("finish results");
-    if (kgv_debug_on()) {
-      unsigned long long tk[3];
-      CK(cudaMemcpyAsync(tk, cnt + 2, sizeof tk, cudaMemcpyDeviceToHost, st));
-      CK(cudaStreamSynchronize(st));
-      fprintf(stderr, "[kgv] walk cycles per block: decide %.0f  commit %.0f  refill %.0f\n", (double)tk[0] / n_blocks, (double)tk[1] / n_blocks, (double)tk[2] / n_blocks);
-    }
     if (stats) CK(cudaEventRecord(ctx->ev_time[2], st));
   } else {
   // ---- in-order pass over the table itself (KGV_REPLAY_WALK=table: the round-2a form, kept as a cross-check of the resolving walk)

@@ -95,12 +95,12 @@ def test_sharded_replay_equals_unsharded(oracle):
     # On a one-GPU box the "ranks" are contexts of ONE device: size every per-call buffer up front (an unsharded dry run on a scratch table), because
     # growing one later means cudaMalloc while the other rank's wait kernel spins - harmless across devices / processes, the real deployment.
     if torch.cuda.device_count() < n_ranks:
-        big = max(wins, key=lambda w: len(w[0].txs))
         for r in range(n_ranks):
             scratch = DagReplayer(ctxs[r], prm, 1 << 16)
-            arr = np.zeros(len(big[2]), dtype=REPLAY_BLOCK_DTYPE)
-            arr["first_tx"], arr["n_txs"], arr["pov_daa_score"], arr["flags"] = big[1][:-1], np.diff(big[1]), big[2], 1
-            scratch.replay_window(big[0], arr)
+            for b, first, pov in wins:  # (buffer sizes follow txs / inputs / outputs / signatures of a window, rounded to powers of two in places)
+                arr = np.zeros(len(pov), dtype=REPLAY_BLOCK_DTYPE)
+                arr["first_tx"], arr["n_txs"], arr["pov_daa_score"], arr["flags"] = first[:-1], np.diff(first), pov, 1
+                scratch.replay_window(b, arr)
             scratch.close()
 
     def rank_body(r):
