@@ -95,50 +95,120 @@ def host_threads():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / power / throttle reasons of ONE GPU during the timed region (B200_PROFILING.md's clocks line).
+
+    Sampled in-process through NVML (nvidia_ml_py), attached to this rank's GPU only and initialised in prepare() BEFORE the warm-up: spawning
+    `nvidia-smi -lms` per rank at the start of the timed region - the round-1 form - makes eight NVML initialisations enumerate every GPU of
+    the node while the steps run, which stalled rank 0's GPU by ~12 ms per step and WAS the N=8 scaling cliff (measured: 197.8 -> 277.3 M
+    verifies/s at N=8 with nothing else changed, profiles/r02_scaling_n8.md).  nvidia-smi remains the fallback when NVML cannot be loaded;
+    it is then started in prepare() as well and only rows that fall inside the timed region are kept."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
-        self.index = index
-        self.rows = []
-        self.proc = None
+    def __init__(self, index, uuid=None, period_s=0.025):
+        self.index, self.uuid, self.period = index, uuid, period_s
+        self.rows = []          # (t, sm, max_sm, power_w, reasons-set)
+        self.nvml = self.handle = self.proc = self.thread = None
+        self.t_start = self.t_stop = None
+        self.active = False
+        self.how = None
+
+    def prepare(self):
+        """everything slow (NVML init / process start) happens here, outside the timed region"""
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = None
+            if self.uuid:
+                for cand in ("GPU-" + self.uuid, self.uuid):
+                    try:
+                        h = pynvml.nvmlDeviceGetHandleByUUID(cand)
+                        break
+                    except Exception:
+                        h = None
+            if h is None:
+                h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)  # fail here rather than in the thread
+            self.nvml, self.handle, self.how = pynvml, h, "nvml"
+        except Exception:
+            self.nvml = None
+            try:
+                self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                             stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                self.how = "nvidia-smi"
+            except Exception:
+                self.proc = None
+        if self.nvml or self.proc:
+            self.thread = threading.Thread(target=self._pump_nvml if self.nvml else self._pump_smi, daemon=True)
+            self.alive = True
+            self.thread.start()
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._pump, daemon=True)
-            self.thread.start()
-        except Exception:
-            self.proc = None
+        if self.thread is None:
+            self.prepare()
+        self.t_start = time.perf_counter()
+        self.active = True
 
-    def _pump(self):
+    def _sample_nvml(self):
+        n, h = self.nvml, self.handle
+        sm = float(n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM))
+        mx = float(n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM))
+        try:
+            pw = n.nvmlDeviceGetPowerUsage(h) / 1000.0
+        except Exception:
+            pw = None
+        try:
+            mask = n.nvmlDeviceGetCurrentClocksEventReasons(h)
+        except Exception:
+            mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        names = (("hw_slowdown", n.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", n.nvmlClocksEventReasonHwThermalSlowdown),
+                 ("sw_thermal_slowdown", n.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", n.nvmlClocksEventReasonSwPowerCap))
+        return sm, mx, pw, {k for k, bit in names if mask & bit}
+
+    def _pump_nvml(self):
+        while self.alive:
+            if self.active:
+                try:
+                    self.rows.append((time.perf_counter(),) + self._sample_nvml())
+                except Exception:
+                    pass
+            time.sleep(self.period)
+
+    def _pump_smi(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
-
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons, power = [], [], set(), []
-        for r in self.rows:
-            f = [x.strip() for x in r.split(",")]
-            if len(f) < 7:
+            f = [x.strip() for x in line.strip().split(",")]
+            if not self.active or len(f) < 7:
                 continue
             try:
-                sm.append(float(f[0])); mx.append(float(f[1])); power.append(float(f[2]))
+                row = (time.perf_counter(), float(f[0]), float(f[1]), float(f[2]))
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+            self.rows.append(row + ({name for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7])
+                                     if v.lower().startswith("active")},))
+
+    def stop(self):
+        self.t_stop = time.perf_counter()
+        if self.nvml and self.active and not self.rows:  # a timed region shorter than one period: one sample at its end
+            try:
+                self.rows.append((self.t_stop,) + self._sample_nvml())
+            except Exception:
+                pass
+        self.active = False
+        self.alive = False
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        if self.thread is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["neither NVML nor nvidia-smi available"]}
+        rows = [r for r in self.rows if self.t_start is None or self.t_start <= r[0] <= self.t_stop]
+        sm = [r[1] for r in rows]
+        power = [r[3] for r in rows if r[3] is not None]
+        reasons = set().union(*[r[4] for r in rows]) if rows else set()
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(r[2] for r in rows) if rows else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons), "sampler": self.how}
 
 
 def measured_peak_hbm():
@@ -534,6 +604,13 @@ def merge_clocks(per_rank):
     out = dict(rows[0])
     out["sm_mhz"] = min(sm) if sm else None
     out["sm_mhz_per_rank"] = [c.get("sm_mhz") for c in rows]
+    if any("kernel_ms" in c for c in rows):
+        out["kernel_ms_per_rank"] = [c.get("kernel_ms") for c in rows]
+        out["step_ms_per_rank"] = [c.get("step_ms") for c in rows]
+        out.pop("kernel_ms", None); out.pop("step_ms", None); out.pop("timeline", None)
+        if any(c.get("timeline") for c in rows):
+            out["timeline_per_rank"] = [c.get("timeline") for c in rows]
+    out["power_w_max_per_rank"] = [c.get("power_w_max") for c in rows]
     out["reasons"] = sorted(set(r for c in rows for r in (c.get("reasons") or [])))
     out["ranks_sampled"] = len(rows)
     return out
@@ -559,7 +636,7 @@ def measure_dag_replay_sharded(ctx, dev, comm, rank, world, n_blocks, tpb, windo
     lib, h = ctx._lib, ctx._h
     cudart = torch.cuda.cudart()
     st = ReplayStats()
-    total_s = gen_s = 0.0
+    total_s = gen_s = pre_ms = ord_ms = 0.0
     n_txs = n_sig = n_acc = done = 0
     try:
         while done < n_blocks:
@@ -582,6 +659,7 @@ def measure_dag_replay_sharded(ctx, dev, comm, rank, world, n_blocks, tpb, windo
             for a in pinned:
                 cudart.cudaHostUnregister(a.ctypes.data)
             n_txs += len(b.txs) - k; n_sig += int(st.n_sig_checks); n_acc += int(st.n_accepted)
+            pre_ms += float(st.pre_check_ms); ord_ms += float(st.in_order_ms)
             done += k
         cnt = gen.counts()
         assert n_acc == n_txs - cnt["n_invalid"] and us.count() == cnt["n_utxos"], (n_acc, n_txs, cnt)
@@ -596,7 +674,10 @@ def measure_dag_replay_sharded(ctx, dev, comm, rank, world, n_blocks, tpb, windo
                         f"against its own 2^25-slot table replica, signature checks sharded over {world} GPUs (kgv_set_sharding), verdict bytes exchanged through the "
                         f"library communicator, kgv_replay_window over {window} blocks per call from page-locked host arrays (uploads inside the timed region)",
             "n_blocks": n_blocks, "n_txs": n_txs, "n_sig_checks": n_sig, "n_gpus": world, "txs_per_s": n_txs / total_s, "blocks_per_s": n_blocks / total_s,
-            "sig_checks_per_s": n_sig / total_s, "seconds": total_s, "generation_s": round(gen_s, 1), "replicas_identical": True}
+            "sig_checks_per_s": n_sig / total_s, "seconds": total_s,
+            "device_ms_rank0": {"pre_check_sharded": round(pre_ms, 2), "in_order_replicated": round(ord_ms, 2),
+                                "note": "device time of the two phases on rank 0 (kgv_replay_stats); the rest of `seconds` is the upload of the window, which every replica repeats"},
+            "generation_s": round(gen_s, 1), "replicas_identical": True}
 
 
 def run_ours(args, rank, world, local_rank):
@@ -632,12 +713,14 @@ def run_ours(args, rank, world, local_rank):
         gathered = torch.empty(nbm * world, dtype=torch.uint8, device=dev) if world > 1 else None
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
-        def exchange():
+        def exchange(mid=None):
             """every rank ends up with every shard's validity bitmap"""
             if world == 1:
                 ctx.status_to_bitmap(dst, n=n, bitmap=dbm)
             elif args.collective == "peer":   # the bitmap kernel writes straight into every peer over NVLink, consumers wait on local flags
                 e = comm.publish_bitmap(dst.data_ptr(), n)
+                if mid is not None:
+                    mid.record(stream)
                 comm.wait(e, nbm, gathered.data_ptr())
             elif args.collective == "nccl":   # ncclAllGather called from the library
                 ctx.status_to_bitmap(dst, n=n, bitmap=dbm)
@@ -650,33 +733,46 @@ def run_ours(args, rank, world, local_rank):
             ctx.verify_schnorr_batch(dpk, dmsg, dsig, n=n, status=dst)
             exchange()
 
+        try:
+            dev_uuid = str(torch.cuda.get_device_properties(dev).uuid)
+        except Exception:
+            dev_uuid = None
+        sampler = ClockSampler(local_rank, dev_uuid)
+        if not os.environ.get("KGV_BENCH_NO_SAMPLER"):  # (diagnosis only: the contract wants the clocks)
+            sampler.prepare()                            # NVML attach happens here, before the warm-up
         for _ in range(max(args.warmup, 3)):
             step()
         stream.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        sampler = ClockSampler(local_rank)
-        sampler.start()
+        if not os.environ.get("KGV_BENCH_NO_SAMPLER"):
+            sampler.start()
         launches0 = ctx.launch_count
         evs = []
         for _ in range(args.steps):
             flush.fill_(1)  # L2 flush, outside the timed events
-            e0, ek, e1 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            e0, ek, ep, e1 = (torch.cuda.Event(enable_timing=True) for _ in range(4))
             e0.record(stream)
             ctx.verify_schnorr_batch(dpk, dmsg, dsig, n=n, status=dst)
             ek.record(stream)
-            exchange()
+            exchange(ep)
             e1.record(stream)
-            evs.append((e0, ek, e1))
+            evs.append((e0, ek, e1, ep))
         stream.synchronize()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         launches = ctx.launch_count - launches0
         clocks = sampler.stop()
-        step_ms = [a.elapsed_time(c) for a, _, c in evs]
-        kern_ms = [a.elapsed_time(b) for a, b, _ in evs]
+        step_ms = [a.elapsed_time(c) for a, _, c, _ in evs]
+        kern_ms = [a.elapsed_time(b) for a, b, _, _ in evs]
+        # where a step's time goes on THIS rank: publish (own stores to every peer), wait (for the slowest peer), and the gap to the next step (L2 flush)
+        timeline = None
+        if world > 1 and args.collective == "peer":
+            timeline = {"publish_ms": round(float(np.mean([b.elapsed_time(p) for _, b, _, p in evs])), 3),
+                        "wait_collect_ms": round(float(np.mean([p.elapsed_time(c) for _, _, c, p in evs])), 3),
+                        "gap_to_next_step_ms": round(float(np.mean([evs[i][2].elapsed_time(evs[i + 1][0]) for i in range(len(evs) - 1)])), 3) if len(evs) > 1 else None}
         total_ms = float(sum(step_ms))
         # correctness guard inside the bench: verdict counts must match the generator's ground truth
         st = dst.cpu().numpy()
@@ -728,6 +824,8 @@ def run_ours(args, rank, world, local_rank):
             rep5 = measure_dag_replay_sharded(ctx, dev, comm, rank, world, args.replay_blocks_multi, 150, args.replay_window)
 
     # max over ranks
+    if isinstance(clocks, dict):  # per-rank device times next to the clocks they ran at (a slow GPU shows up here, not in the max)
+        clocks = dict(clocks, kernel_ms=round(float(np.mean(kern_ms)), 3), step_ms=round(float(np.mean(step_ms)), 3), timeline=timeline)
     cl_all = [clocks]
     if world > 1:
         cl_all = [None] * world
