@@ -848,8 +848,8 @@ def run_ours(args, rank, world, local_rank):
     achieved = ALG_BYTES_PER_VERIFY * n / (kern_ms_avg * 1e-3) / 1e9
     traffic = None
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_schnorr_verify_ncu_summary.json")) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch_at_bench_size")
+        with open(os.path.join(ROOT, "profiles", "r02_schnorr_verify_ncu_summary.json")) as f:  # one `ncu --set full` capture at the bench size (1 Mi triples per launch)
+            traffic = int(json.load(f).get("dram_bytes_per_launch"))
     except Exception:
         pass
 

@@ -85,13 +85,14 @@ __global__ void __launch_bounds__(128) k_build_gtab(uint32_t* __restrict__ gtab)
 // ONE modular inversion among them (Montgomery's trick): the field inversion of BIP-340's final affine
 // conversion, resp. the scalar inversion s^-1 of ECDSA, drops from 1 to 1/KGV_ITEMS per signature with no
 // cross-thread synchronisation.  Pending state sits in (L1-resident) local memory between the phases.
-template <bool ALIGNED>
+template <bool ALIGNED, bool INDEXED>
 __global__ void __launch_bounds__(KGV_BLOCK, KGV_BLOCKS_PER_SM)
 k_schnorr_verify(const uint8_t* __restrict__ pk, const uint8_t* __restrict__ msg, const uint8_t* __restrict__ sig, size_t n_arg,
                  uint8_t* __restrict__ status, const uint32_t* __restrict__ gtab, const uint32_t* __restrict__ index, const uint32_t* __restrict__ n_dev) {
-  // index / n_dev (both optional): verify only the listed items (the signature-cache misses), their count read on the device
+  // INDEXED: verify only the listed items (the signature-cache misses), their count read on the device.  A separate instantiation: the two
+  // extra pointers live across the whole kernel cost the plain form 3 % (register pressure at the 168-register cap, measured).
   extern __shared__ uint32_t smem[];
-  const size_t n = n_dev ? (size_t)*n_dev : n_arg;
+  const size_t n = (INDEXED && n_dev) ? (size_t)*n_dev : n_arg;
   const size_t total = (size_t)gridDim.x * KGV_BLOCK;
   const size_t tid = (size_t)blockIdx.x * KGV_BLOCK + threadIdx.x;
   SmemTab tab{smem + threadIdx.x};
@@ -109,7 +110,7 @@ k_schnorr_verify(const uint8_t* __restrict__ pk, const uint8_t* __restrict__ msg
     size_t i = base + tid + (size_t)j * total;
     st[j] = KGV_ST_INVALID;
     if (i >= n) continue;
-    if (index) i = index[i];
+    if (INDEXED) i = index[i];
     uint32_t pkw[8], mw[8], sw[16];
     load_be32<ALIGNED>(pkw, pk + 32 * i);
     load_be32<ALIGNED>(mw, msg + 32 * i);
@@ -140,19 +141,19 @@ k_schnorr_verify(const uint8_t* __restrict__ pk, const uint8_t* __restrict__ msg
 #pragma unroll 1
   for (int j = 0; j < KGV_ITEMS; j++) {
     size_t i = base + tid + (size_t)j * total;
-    if (i < n) status[index ? index[i] : i] = st[j];
+    if (i < n) status[INDEXED ? index[i] : i] = st[j];
   }
   }
 }
 
 struct sc_words { uint32_t v[8]; };
 
-template <bool ALIGNED>
+template <bool ALIGNED, bool INDEXED>
 __global__ void __launch_bounds__(KGV_BLOCK, KGV_BLOCKS_PER_SM)
 k_ecdsa_verify(const uint8_t* __restrict__ pk, const uint8_t* __restrict__ msg, const uint8_t* __restrict__ sig, size_t n_arg,
                uint8_t* __restrict__ status, const uint32_t* __restrict__ gtab, const uint32_t* __restrict__ index, const uint32_t* __restrict__ n_dev) {
   extern __shared__ uint32_t smem[];
-  const size_t n = n_dev ? (size_t)*n_dev : n_arg;
+  const size_t n = (INDEXED && n_dev) ? (size_t)*n_dev : n_arg;
   const size_t total = (size_t)gridDim.x * KGV_BLOCK;
   const size_t tid = (size_t)blockIdx.x * KGV_BLOCK + threadIdx.x;
   SmemTab tab{smem + threadIdx.x};
@@ -168,7 +169,7 @@ k_ecdsa_verify(const uint8_t* __restrict__ pk, const uint8_t* __restrict__ msg, 
     size_t i = base + tid + (size_t)j * total;
     st[j] = KGV_ST_INVALID;
     if (i >= n) continue;
-    if (index) i = index[i];
+    if (INDEXED) i = index[i];
     uint32_t pkw[8], mw[8], sw[16];
     const uint8_t* kp = pk + 33 * i;  // 33-byte stride: never word aligned
     uint32_t tag = kp[0];
@@ -203,7 +204,7 @@ k_ecdsa_verify(const uint8_t* __restrict__ pk, const uint8_t* __restrict__ msg, 
 #pragma unroll 1
   for (int j = 0; j < KGV_ITEMS; j++) {
     size_t i = base + tid + (size_t)j * total;
-    if (i < n) status[index ? index[i] : i] = st[j];
+    if (i < n) status[INDEXED ? index[i] : i] = st[j];
   }
   }
 }
@@ -348,12 +349,16 @@ extern "C" int kgv_create(int device, uint32_t flags, kgv_ctx** out) {
     CK(cudaGetLastError());
     ctx->launches++;
     const int smem = KGV_BLOCK * 128 * (int)sizeof(uint32_t);
-    CK(cudaFuncSetAttribute(k_schnorr_verify<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    CK(cudaFuncSetAttribute(k_schnorr_verify<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    CK(cudaFuncSetAttribute(k_ecdsa_verify<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    CK(cudaFuncSetAttribute(k_ecdsa_verify<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CK(cudaFuncSetAttribute(k_schnorr_verify<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CK(cudaFuncSetAttribute(k_schnorr_verify<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CK(cudaFuncSetAttribute(k_schnorr_verify<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CK(cudaFuncSetAttribute(k_schnorr_verify<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CK(cudaFuncSetAttribute(k_ecdsa_verify<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CK(cudaFuncSetAttribute(k_ecdsa_verify<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CK(cudaFuncSetAttribute(k_ecdsa_verify<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CK(cudaFuncSetAttribute(k_ecdsa_verify<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int per_sm = 0, sms = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_schnorr_verify<true>, KGV_BLOCK, smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_schnorr_verify<true, false>, KGV_BLOCK, smem));
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
     ctx->resident_blocks = per_sm * sms > 0 ? per_sm * sms : 148 * KGV_BLOCKS_PER_SM;
     CK(cudaStreamSynchronize(ctx->stream));
@@ -430,11 +435,21 @@ int kgv_launch_verify(kgv_ctx* ctx, const uint8_t* dpk, const uint8_t* dmsg, con
   unsigned blocks = (unsigned)(want < (size_t)ctx->resident_blocks ? want : (size_t)ctx->resident_blocks);
   bool aligned = (((uintptr_t)dmsg | (uintptr_t)dsig | (ecdsa ? 0 : (uintptr_t)dpk)) & 31) == 0;
   if (ecdsa) {
-    if (aligned) k_ecdsa_verify<true><<<blocks, KGV_BLOCK, smem, st>>>(dpk, dmsg, dsig, n, dst, ctx->gtab, index, n_dev);
-    else k_ecdsa_verify<false><<<blocks, KGV_BLOCK, smem, st>>>(dpk, dmsg, dsig, n, dst, ctx->gtab, index, n_dev);
+    if (index) {
+      if (aligned) k_ecdsa_verify<true, true><<<blocks, KGV_BLOCK, smem, st>>>(dpk, dmsg, dsig, n, dst, ctx->gtab, index, n_dev);
+      else k_ecdsa_verify<false, true><<<blocks, KGV_BLOCK, smem, st>>>(dpk, dmsg, dsig, n, dst, ctx->gtab, index, n_dev);
+    } else {
+      if (aligned) k_ecdsa_verify<true, false><<<blocks, KGV_BLOCK, smem, st>>>(dpk, dmsg, dsig, n, dst, ctx->gtab, nullptr, nullptr);
+      else k_ecdsa_verify<false, false><<<blocks, KGV_BLOCK, smem, st>>>(dpk, dmsg, dsig, n, dst, ctx->gtab, nullptr, nullptr);
+    }
   } else {
-    if (aligned) k_schnorr_verify<true><<<blocks, KGV_BLOCK, smem, st>>>(dpk, dmsg, dsig, n, dst, ctx->gtab, index, n_dev);
-    else k_schnorr_verify<false><<<blocks, KGV_BLOCK, smem, st>>>(dpk, dmsg, dsig, n, dst, ctx->gtab, index, n_dev);
+    if (index) {
+      if (aligned) k_schnorr_verify<true, true><<<blocks, KGV_BLOCK, smem, st>>>(dpk, dmsg, dsig, n, dst, ctx->gtab, index, n_dev);
+      else k_schnorr_verify<false, true><<<blocks, KGV_BLOCK, smem, st>>>(dpk, dmsg, dsig, n, dst, ctx->gtab, index, n_dev);
+    } else {
+      if (aligned) k_schnorr_verify<true, false><<<blocks, KGV_BLOCK, smem, st>>>(dpk, dmsg, dsig, n, dst, ctx->gtab, nullptr, nullptr);
+      else k_schnorr_verify<false, false><<<blocks, KGV_BLOCK, smem, st>>>(dpk, dmsg, dsig, n, dst, ctx->gtab, nullptr, nullptr);
+    }
   }
   CK(cudaGetLastError());
   ctx->launches++;
