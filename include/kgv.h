@@ -229,6 +229,19 @@ int kgv_utxo_apply_diff(kgv_ctx* ctx, kgv_utxo_table* t, const uint8_t* rem_keys
  * BLAKE2b "MuHashElement" hashes of every (outpoint, entry) (consensus/core/src/muhash.rs:47-59). */
 int kgv_utxo_count(kgv_ctx* ctx, kgv_utxo_table* t, uint64_t* count);
 int kgv_utxo_digest(kgv_ctx* ctx, kgv_utxo_table* t, uint8_t out32[32]);
+/* DbUtxoSetStore::iterator (utxo_set.rs:114-129): every live entry as (key, entry record, script bytes), in the table's (arbitrary) order -
+ * what the syncer side of a pruning-point import streams out, and what `virtual.utxo_set := pruning-point utxo_set` copies
+ * (consensus/src/pipeline/virtual_processor/processor.rs:1150-1158).  Arrays all host or all device.  With keys36 == NULL only the sizes are
+ * returned (*n_out entries, *bytes_out script bytes); arrays smaller than that give KGV_ERR_NOMEM with the sizes still set. */
+int kgv_utxo_export(kgv_ctx* ctx, kgv_utxo_table* t, uint8_t* keys36, kgv_utxo_entry* entries, uint8_t* bytes, size_t max_n, size_t bytes_cap, size_t* n_out,
+                    size_t* bytes_out);
+/* append_imported_pruning_point_utxos (consensus/src/consensus/mod.rs:1070-1083) for one chunk of the imported UTXO set: the entries are
+ * written into the table (write_many) and MuHash::from_utxo of every (outpoint, entry), reduced, is combined into the running multiset
+ * numerator384 (host value, in / out, 384 little-endian bytes; start from 1).  The caller then compares kgv_muhash_finalize(numerator, 1)
+ * with the new pruning point's header.utxo_commitment (processor.rs:1133-1139: ImportedMultisetHashMismatch) and validates the pruning
+ * point's own transactions with kgv_validate_txs (:1162-1172). */
+int kgv_utxo_import_chunk(kgv_ctx* ctx, kgv_utxo_table* t, const uint8_t* keys36, const kgv_utxo_entry* entries, const uint8_t* bytes, size_t n_bytes, size_t n,
+                          uint8_t* numerator384);
 
 /* Composed views (consensus/core/src/utxo/utxo_view.rs:22-35 ComposedUtxoView / UtxoViewComposition::compose; UtxoDiff utxo_diff.rs:15-19):
  * a DIFF LAYER on the device.  The returned handle is a kgv_utxo_table that every call accepting a table accepts; it behaves as base ∘ diff:

@@ -103,6 +103,41 @@ __global__ void k_utxo_insert(TableView t, const uint8_t* __restrict__ keys, con
   if (status) status[i] = (uint8_t)r;
 }
 
+// export (DbUtxoSetStore::iterator, utxo_set.rs:114-129: the syncer side of a pruning-point import and the source of `virtual.utxo_set := pruning
+// utxo_set`, processor.rs:1150-1158): every live slot is compacted into (key, entry, script bytes) arrays; order is the table's, i.e. arbitrary
+__global__ void k_utxo_export(TableView t, uint8_t* __restrict__ keys, kgv_utxo_entry* __restrict__ entries, uint8_t* __restrict__ bytes, uint64_t max_n, uint64_t bytes_cap,
+                              unsigned long long* __restrict__ cnt) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > t.mask) return;
+  const UtxoSlot* s = &t.slots[i];
+  if (s->state != SLOT_FULL) return;
+  DevEntry e;
+  slot_to_entry(e, t, s);
+  const unsigned long long at = atomicAdd(&cnt[0], 1ull);
+  const unsigned long long off = atomicAdd(&cnt[1], (unsigned long long)e.script_len);
+  if (!keys || at >= max_n || off + e.script_len > bytes_cap || off + e.script_len > 0xFFFFFFFFull) return;  // counting pass / caller's arrays too small (reported by the host side)
+  uint32_t* kw = (uint32_t*)(keys + 36 * at);
+#pragma unroll
+  for (int w = 0; w < 9; w++) kw[w] = s->key[w];
+  kgv_utxo_entry o;
+  o.amount = e.amount; o.block_daa_score = e.block_daa_score; o.script_off = (uint32_t)off; o.script_len = e.script_len; o.spk_version = e.spk_version; o.is_coinbase = e.is_coinbase;
+  memset(o.pad_, 0, sizeof o.pad_);
+  entries[at] = o;
+  for (uint32_t b = 0; b < e.script_len; b++) bytes[off + b] = e.script[b];
+}
+// MuHash::from_utxo of every (outpoint, entry) of a chunk (consensus/src/consensus/mod.rs:1075-1080): level 0 of a product tree
+__global__ void __launch_bounds__(128) k_muhash_utxo_elements(const uint8_t* __restrict__ keys, const kgv_utxo_entry* __restrict__ entries, const uint8_t* __restrict__ bytes, size_t n,
+                                                              uint32_t* __restrict__ e_num) {
+  size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n) return;
+  uint32_t k[9];
+  load_key(k, keys + 36 * g);
+  const kgv_utxo_entry e = entries[g];
+  uint64_t d[4];
+  muhash_utxo_digest(d, k, k[8], e.block_daa_score, e.amount, e.is_coinbase != 0, e.spk_version, bytes + e.script_off, e.script_len);
+  muhash_expand_store(e_num, n, g, d);
+}
+
 // digest: sum of MuHashElement hashes, accumulated as 8 x 32-bit limbs in 64-bit counters (carries folded on the host)
 __global__ void k_utxo_digest(TableView t, unsigned long long* __restrict__ acc) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -598,6 +633,88 @@ extern "C" int kgv_utxo_apply_diff(kgv_ctx* ctx, kgv_utxo_table* t, const uint8_
     CK(cudaStreamSynchronize(ctx->stream));
   }
   return KGV_OK;
+}
+
+extern "C" int kgv_utxo_export(kgv_ctx* ctx, kgv_utxo_table* t, uint8_t* keys36, kgv_utxo_entry* entries, uint8_t* bytes, size_t max_n, size_t bytes_cap, size_t* n_out,
+                               size_t* bytes_out) {
+  if (!ctx || !t) return KGV_ERR_ARG;
+  std::lock_guard<std::recursive_mutex> g(ctx->mu);
+  if (t->base) { ctx->err = "export is defined on plain tables: commit the view first"; return KGV_ERR_ARG; }
+  const bool counting = !keys36;
+  if (!counting && (!entries || (bytes_cap && !bytes))) { ctx->err = "null buffer"; return KGV_ERR_ARG; }
+  CK(cudaSetDevice(ctx->device));
+  const bool dev = counting ? true : kgv_ptr_is_device(keys36);
+  uint8_t *dk = keys36, *db = bytes;
+  kgv_utxo_entry* de = entries;
+  size_t o_e = al256(max_n * 36), o_b = al256(o_e + max_n * sizeof(kgv_utxo_entry));
+  if (!counting && !dev) {
+    int rc = kgv_reserve(ctx, &ctx->d_out, &ctx->d_out_cap, o_b + bytes_cap + 16);
+    if (rc) return rc;
+    dk = ctx->d_out; de = (kgv_utxo_entry*)(ctx->d_out + o_e); db = ctx->d_out + o_b;
+  }
+  unsigned long long* cnt = t->counters + 8;  // (the digest's scratch words)
+  CK(cudaMemsetAsync(cnt, 0, 2 * sizeof(unsigned long long), ctx->stream));
+  k_utxo_export<<<nblk(t->mask + 1, 128), 128, 0, ctx->stream>>>(view_of(t), counting ? nullptr : dk, de, db, max_n, bytes_cap, cnt);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  unsigned long long c[2];
+  CK(cudaMemcpyAsync(c, cnt, sizeof c, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (n_out) *n_out = (size_t)c[0];
+  if (bytes_out) *bytes_out = (size_t)c[1];
+  if (counting) return KGV_OK;
+  if (c[0] > max_n || c[1] > bytes_cap) { ctx->err = "kgv_utxo_export: the caller's arrays are too small (sizes returned)"; return KGV_ERR_NOMEM; }
+  if (!dev) {
+    if (c[0]) {
+      CK(cudaMemcpyAsync(keys36, dk, (size_t)c[0] * 36, cudaMemcpyDeviceToHost, ctx->stream));
+      CK(cudaMemcpyAsync(entries, de, (size_t)c[0] * sizeof(kgv_utxo_entry), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (c[1]) CK(cudaMemcpyAsync(bytes, db, (size_t)c[1], cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  return KGV_OK;
+}
+
+extern "C" int kgv_utxo_import_chunk(kgv_ctx* ctx, kgv_utxo_table* t, const uint8_t* keys36, const kgv_utxo_entry* entries, const uint8_t* bytes, size_t n_bytes, size_t n,
+                                     uint8_t* numerator384) {
+  if (!ctx || !t) return KGV_ERR_ARG;
+  std::lock_guard<std::recursive_mutex> g(ctx->mu);
+  if (!numerator384) { ctx->err = "null argument"; return KGV_ERR_ARG; }
+  if (n == 0) return KGV_OK;
+  if (!keys36 || !entries || (n_bytes && !bytes)) { ctx->err = "null buffer"; return KGV_ERR_ARG; }
+  if (kgv_ptr_is_device(numerator384)) { ctx->err = "numerator384 is a host value"; return KGV_ERR_ARG; }
+  for (size_t i = 0; !kgv_ptr_is_device(keys36) && i < n; i++)
+    if ((uint64_t)entries[i].script_off + entries[i].script_len > n_bytes) { ctx->err = "entry script outside the byte arena"; return KGV_ERR_ARG; }
+  CK(cudaSetDevice(ctx->device));
+  const uint8_t *dk = keys36, *db = bytes;
+  const kgv_utxo_entry* de = entries;
+  if (!kgv_ptr_is_device(keys36)) {  // one upload serves the insert and the multiset
+    size_t o_e = al256(n * 36), o_b = al256(o_e + n * sizeof(kgv_utxo_entry));
+    int rc = kgv_reserve(ctx, &ctx->d_scratch, &ctx->d_scratch_cap, o_b + n_bytes + 16);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(ctx->d_scratch, keys36, n * 36, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_scratch + o_e, entries, n * sizeof(kgv_utxo_entry), cudaMemcpyHostToDevice, ctx->stream));
+    if (n_bytes) CK(cudaMemcpyAsync(ctx->d_scratch + o_b, bytes, n_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    dk = ctx->d_scratch; de = (const kgv_utxo_entry*)(ctx->d_scratch + o_e); db = ctx->d_scratch + o_b;
+  }
+  // pruning_meta.utxo_set.write_many(chunk) (consensus/mod.rs:1072)
+  int rc = kgv_utxo_apply_diff(ctx, t, nullptr, 0, nullptr, dk, de, db, n_bytes, n, nullptr);
+  if (rc) return rc;
+  // chunk.par_iter().map(MuHash::from_utxo).reduce(combine) (:1075-1080), then current_multiset.combine (:1082)
+  uint32_t *e_den = nullptr, *e_num = nullptr;
+  rc = kgv_mu_reserve(ctx, 0, n, &e_den, &e_num);
+  if (rc) return rc;
+  k_muhash_utxo_elements<<<nblk(n, 128), 128, 0, ctx->stream>>>(dk, de, db, n, e_num);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  uint8_t chunk_num[384], chunk_den[384], one[384];
+  rc = kgv_mu_reduce(ctx, 0, n, chunk_num, chunk_den);
+  if (rc) return rc;
+  memset(one, 0, sizeof one);
+  one[0] = 1;
+  uint8_t den[384];
+  memcpy(den, one, sizeof den);
+  return kgv_muhash_combine(ctx, numerator384, den, chunk_num, one);
 }
 
 extern "C" int kgv_utxo_count(kgv_ctx* ctx, kgv_utxo_table* t, uint64_t* count) {

@@ -135,6 +135,16 @@ class GpuUtxoSet:
         self.ctx._check(self._lib.kgv_utxo_digest(self.ctx._h, self._h, ctypes.addressof(out)))
         return bytes(out)
 
+    def export(self):
+        """DbUtxoSetStore::iterator (utxo_set.rs:114-129): every live entry. Returns (keys36 (n, 36), entries (n,) ENTRY_DTYPE, arena bytes)."""
+        n, nb = ctypes.c_size_t(), ctypes.c_size_t()
+        self.ctx._check(self._lib.kgv_utxo_export(self.ctx._h, self._h, None, None, None, 0, 0, ctypes.byref(n), ctypes.byref(nb)))
+        keys = np.zeros((max(n.value, 1), 36), dtype=np.uint8)
+        ent = np.zeros(max(n.value, 1), dtype=ENTRY_DTYPE)
+        arena = np.zeros(max(nb.value, 8), dtype=np.uint8)
+        self.ctx._check(self._lib.kgv_utxo_export(self.ctx._h, self._h, keys.ctypes.data, ent.ctypes.data, arena.ctypes.data, n.value, nb.value, ctypes.byref(n), ctypes.byref(nb)))
+        return keys[:n.value], ent[:n.value], arena[:nb.value]
+
 
 class TransactionValidator:
     """Batch counterpart of the reference's TransactionValidator for the UTXO-context rules."""
