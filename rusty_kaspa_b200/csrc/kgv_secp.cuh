@@ -171,19 +171,50 @@ KGV_HD void sc_sqr(uint32_t* r, const uint32_t* a) {
   sc_reduce512(r, t);
 }
 #endif
-// r = a^(n-2) mod n (a != 0). The exponent is public and identical in every lane: no divergence.
+// r = a^(n-2) mod n (a != 0).  The exponent is public and identical in every lane: no divergence.  Addition chain: the 127 leading one bits
+// of n-2 through x_k = a^(2^k - 1) (k = 2, 3, 6, 8, 14, 28, 56, 112, 126: the ladder libsecp256k1's scalar inverse uses), the remaining 129 bits
+// by a sliding window over the odd powers a, a^3, a^5, a^7 (schedule derived and checked against pow(a, n-2, n) by
+// tools/derive_sc_inv_chain.py; tests/test_hostsim.py runs this very function on the host): 255 squarings + 44 multiplications instead of the 255 + 191
+// of plain square-and-multiply (ECDSA shares one inversion among KGV_ITEMS signatures; it was 11 % of an ECDSA verification).
+KGV_HD void sc_sqr_n(uint32_t* r, int n) {
+  for (int i = 0; i < n; i++) sc_sqr(r, r);
+}
 KGV_HD void sc_inv(uint32_t* r, const uint32_t* a) {
-  // n - 2
-  const uint32_t e[8] = {0xD036413Fu, 0xBFD25E8Cu, 0xAF48A03Bu, 0xBAAEDCE6u, 0xFFFFFFFEu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
-  uint32_t acc[8];
+  uint32_t a1[8], a3[8], a5[8], a7[8], x6[8], x14[8], t[8], u[8];
 #pragma unroll
-  for (int i = 0; i < 8; i++) acc[i] = a[i];  // top bit of the exponent is 1
-  for (int bit = 254; bit >= 0; bit--) {
-    sc_sqr(acc, acc);
-    if ((e[bit >> 5] >> (bit & 31)) & 1u) sc_mul(acc, acc, a);
-  }
+  for (int i = 0; i < 8; i++) a1[i] = a[i];
+  sc_sqr(u, a1);                       // a^2
+  sc_mul(a3, u, a1);                   // x2 = a^3
+  sc_mul(a5, a3, u);                   // a^5
+  sc_sqr(t, a3); sc_mul(a7, t, a1);    // x3 = a^7
 #pragma unroll
-  for (int i = 0; i < 8; i++) r[i] = acc[i];
+  for (int i = 0; i < 8; i++) t[i] = a7[i];
+  sc_sqr_n(t, 3); sc_mul(x6, t, a7);                                   // x6
+#pragma unroll
+  for (int i = 0; i < 8; i++) t[i] = x6[i];
+  sc_sqr_n(t, 2); sc_mul(t, t, a3);                                    // x8
+  sc_sqr_n(t, 6); sc_mul(x14, t, x6);                                  // x14
+#pragma unroll
+  for (int i = 0; i < 8; i++) t[i] = x14[i];
+  sc_sqr_n(t, 14); sc_mul(t, t, x14);                                  // x28
+#pragma unroll
+  for (int i = 0; i < 8; i++) u[i] = t[i];
+  sc_sqr_n(t, 28); sc_mul(t, t, u);                                    // x56
+#pragma unroll
+  for (int i = 0; i < 8; i++) u[i] = t[i];
+  sc_sqr_n(t, 56); sc_mul(t, t, u);                                    // x112
+  sc_sqr_n(t, 14); sc_mul(t, t, x14);                                  // x126
+  sc_sqr_n(t, 1); sc_mul(t, t, a1);                                    // the 127 leading ones
+#define SC_STEP(k, x) sc_sqr_n(t, k); sc_mul(t, t, x);
+  SC_STEP(4, a5) SC_STEP(2, a3) SC_STEP(4, a5) SC_STEP(4, a5) SC_STEP(2, a3) SC_STEP(3, a3)
+  SC_STEP(4, a7) SC_STEP(5, a7) SC_STEP(4, a3) SC_STEP(4, a5) SC_STEP(4, a7) SC_STEP(3, a5)
+  SC_STEP(3, a1) SC_STEP(6, a5) SC_STEP(10, a7) SC_STEP(4, a7) SC_STEP(4, a7) SC_STEP(3, a7)
+  SC_STEP(2, a3) SC_STEP(2, a1) SC_STEP(3, a1) SC_STEP(5, a5) SC_STEP(3, a7) SC_STEP(2, a1)
+  SC_STEP(5, a3) SC_STEP(4, a3) SC_STEP(2, a1) SC_STEP(8, a3) SC_STEP(3, a3) SC_STEP(3, a1)
+  SC_STEP(6, a1) SC_STEP(5, a7) SC_STEP(3, a7)
+#undef SC_STEP
+#pragma unroll
+  for (int i = 0; i < 8; i++) r[i] = t[i];
 }
 // a > (n-1)/2 ?
 KGV_HD bool sc_is_high(const uint32_t* a) {
