@@ -364,6 +364,43 @@ class UtxoSet {
     c_.check(kgv_utxo_apply_accepted(c_.get(), h_, &v, accept.data(), pov_daa_score));
   }
   uint64_t count() { uint64_t n = 0; c_.check(kgv_utxo_count(c_.get(), h_, &n)); return n; }
+  // DbUtxoSetStore::iterator (consensus/src/model/stores/utxo_set.rs:114-129): every live entry, in the table's (arbitrary) order
+  std::vector<std::pair<TransactionOutpoint, UtxoEntry>> iterator() {
+    size_t n = 0, nb = 0;
+    c_.check(kgv_utxo_export(c_.get(), h_, nullptr, nullptr, nullptr, 0, 0, &n, &nb));
+    std::vector<uint8_t> keys(36 * n + 4), bytes(nb + 8);
+    std::vector<kgv_utxo_entry> ent(n + 1);
+    c_.check(kgv_utxo_export(c_.get(), h_, keys.data(), ent.data(), bytes.data(), n, nb, &n, &nb));
+    std::vector<std::pair<TransactionOutpoint, UtxoEntry>> out(n);
+    for (size_t i = 0; i < n; i++) {
+      std::memcpy(out[i].first.transaction_id.data(), keys.data() + 36 * i, 32);
+      out[i].first.index = 0;
+      for (int b = 0; b < 4; b++) out[i].first.index |= (uint32_t)keys[36 * i + 32 + b] << (8 * b);
+      UtxoEntry& e = out[i].second;
+      e.amount = ent[i].amount; e.block_daa_score = ent[i].block_daa_score; e.is_coinbase = ent[i].is_coinbase != 0;
+      e.script_public_key.version = ent[i].spk_version;
+      e.script_public_key.script.assign(bytes.begin() + ent[i].script_off, bytes.begin() + ent[i].script_off + ent[i].script_len);
+    }
+    return out;
+  }
+  // Consensus::append_imported_pruning_point_utxos (consensus/src/consensus/mod.rs:1070-1083): the chunk goes into the set, MuHash::from_utxo of
+  // its entries into `current_multiset` (whose denominator stays untouched)
+  void append_imported_pruning_point_utxos(const std::vector<std::pair<TransactionOutpoint, UtxoEntry>>& chunk, MuHash& current_multiset) {
+    if (chunk.empty()) return;
+    std::vector<uint8_t> ak(36 * chunk.size()), bytes(8);
+    std::vector<kgv_utxo_entry> ae(chunk.size());
+    for (size_t i = 0; i < chunk.size(); i++) {
+      key36(ak.data() + 36 * i, chunk[i].first);
+      const UtxoEntry& e = chunk[i].second;
+      std::memset(&ae[i], 0, sizeof ae[i]);
+      ae[i].amount = e.amount; ae[i].block_daa_score = e.block_daa_score; ae[i].spk_version = e.script_public_key.version; ae[i].is_coinbase = e.is_coinbase ? 1 : 0;
+      ae[i].script_off = (uint32_t)bytes.size(); ae[i].script_len = (uint32_t)e.script_public_key.script.size();
+      bytes.insert(bytes.end(), e.script_public_key.script.begin(), e.script_public_key.script.end());
+    }
+    std::array<uint8_t, 384> num = current_multiset.numerator();
+    c_.check(kgv_utxo_import_chunk(c_.get(), h_, ak.data(), ae.data(), bytes.data(), bytes.size(), chunk.size(), num.data()));
+    current_multiset = MuHash(c_, num, current_multiset.denominator());
+  }
   MuHash muhash() {
     std::array<uint8_t, 384> num{}, one{};
     one[0] = 1;

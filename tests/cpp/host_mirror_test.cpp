@@ -5,6 +5,7 @@
 // <dir> holds txs.bin inputs.bin outputs.bin entries.bin arena.bin (flat records of include/kgv.h), blocks.bin (u32 offsets),
 // fund_keys.bin fund_entries.bin fund_arena.bin (the UTXO entries the batch spends), elements.txt (hex lines; "-" prefix = remove),
 // triples.bin (n x (32 pk, 32 msg, 64 sig)).
+#include <algorithm>
 #include <cstdio>
 #include <fstream>
 #include <iostream>
@@ -128,6 +129,19 @@ int main(int argc, char** argv) {
     us.add_transactions(b, accept, 10);
     before.combine(vm.second);
     std::cout << "commitment_matches " << (before.finalize() == us.muhash().finalize() ? 1 : 0) << "\n";
+    // --- pruning-point import through the mirror: the set leaves `us` through its iterator and enters a fresh set chunk by chunk
+    //     (append_imported_pruning_point_utxos); the imported multiset must finalize to the source's commitment
+    {
+      auto all = us.iterator();
+      kgv::UtxoSet imported(ctx, 1 << 12);
+      kgv::MuHash ms(ctx);
+      for (size_t a = 0; a < all.size(); a += 7) {
+        std::vector<std::pair<kgv::TransactionOutpoint, kgv::UtxoEntry>> chunk(all.begin() + a, all.begin() + std::min(all.size(), a + 7));
+        imported.append_imported_pruning_point_utxos(chunk, ms);
+      }
+      std::cout << "pruning_import " << all.size() << " " << imported.count() << " " << (ms.finalize() == us.muhash().finalize() ? 1 : 0) << " "
+                << (imported.muhash().finalize() == us.muhash().finalize() ? 1 : 0) << "\n";
+    }
     // --- block bodies
     auto first = slurp<uint32_t>(dir + "blocks.bin");
     auto roots = kgv::calc_hash_merkle_roots(ctx, b, first);

@@ -86,6 +86,9 @@ def test_cpp_mirror_end_to_end(tmp_path, oracle):
     oracle.ok_muhash_raw(ctypes.byref(m), num, den)
     assert lines["tx_muhash_num"] == num.raw.hex() and lines["tx_muhash_den"] == den.raw.hex()
     assert lines["commitment_matches"] == "1"
+    # pruning-point import through the mirror (UtxoSet::iterator -> append_imported_pruning_point_utxos in chunks of 7): same size, same commitment
+    n_src, n_dst, ms_ok, set_ok = lines["pruning_import"].split()
+    assert n_src == n_dst and int(n_src) > 40 and ms_ok == "1" and set_ok == "1"
     # composed view + SigCache through the C++ mirror: same verdicts, base untouched, second pass served by the cache, spent-in-view outpoints missing
     same, base_count, second_hits, first_inserts, second_inserts, missing, n_acc = (int(x) for x in lines["view"].split())
     assert same == 1 and base_count == len(fe) and first_inserts > 40 and second_hits >= first_inserts and second_inserts <= 2 and missing == n_acc > 40
