@@ -176,9 +176,29 @@ KGV_HD void sc_sqr(uint32_t* r, const uint32_t* a) {
 // by a sliding window over the odd powers a, a^3, a^5, a^7 (schedule derived and checked against pow(a, n-2, n) by
 // tools/derive_sc_inv_chain.py; tests/test_hostsim.py runs this very function on the host): 255 squarings + 44 multiplications instead of the 255 + 191
 // of plain square-and-multiply (ECDSA shares one inversion among KGV_ITEMS signatures; it was 11 % of an ECDSA verification).
+#if defined(__CUDACC__) && KGV_NOINLINE_MUL && KGV_SC_SQRN_CALL
+static __device__ __noinline__ sc8 sc_sqr_n_call(sc8 a, int n) {  // one call per run of squarings (see fe_sqr_n)
+#pragma unroll 1
+  for (int i = 0; i < n; i++) {
+    uint32_t t[16];
+    sqr_wide(t, a.v);
+    sc_reduce512(a.v, t);
+  }
+  return a;
+}
+KGV_HD void sc_sqr_n(uint32_t* r, int n) {
+  sc8 x;
+#pragma unroll
+  for (int i = 0; i < 8; i++) x.v[i] = r[i];
+  x = sc_sqr_n_call(x, n);
+#pragma unroll
+  for (int i = 0; i < 8; i++) r[i] = x.v[i];
+}
+#else
 KGV_HD void sc_sqr_n(uint32_t* r, int n) {
   for (int i = 0; i < n; i++) sc_sqr(r, r);
 }
+#endif
 KGV_HD void sc_inv(uint32_t* r, const uint32_t* a) {
   uint32_t a1[8], a3[8], a5[8], a7[8], x6[8], x14[8], t[8], u[8];
 #pragma unroll
