@@ -399,6 +399,13 @@ def measure_dag_replay(ctx, dev, n_blocks, tpb, window, cpu_budget_s, mix=(1.0, 
         ts = [torch.from_numpy(a.view(np.uint8).reshape(-1)).to(dev) for a in (b.txs, b.inputs, b.outputs, b.arena)]
         dres = torch.empty(len(b.txs) * 16, dtype=torch.uint8, device=dev)
         dwins.append((ts, dres, c_batch([t.data_ptr() for t in ts], b)))
+    # warm-up: the whole chain once against a scratch table (untimed) - it sizes every per-call buffer of the context (the first windows of a
+    # cold context would otherwise pay cudaMalloc inside the timed region: +-25 % on a leg of only 3-4 windows)
+    scratch = GpuUtxoSet(ctx, 1 << 24)
+    for (b, arr, _, _), (ts, dres, cb) in zip(wins, dwins):
+        ctx._check(lib.kgv_replay_window(h, scratch._h, C.byref(cb), arr.ctypes.data, len(arr), C.byref(prm), dres.data_ptr(), None, None))
+    ctx.synchronize()
+    scratch.close()
     stream.synchronize()
     l0 = ctx.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -416,22 +423,39 @@ def measure_dag_replay(ctx, dev, n_blocks, tpb, window, cpu_budget_s, mix=(1.0, 
     del dwins
     # ---- end to end from page-locked host arrays
     cudart = torch.cuda.cudart()
-    pinned = []
+    # page-locked copies of the windows (cudaHostAlloc through torch: pinning the generator's arrays in place with cudaHostRegister ran into the
+    # box's locked-memory limit beyond a few hundred MB, and an array that silently stays pageable uploads at a fraction of the PCIe rate)
+    pinned, n_pin_failed = [], 0
+    hbufs = []
     for b, arr, _, _ in wins:
+        row = []
         for a in (b.txs, b.inputs, b.outputs, b.arena):
-            if a.nbytes and int(cudart.cudaHostRegister(a.ctypes.data, a.nbytes, 0)) == 0:
-                pinned.append(a)
+            src = torch.from_numpy(a.view(np.uint8).reshape(-1))
+            try:
+                t = src.pin_memory() if a.nbytes else src
+            except Exception:
+                t, n_pin_failed = src, n_pin_failed + 1
+            row.append(t)
+        hbufs.append(row)
     us = GpuUtxoSet(ctx, 1 << 24)
-    hres = [np.zeros(len(w[0].txs), dtype=RESULT_DTYPE) for w in wins]
-    for r in hres:
-        if int(cudart.cudaHostRegister(r.ctypes.data, r.nbytes, 0)) == 0:
-            pinned.append(r)
+    hres_t = []
+    for w in wins:
+        t = torch.zeros(len(w[0].txs) * RESULT_DTYPE.itemsize, dtype=torch.uint8)
+        try:
+            t = t.pin_memory()
+        except Exception:
+            n_pin_failed += 1
+        hres_t.append(t)
+    hres = [t.numpy().view(RESULT_DTYPE) for t in hres_t]
     st = ReplayStats()
     n_acc = n_sig = 0
     h2d = 0
     t0 = time.perf_counter()
-    for (b, arr, _, _), r in zip(wins, hres):
-        cb = c_batch([a.ctypes.data for a in (b.txs, b.inputs, b.outputs, b.arena)], b)
+    cbs = [c_batch([t.data_ptr() for t in row], w[0]) for row, w in zip(hbufs, wins)]
+    for wi, ((b, arr, _, _), r) in enumerate(zip(wins, hres)):
+        cb = cbs[wi]
+        if wi + 1 < len(wins):  # the next window's upload rides on a side stream under this window's compute (kgv_batch_prefetch)
+            ctx._check(lib.kgv_batch_prefetch(h, C.byref(cbs[wi + 1])))
         ctx._check(lib.kgv_replay_window(h, us._h, C.byref(cb), arr.ctypes.data, len(arr), C.byref(prm), r.ctypes.data, None, C.byref(st)))
         n_acc += int(st.n_accepted); n_sig += int(st.n_sig_checks)
         h2d += b.txs.nbytes + b.inputs.nbytes + b.outputs.nbytes + b.arena.nbytes
@@ -474,7 +498,8 @@ def measure_dag_replay(ctx, dev, n_blocks, tpb, window, cpu_budget_s, mix=(1.0, 
                         f"kgv_replay_window over {window} blocks per call",
             "n_blocks": n_blocks, "n_txs": n_user, "n_sig_checks": n_sig, "n_accepted": n_acc, "window_blocks": window,
             "txs_per_s": n_user / dev_s, "blocks_per_s": n_blocks / dev_s, "sig_checks_per_s": n_sig / dev_s, "ms_total": dev_s * 1e3, "gpu_launches": int(launches),
-            "e2e_txs_per_s": n_user / e2e_s, "e2e_sig_checks_per_s": n_sig / e2e_s, "e2e_h2d_bytes": int(h2d), "e2e_d2h_bytes": int(16 * n_txs),
+            "e2e_txs_per_s": n_user / e2e_s, "e2e_sig_checks_per_s": n_sig / e2e_s, "e2e_h2d_bytes": int(h2d), "e2e_d2h_bytes": int(16 * n_txs), "e2e_arrays_not_page_locked": n_pin_failed,
+            "e2e_how": "per window: kgv_batch_prefetch of the NEXT window (checks + upload on a worker thread / side stream), kgv_replay_window of this one from page-locked host arrays, verdicts to host memory",
             "cpu_baseline": cpu, "generation_s": round(gen_s, 1), "generator_signatures": n_sigs_gen}
 
 
@@ -639,8 +664,9 @@ def measure_dag_replay_sharded(ctx, dev, comm, rank, world, n_blocks, tpb, windo
     total_s = gen_s = pre_ms = ord_ms = 0.0
     n_txs = n_sig = n_acc = done = 0
     try:
-        while done < n_blocks:
-            k = min(window, n_blocks - done)
+        def make_window(k):
+            """generate + page-lock one window (outside the timed region)"""
+            nonlocal gen_s
             t0 = time.perf_counter()
             gen.generate(k, tpb)
             b, first, pov = gen.take()
@@ -650,8 +676,16 @@ def measure_dag_replay_sharded(ctx, dev, comm, rank, world, n_blocks, tpb, windo
             res = np.zeros(len(b.txs), dtype=RESULT_DTYPE)
             pinned = [a for a in (b.txs, b.inputs, b.outputs, b.arena, res) if a.nbytes and int(cudart.cudaHostRegister(a.ctypes.data, a.nbytes, 0)) == 0]
             cb = _KgvTxBatch(b.txs.ctypes.data, len(b.txs), b.inputs.ctypes.data, len(b.inputs), b.outputs.ctypes.data, len(b.outputs), None, b.arena.ctypes.data, len(b.arena))
+            return b, arr, res, pinned, cb, k
+
+        cur = make_window(min(window, n_blocks))
+        while cur is not None:
+            b, arr, res, pinned, cb, k = cur
+            nxt = make_window(min(window, n_blocks - done - k)) if done + k < n_blocks else None
             dist.barrier()
             t0 = time.perf_counter()
+            if nxt is not None:  # the next window's upload overlaps this window's compute
+                ctx._check(lib.kgv_batch_prefetch(h, C.byref(nxt[4])))
             ctx._check(lib.kgv_replay_window(h, us._h, C.byref(cb), arr.ctypes.data, k, C.byref(prm), res.ctypes.data, None, C.byref(st)))
             dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
@@ -661,6 +695,7 @@ def measure_dag_replay_sharded(ctx, dev, comm, rank, world, n_blocks, tpb, windo
             n_txs += len(b.txs) - k; n_sig += int(st.n_sig_checks); n_acc += int(st.n_accepted)
             pre_ms += float(st.pre_check_ms); ord_ms += float(st.in_order_ms)
             done += k
+            cur = nxt
         cnt = gen.counts()
         assert n_acc == n_txs - cnt["n_invalid"] and us.count() == cnt["n_utxos"], (n_acc, n_txs, cnt)
         dig = torch.frombuffer(bytearray(us.digest()), dtype=torch.uint8).to(dev)

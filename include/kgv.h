@@ -367,6 +367,13 @@ int kgv_replay_window(kgv_ctx* ctx, kgv_utxo_table* t, const kgv_tx_batch* batch
  * found at each block's position).  Must directly follow that kgv_replay_window call (no other batch call in between).
  * With kgv_muhash_prefix_combine and kgv_muhash_finalize_batch this yields every chain block's utxo_commitment of a window (:188-192). */
 int kgv_replay_muhash(kgv_ctx* ctx, const uint32_t* group_first_block, size_t n_groups, uint8_t* values768);
+/* Overlap of the next window's upload with the current window's compute (IBD: the caller knows the blocks ahead).  A HOST batch is checked and
+ * copied to the device on a side stream into a second staging buffer; the next kgv_replay_window / kgv_validate_txs / kgv_tx_ids ... call that is
+ * handed exactly this batch (the same arrays and sizes) takes that buffer over instead of uploading.  The arrays must stay unchanged - and be
+ * page-locked for the copy to really be asynchronous - until that call.  A device-resident batch is a no-op.  Two batches can be in flight (the
+ * usual order is: prefetch window i+1, then the synchronous call for window i, whose own copy was prefetched one step earlier); a third
+ * prefetch replaces the older one. */
+int kgv_batch_prefetch(kgv_ctx* ctx, const kgv_tx_batch* batch);
 
 /* ------------------------------------------------------------------------------------------------
  * Merkle roots: crypto/merkle/src/lib.rs:3-30 calc_merkle_root / merkle_hash.

@@ -40,6 +40,7 @@ SYMBOLS = [
     ("kgv_utxo_apply_diff", _c.c_int, [_c.c_void_p, _c.c_void_p, _u8p, _c.c_size_t, _u8p, _u8p, _u8p, _u8p, _c.c_size_t, _c.c_size_t, _u8p]),
     ("kgv_utxo_count", _c.c_int, [_c.c_void_p, _c.c_void_p, _c.POINTER(_c.c_uint64)]),
     ("kgv_utxo_digest", _c.c_int, [_c.c_void_p, _c.c_void_p, _u8p]),
+    ("kgv_batch_prefetch", _c.c_int, [_c.c_void_p, _c.c_void_p]),
     ("kgv_utxo_export", _c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_size_t, _c.POINTER(_c.c_size_t), _c.POINTER(_c.c_size_t)]),
     ("kgv_utxo_import_chunk", _c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_size_t, _c.c_void_p]),
     ("kgv_validate_txs", _c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_uint64, _c.c_uint32, _c.c_void_p, _u8p]),

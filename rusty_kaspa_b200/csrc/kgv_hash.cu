@@ -23,22 +23,11 @@ using namespace kgv;
 
 static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 
-int kgv_batch_to_device(kgv_ctx* ctx, const kgv_tx_batch* b, kgv_dev_batch* out, bool need_entries) {
-  if (!b) { ctx->err = "null batch"; return KGV_ERR_ARG; }
-  ctx->last_replay.valid = false;  // whatever the last replay staged may be overwritten from here on
-  if ((b->n_txs && !b->txs) || (b->n_inputs && !b->inputs) || (b->n_outputs && !b->outputs) || (b->n_bytes && !b->bytes) ||
-      (need_entries && b->n_inputs && !b->entries)) {
-    ctx->err = "batch array missing";
-    return KGV_ERR_ARG;
-  }
-  out->n_txs = b->n_txs; out->n_inputs = b->n_inputs; out->n_outputs = b->n_outputs; out->n_bytes = b->n_bytes;
-  const void* probe = b->n_txs ? (const void*)b->txs : (const void*)b->bytes;
-  if (probe && kgv_ptr_is_device(probe)) {
-    out->txs = b->txs; out->inputs = b->inputs; out->outputs = b->outputs; out->entries = b->entries; out->bytes = b->bytes;
-    return KGV_OK;
-  }
-  // host-resident batch: the records are about to drive device-side pointer arithmetic, so every range is checked first
-  // (a device-resident batch is trusted: its producer is device code of the same process)
+// range checks of a HOST batch (a device-resident batch is trusted: its producer is device code of the same process)
+static int kgv_check_host_batch(std::string& err_out, const kgv_tx_batch* b) {
+  struct { std::string& err; } ctx_{err_out};
+  auto* ctx = &ctx_;
+  // the records are about to drive device-side pointer arithmetic, so every range is checked first
   for (size_t i = 0; i < b->n_txs; i++) {
     const kgv_tx& t = b->txs[i];
     if ((uint64_t)t.first_input + t.n_inputs > b->n_inputs || (uint64_t)t.first_output + t.n_outputs > b->n_outputs ||
@@ -77,25 +66,126 @@ int kgv_batch_to_device(kgv_ctx* ctx, const kgv_tx_batch* b, kgv_dev_batch* out,
         ctx->err = "malformed batch: script of entry " + std::to_string(i) + " lies outside the byte arena";
         return KGV_ERR_ARG;
       }
-  size_t o_tx = 0;
-  size_t o_in = al256(o_tx + b->n_txs * sizeof(kgv_tx));
-  size_t o_out = al256(o_in + b->n_inputs * sizeof(kgv_input));
-  size_t o_ent = al256(o_out + b->n_outputs * sizeof(kgv_output));
-  size_t o_by = al256(o_ent + (b->entries ? b->n_inputs * sizeof(kgv_utxo_entry) : 0));
-  size_t total = al256(o_by + b->n_bytes + 16);
-  int rc = kgv_reserve(ctx, &ctx->d_batch, &ctx->d_batch_cap, total);
+  return KGV_OK;
+}
+struct BatchLayout { size_t o_tx, o_in, o_out, o_ent, o_by, total; };
+static BatchLayout kgv_batch_layout(const kgv_tx_batch* b) {
+  BatchLayout L;
+  L.o_tx = 0;
+  L.o_in = al256(L.o_tx + b->n_txs * sizeof(kgv_tx));
+  L.o_out = al256(L.o_in + b->n_inputs * sizeof(kgv_input));
+  L.o_ent = al256(L.o_out + b->n_outputs * sizeof(kgv_output));
+  L.o_by = al256(L.o_ent + (b->entries ? b->n_inputs * sizeof(kgv_utxo_entry) : 0));
+  L.total = al256(L.o_by + b->n_bytes + 16);
+  return L;
+}
+static int kgv_batch_upload(kgv_ctx* ctx, const kgv_tx_batch* b, uint8_t* d, const BatchLayout& L, cudaStream_t st) {
+  if (b->n_txs) CK(cudaMemcpyAsync(d + L.o_tx, b->txs, b->n_txs * sizeof(kgv_tx), cudaMemcpyHostToDevice, st));
+  if (b->n_inputs) CK(cudaMemcpyAsync(d + L.o_in, b->inputs, b->n_inputs * sizeof(kgv_input), cudaMemcpyHostToDevice, st));
+  if (b->n_outputs) CK(cudaMemcpyAsync(d + L.o_out, b->outputs, b->n_outputs * sizeof(kgv_output), cudaMemcpyHostToDevice, st));
+  if (b->entries && b->n_inputs) CK(cudaMemcpyAsync(d + L.o_ent, b->entries, b->n_inputs * sizeof(kgv_utxo_entry), cudaMemcpyHostToDevice, st));
+  if (b->n_bytes) CK(cudaMemcpyAsync(d + L.o_by, b->bytes, b->n_bytes, cudaMemcpyHostToDevice, st));
+  return KGV_OK;
+}
+static void kgv_batch_pointers(kgv_dev_batch* out, const kgv_tx_batch* b, uint8_t* d, const BatchLayout& L) {
+  out->txs = (const kgv_tx*)(d + L.o_tx);
+  out->inputs = (const kgv_input*)(d + L.o_in);
+  out->outputs = (const kgv_output*)(d + L.o_out);
+  out->entries = b->entries ? (const kgv_utxo_entry*)(d + L.o_ent) : nullptr;
+  out->bytes = d + L.o_by;
+}
+
+// Upload of a host batch AHEAD of its use: checked here, copied on a side stream into one of two prefetch buffers; the call that is later handed
+// exactly this batch (same arrays, same sizes) computes straight out of that buffer instead of uploading.  The arrays must stay unchanged
+// (and page-locked, for the copy to be asynchronous) until that call.  Typical use: prefetch(window i+1), then the synchronous call for window i.
+extern "C" int kgv_batch_prefetch(kgv_ctx* ctx, const kgv_tx_batch* b) {
+  if (!ctx) return KGV_ERR_ARG;
+  std::lock_guard<std::recursive_mutex> g(ctx->mu);
+  if (!b) { ctx->err = "null batch"; return KGV_ERR_ARG; }
+  if ((b->n_txs && !b->txs) || (b->n_inputs && !b->inputs) || (b->n_outputs && !b->outputs) || (b->n_bytes && !b->bytes)) { ctx->err = "batch array missing"; return KGV_ERR_ARG; }
+  const void* probe = b->n_txs ? (const void*)b->txs : (const void*)b->bytes;
+  if (!probe || kgv_ptr_is_device(probe)) return KGV_OK;  // nothing to upload
+  CK(cudaSetDevice(ctx->device));
+  int k = !ctx->prefetch[0].valid ? 0 : (!ctx->prefetch[1].valid ? 1 : ctx->prefetch_next);
+  ctx->prefetch_next = k ^ 1;
+  auto& P = ctx->prefetch[k];
+  if (P.worker.joinable()) P.worker.join();
+  P.valid = false;
+  if (ctx->last_replay.valid && P.buf && (const uint8_t*)ctx->last_replay.txs >= P.buf && (const uint8_t*)ctx->last_replay.txs < P.buf + P.cap)
+    ctx->last_replay.valid = false;  // the window kgv_replay_muhash would read lives in this slot: it has to be asked for before the slot is reused
+  const BatchLayout L = kgv_batch_layout(b);
+  int rc = kgv_reserve(ctx, &P.buf, &P.cap, L.total);
   if (rc) return rc;
-  uint8_t* d = ctx->d_batch;
-  if (b->n_txs) CK(cudaMemcpyAsync(d + o_tx, b->txs, b->n_txs * sizeof(kgv_tx), cudaMemcpyHostToDevice, ctx->stream));
-  if (b->n_inputs) CK(cudaMemcpyAsync(d + o_in, b->inputs, b->n_inputs * sizeof(kgv_input), cudaMemcpyHostToDevice, ctx->stream));
-  if (b->n_outputs) CK(cudaMemcpyAsync(d + o_out, b->outputs, b->n_outputs * sizeof(kgv_output), cudaMemcpyHostToDevice, ctx->stream));
-  if (b->entries && b->n_inputs) CK(cudaMemcpyAsync(d + o_ent, b->entries, b->n_inputs * sizeof(kgv_utxo_entry), cudaMemcpyHostToDevice, ctx->stream));
-  if (b->n_bytes) CK(cudaMemcpyAsync(d + o_by, b->bytes, b->n_bytes, cudaMemcpyHostToDevice, ctx->stream));
-  out->txs = (const kgv_tx*)(d + o_tx);
-  out->inputs = (const kgv_input*)(d + o_in);
-  out->outputs = (const kgv_output*)(d + o_out);
-  out->entries = b->entries ? (const kgv_utxo_entry*)(d + o_ent) : nullptr;
-  out->bytes = d + o_by;
+  if (!P.done) CK(cudaEventCreateWithFlags(&P.done, cudaEventDisableTiming));
+  if (!ctx->ev_prefetch) CK(cudaEventCreateWithFlags(&ctx->ev_prefetch, cudaEventDisableTiming));
+  if (!ctx->copy_stream) CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  // the slot may have fed an earlier call: everything enqueued so far has to be done with it before it is overwritten
+  CK(cudaEventRecord(ctx->ev_prefetch, ctx->stream));
+  CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_prefetch, 0));
+  P.txs = b->txs; P.inputs = b->inputs; P.outputs = b->outputs; P.entries = b->entries; P.bytes = b->bytes;
+  P.n_txs = b->n_txs; P.n_inputs = b->n_inputs; P.n_outputs = b->n_outputs; P.n_bytes = b->n_bytes;
+  P.rc = KGV_OK;
+  P.err.clear();
+  // The range checks stream over every record of the batch (~3 ms for a 150 k-transaction window): they and the copy calls run on a worker
+  // thread, so that the caller can issue the current window's call right away.  The worker touches only this slot, the copy stream and the
+  // caller's (unchanging) arrays; whoever consumes or reuses the slot joins it first.
+  const kgv_tx_batch copy = *b;
+  const int device = ctx->device;
+  cudaStream_t cs = ctx->copy_stream;
+  kgv_ctx::PrefetchSlot* slot = &P;
+  P.worker = std::thread([copy, device, cs, slot, L]() {
+    slot->rc = kgv_check_host_batch(slot->err, &copy);
+    if (slot->rc) return;
+    cudaError_t e = cudaSetDevice(device);
+    uint8_t* d = slot->buf;
+    auto cp = [&](size_t off, const void* src, size_t bytes) { if (e == cudaSuccess && bytes) e = cudaMemcpyAsync(d + off, src, bytes, cudaMemcpyHostToDevice, cs); };
+    cp(L.o_tx, copy.txs, copy.n_txs * sizeof(kgv_tx));
+    cp(L.o_in, copy.inputs, copy.n_inputs * sizeof(kgv_input));
+    cp(L.o_out, copy.outputs, copy.n_outputs * sizeof(kgv_output));
+    if (copy.entries) cp(L.o_ent, copy.entries, copy.n_inputs * sizeof(kgv_utxo_entry));
+    cp(L.o_by, copy.bytes, copy.n_bytes);
+    if (e == cudaSuccess) e = cudaEventRecord(slot->done, cs);
+    if (e != cudaSuccess) { slot->rc = KGV_ERR_CUDA; slot->err = std::string("kgv_batch_prefetch: ") + cudaGetErrorString(e); }
+  });
+  P.valid = true;
+  return KGV_OK;
+}
+
+int kgv_batch_to_device(kgv_ctx* ctx, const kgv_tx_batch* b, kgv_dev_batch* out, bool need_entries) {
+  if (!b) { ctx->err = "null batch"; return KGV_ERR_ARG; }
+  ctx->last_replay.valid = false;  // whatever the last replay staged may be overwritten from here on
+  if ((b->n_txs && !b->txs) || (b->n_inputs && !b->inputs) || (b->n_outputs && !b->outputs) || (b->n_bytes && !b->bytes) ||
+      (need_entries && b->n_inputs && !b->entries)) {
+    ctx->err = "batch array missing";
+    return KGV_ERR_ARG;
+  }
+  out->n_txs = b->n_txs; out->n_inputs = b->n_inputs; out->n_outputs = b->n_outputs; out->n_bytes = b->n_bytes;
+  const void* probe = b->n_txs ? (const void*)b->txs : (const void*)b->bytes;
+  if (probe && kgv_ptr_is_device(probe)) {
+    out->txs = b->txs; out->inputs = b->inputs; out->outputs = b->outputs; out->entries = b->entries; out->bytes = b->bytes;
+    return KGV_OK;
+  }
+  for (auto& P : ctx->prefetch)
+    if (P.valid && P.txs == b->txs && P.inputs == b->inputs && P.outputs == b->outputs && P.entries == b->entries && P.bytes == b->bytes && P.n_txs == b->n_txs &&
+        P.n_inputs == b->n_inputs && P.n_outputs == b->n_outputs && P.n_bytes == b->n_bytes && (!need_entries || b->entries)) {
+      // this very batch was uploaded ahead of time (kgv_batch_prefetch): compute out of its buffer
+      P.valid = false;
+      if (P.worker.joinable()) P.worker.join();
+      if (P.rc) { ctx->err = P.err; return P.rc; }
+      CK(cudaStreamWaitEvent(ctx->stream, P.done, 0));
+      kgv_batch_pointers(out, b, P.buf, kgv_batch_layout(b));
+      return KGV_OK;
+    }
+  {
+    int rc0 = kgv_check_host_batch(ctx->err, b);
+    if (rc0) return rc0;
+  }
+  const BatchLayout L = kgv_batch_layout(b);
+  int rc = kgv_reserve(ctx, &ctx->d_batch, &ctx->d_batch_cap, L.total);
+  if (rc) return rc;
+  rc = kgv_batch_upload(ctx, b, ctx->d_batch, L, ctx->stream);
+  if (rc) return rc;
+  kgv_batch_pointers(out, b, ctx->d_batch, L);
   return KGV_OK;
 }
 

@@ -4,6 +4,7 @@
 #include <cstdint>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #ifndef KGV_BLOCK
@@ -33,6 +34,22 @@ struct kgv_ctx {
   size_t d_out_cap = 0;
   uint8_t* d_batch = nullptr;   // staging for host-resident transaction batches
   size_t d_batch_cap = 0;
+  // kgv_batch_prefetch: host batches uploaded ahead of their use on copy_stream.  Two slots, because the caller prefetches window i+1 BEFORE it
+  // issues the (synchronous) call for window i, whose own prefetched copy is still waiting in the other slot.
+  struct PrefetchSlot {
+    uint8_t* buf = nullptr;
+    size_t cap = 0;
+    bool valid = false;
+    const void *txs = nullptr, *inputs = nullptr, *outputs = nullptr, *entries = nullptr, *bytes = nullptr;
+    size_t n_txs = 0, n_inputs = 0, n_outputs = 0, n_bytes = 0;
+    cudaEvent_t done = nullptr;   // upload finished
+    std::thread worker;           // range checks + upload run here, off the caller's critical path; joined by whoever consumes / reuses the slot
+    int rc = 0;
+    std::string err;
+  } prefetch[2];
+  int prefetch_next = 0;          // slot the next kgv_batch_prefetch overwrites when both are taken
+  cudaEvent_t ev_prefetch = nullptr;
+  cudaStream_t copy_stream = nullptr;  // its own stream: aux_stream carries the ECDSA half of a validation call
   uint8_t* d_scratch = nullptr; // per-call device scratch (sub-hashes, sig items, ...)
   size_t d_scratch_cap = 0;
   uint8_t* d_work = nullptr;    // per-call populated entries / input->tx index / verdicts of the validation calls

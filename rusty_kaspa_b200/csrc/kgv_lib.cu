@@ -377,13 +377,18 @@ extern "C" int kgv_create(int device, uint32_t flags, kgv_ctx** out) {
 extern "C" void kgv_destroy(kgv_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
+  for (auto& P : ctx->prefetch) if (P.worker.joinable()) P.worker.join();
+  if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
   cudaStreamSynchronize(ctx->stream);
   if (ctx->gtab) cudaFree(ctx->gtab);
-  for (uint8_t* b : {ctx->d_in, ctx->d_out, ctx->d_batch, ctx->d_scratch, ctx->d_mu, ctx->d_work, ctx->d_replay})
+  for (uint8_t* b : {ctx->d_in, ctx->d_out, ctx->d_batch, ctx->prefetch[0].buf, ctx->prefetch[1].buf, ctx->d_scratch, ctx->d_mu, ctx->d_work, ctx->d_replay})
     if (b) cudaFree(b);
   for (uint8_t* b : ctx->parked) cudaFree(b);
   for (cudaEvent_t e : ctx->ev_chunk) if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : ctx->ev_time) if (e) cudaEventDestroy(e);
+  if (ctx->ev_prefetch) cudaEventDestroy(ctx->ev_prefetch);
+  for (auto& P : ctx->prefetch) if (P.done) cudaEventDestroy(P.done);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
@@ -412,6 +417,7 @@ extern "C" int kgv_synchronize(kgv_ctx* ctx) {
   CK(cudaStreamSynchronize(ctx->stream));
   if (!ctx->parked.empty()) {  // the caller declared the context idle: outgrown buffers can go
     CK(cudaStreamSynchronize(ctx->aux_stream));
+    if (ctx->copy_stream) CK(cudaStreamSynchronize(ctx->copy_stream));
     for (uint8_t* p : ctx->parked) cudaFree(p);
     ctx->parked.clear();
   }

@@ -97,6 +97,12 @@ class DagReplayer:
                            "in_order_ms": float(st.in_order_ms)}
         return (res, acc) if want_accept else res
 
+    def prefetch(self, batch):
+        """kgv_batch_prefetch: start uploading the NEXT window's (host) batch while the current window computes; the replay_window call that gets
+        this very batch object then skips its upload"""
+        cb = _c_batch(batch, with_entries=False)
+        self.ctx._check(self.ctx._lib.kgv_batch_prefetch(self.ctx._h, ctypes.byref(cb)))
+
     def replay_muhash(self, group_first_block):
         """kgv_replay_muhash for the window just replayed: (n_groups, 768) uint8 (numerator || denominator) of what each group of blocks accepted"""
         gf = np.ascontiguousarray(group_first_block, dtype=np.uint32)

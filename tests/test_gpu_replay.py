@@ -140,9 +140,15 @@ def test_replay_of_150k_generated_transactions_matches_the_cpu_path(gpu_ctx, ora
     ost = oracle_tx.State(oracle)
     n_tx = n_acc = 0
     seen = set()
-    for b, first, pov in wins:
+    for wi, (b, first, pov) in enumerate(wins):
         arr = np.zeros(len(pov), dtype=REPLAY_BLOCK_DTYPE)
         arr["first_tx"], arr["n_txs"], arr["pov_daa_score"], arr["flags"] = first[:-1], np.diff(first), pov, 1
+        # kgv_batch_prefetch: the next window's upload overlaps this window's compute (every second window; once with a batch that is then NOT the
+        # one replayed next: the prefetched copy must simply be ignored)
+        if wi + 1 < len(wins) and wi % 2 == 0:
+            r.prefetch(wins[wi + 1][0])
+        elif wi + 2 < len(wins) and wi == 3:
+            r.prefetch(wins[wi + 2][0])
         got, acc = r.replay_window(b, arr, want_accept=True)
         exp, eacc = oracle_tx.state_replay(ost, b, first, pov, op, threads=16)
         for f in ("status", "script_err"):
