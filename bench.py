@@ -707,11 +707,11 @@ def measure_dag_replay_sharded(ctx, dev, comm, rank, world, n_blocks, tpb, windo
         us.close(); gen.close()
     return {"workload": f"config 5 shape: generated chain of {n_blocks} blocks (<= {tpb} txs/block, mixed 1-/2-input P2PK Schnorr, ~1% invalid) replayed in order on every rank "
                         f"against its own 2^25-slot table replica, signature checks sharded over {world} GPUs (kgv_set_sharding), verdict bytes exchanged through the "
-                        f"library communicator, kgv_replay_window over {window} blocks per call from page-locked host arrays (uploads inside the timed region)",
+                        f"library communicator, kgv_replay_window over {window} blocks per call from page-locked host arrays, the next window's upload prefetched (kgv_batch_prefetch) inside the timed region",
             "n_blocks": n_blocks, "n_txs": n_txs, "n_sig_checks": n_sig, "n_gpus": world, "txs_per_s": n_txs / total_s, "blocks_per_s": n_blocks / total_s,
             "sig_checks_per_s": n_sig / total_s, "seconds": total_s,
             "device_ms_rank0": {"pre_check_sharded": round(pre_ms, 2), "in_order_replicated": round(ord_ms, 2),
-                                "note": "device time of the two phases on rank 0 (kgv_replay_stats); the rest of `seconds` is the upload of the window, which every replica repeats"},
+                                "note": "device time of the two phases on rank 0 (kgv_replay_stats): the pre-check holds the sharded signature work, the in-order part is replicated; every replica still uploads the whole window (prefetched under the previous window's compute, kgv_batch_prefetch)"},
             "generation_s": round(gen_s, 1), "replicas_identical": True}
 
 
