@@ -468,6 +468,12 @@ class TransactionValidator {
     c_.check(kgv_replay_window(c_.get(), utxo_view.get(), &v, blocks.data(), blocks.size(), &p_, res.data(), accept ? accept->data() : nullptr, stats));
     return res;
   }
+  // the NEXT window's range checks and upload under the current window's compute (kgv_batch_prefetch): call it with window i+1, then
+  // replay_window with window i; `next` must stay alive and unchanged until it is replayed
+  void prefetch(const TxBatch& next) {
+    kgv_tx_batch v = next.view(false);
+    c_.check(kgv_batch_prefetch(c_.get(), &v));
+  }
   // validate_mempool_transactions_in_parallel (consensus/src/pipeline/virtual_processor/processor.rs:853-878): same kernels, but every
   // outcome is returned (Vec<TxResult<()>>); `fee` feeds the host-side feerate check (tx_validation_in_utxo_context.rs:63-73)
   std::vector<kgv_tx_result> validate_mempool_transactions_in_parallel(UtxoSet& virtual_utxo_view, const TxBatch& b, uint64_t virtual_daa_score,
