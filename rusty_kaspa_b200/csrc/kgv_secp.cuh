@@ -127,8 +127,55 @@ KGV_HD void sc_reduce512(uint32_t* r, const uint32_t* t) {
   sc_reduce_once(r);
 }
 // As for fe_mul / fe_sqr, the device versions are real functions (operands by value, in registers).
+// KGV_SC_ONE_BLOCK (default): ALL scalar arithmetic of the ECDSA kernel goes through ONE non-inlined function, r = a^(2^k) * (b or 1), with a
+// single copy of the 8x8 product and of the reduction (squarings use the general product: +28 multiplies each, 0.4 % more instructions per
+// verification).  Three separate blocks (multiply, square, run-of-squarings: ~19 KB of SASS next to the 25 KB of the point arithmetic) pushed
+// the kernel's hot code out of the instruction cache: ncu showed `no_instruction` stalls at 1.88 per issued instruction against 0.75 in the
+// Schnorr kernel.
+#ifndef KGV_SC_ONE_BLOCK
+#define KGV_SC_ONE_BLOCK 1
+#endif
 struct sc8 { uint32_t v[8]; };
-#if defined(__CUDACC__) && KGV_NOINLINE_MUL
+#if defined(__CUDACC__) && KGV_NOINLINE_MUL && KGV_SC_ONE_BLOCK
+static __device__ __noinline__ sc8 sc_pow2k_mul_call(sc8 a, int k, int with_mul, sc8 b) {
+  const int n = k + with_mul;
+#pragma unroll 1
+  for (int i = 0; i < n; i++) {
+    sc8 y;
+#pragma unroll
+    for (int w = 0; w < 8; w++) y.v[w] = i < k ? a.v[w] : b.v[w];
+    uint32_t t[16];
+    mul_wide(t, a.v, y.v);
+    sc_reduce512(a.v, t);
+  }
+  return a;
+}
+KGV_HD void sc_mul(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+  sc8 x, y;
+#pragma unroll
+  for (int i = 0; i < 8; i++) { x.v[i] = a[i]; y.v[i] = b[i]; }
+  sc8 z = sc_pow2k_mul_call(x, 0, 1, y);
+#pragma unroll
+  for (int i = 0; i < 8; i++) r[i] = z.v[i];
+}
+KGV_HD void sc_sqr(uint32_t* r, const uint32_t* a) {
+  sc8 x;
+#pragma unroll
+  for (int i = 0; i < 8; i++) x.v[i] = a[i];
+  sc8 z = sc_pow2k_mul_call(x, 1, 0, x);
+#pragma unroll
+  for (int i = 0; i < 8; i++) r[i] = z.v[i];
+}
+// r = r^(2^k) * m
+KGV_HD void sc_sqr_n_mul(uint32_t* r, int k, const uint32_t* m) {
+  sc8 x, y;
+#pragma unroll
+  for (int i = 0; i < 8; i++) { x.v[i] = r[i]; y.v[i] = m[i]; }
+  sc8 z = sc_pow2k_mul_call(x, k, 1, y);
+#pragma unroll
+  for (int i = 0; i < 8; i++) r[i] = z.v[i];
+}
+#elif defined(__CUDACC__) && KGV_NOINLINE_MUL
 static __device__ __noinline__ sc8 sc_mul_call(sc8 a, sc8 b) {
   sc8 r;
   uint32_t t[16];
@@ -176,6 +223,9 @@ KGV_HD void sc_sqr(uint32_t* r, const uint32_t* a) {
 // by a sliding window over the odd powers a, a^3, a^5, a^7 (schedule derived and checked against pow(a, n-2, n) by
 // tools/derive_sc_inv_chain.py; tests/test_hostsim.py runs this very function on the host): 255 squarings + 44 multiplications instead of the 255 + 191
 // of plain square-and-multiply (ECDSA shares one inversion among KGV_ITEMS signatures; it was 11 % of an ECDSA verification).
+#if defined(__CUDACC__) && KGV_NOINLINE_MUL && KGV_SC_ONE_BLOCK
+// (sc_sqr_n_mul above)
+#else
 #if defined(__CUDACC__) && KGV_NOINLINE_MUL && KGV_SC_SQRN_CALL
 static __device__ __noinline__ sc8 sc_sqr_n_call(sc8 a, int n) {  // one call per run of squarings (see fe_sqr_n)
 #pragma unroll 1
@@ -199,6 +249,8 @@ KGV_HD void sc_sqr_n(uint32_t* r, int n) {
   for (int i = 0; i < n; i++) sc_sqr(r, r);
 }
 #endif
+KGV_HD void sc_sqr_n_mul(uint32_t* r, int k, const uint32_t* m) { sc_sqr_n(r, k); sc_mul(r, r, m); }
+#endif
 KGV_HD void sc_inv(uint32_t* r, const uint32_t* a) {
   uint32_t a1[8], a3[8], a5[8], a7[8], x6[8], x14[8], t[8], u[8];
 #pragma unroll
@@ -209,23 +261,23 @@ KGV_HD void sc_inv(uint32_t* r, const uint32_t* a) {
   sc_sqr(t, a3); sc_mul(a7, t, a1);    // x3 = a^7
 #pragma unroll
   for (int i = 0; i < 8; i++) t[i] = a7[i];
-  sc_sqr_n(t, 3); sc_mul(x6, t, a7);                                   // x6
+  sc_sqr_n_mul(t, 3, a7);                                              // x6
 #pragma unroll
-  for (int i = 0; i < 8; i++) t[i] = x6[i];
-  sc_sqr_n(t, 2); sc_mul(t, t, a3);                                    // x8
-  sc_sqr_n(t, 6); sc_mul(x14, t, x6);                                  // x14
+  for (int i = 0; i < 8; i++) x6[i] = t[i];
+  sc_sqr_n_mul(t, 2, a3);                                              // x8
+  sc_sqr_n_mul(t, 6, x6);                                              // x14
 #pragma unroll
-  for (int i = 0; i < 8; i++) t[i] = x14[i];
-  sc_sqr_n(t, 14); sc_mul(t, t, x14);                                  // x28
-#pragma unroll
-  for (int i = 0; i < 8; i++) u[i] = t[i];
-  sc_sqr_n(t, 28); sc_mul(t, t, u);                                    // x56
+  for (int i = 0; i < 8; i++) x14[i] = t[i];
+  sc_sqr_n_mul(t, 14, x14);                                            // x28
 #pragma unroll
   for (int i = 0; i < 8; i++) u[i] = t[i];
-  sc_sqr_n(t, 56); sc_mul(t, t, u);                                    // x112
-  sc_sqr_n(t, 14); sc_mul(t, t, x14);                                  // x126
-  sc_sqr_n(t, 1); sc_mul(t, t, a1);                                    // the 127 leading ones
-#define SC_STEP(k, x) sc_sqr_n(t, k); sc_mul(t, t, x);
+  sc_sqr_n_mul(t, 28, u);                                              // x56
+#pragma unroll
+  for (int i = 0; i < 8; i++) u[i] = t[i];
+  sc_sqr_n_mul(t, 56, u);                                              // x112
+  sc_sqr_n_mul(t, 14, x14);                                            // x126
+  sc_sqr_n_mul(t, 1, a1);                                              // the 127 leading ones
+#define SC_STEP(k, x) sc_sqr_n_mul(t, k, x);
   SC_STEP(4, a5) SC_STEP(2, a3) SC_STEP(4, a5) SC_STEP(4, a5) SC_STEP(2, a3) SC_STEP(3, a3)
   SC_STEP(4, a7) SC_STEP(5, a7) SC_STEP(4, a3) SC_STEP(4, a5) SC_STEP(4, a7) SC_STEP(3, a5)
   SC_STEP(3, a1) SC_STEP(6, a5) SC_STEP(10, a7) SC_STEP(4, a7) SC_STEP(4, a7) SC_STEP(3, a7)
