@@ -522,7 +522,22 @@ KGV_HD void gej_add_ge_body(gej& r, const fe& bx, const fe& by, fe* hout) {
 #endif
 }
 
-#if defined(__CUDACC__) && KGV_NOINLINE_POINT
+// KGV_ADD_ONE_BLOCK (default): ONE copy of the mixed addition in the kernel.  The table builder needs the addition's H value and used to get
+// it from an INLINED body - seven unrolled copies, ~160 KB of straight-line code that every signature streamed through once, evicting the
+// ladder's hot code from the instruction cache.  Now the one non-inlined function always returns H as well (8 more
+// registers by value, ignored by the ladder).
+#ifndef KGV_ADD_ONE_BLOCK
+#define KGV_ADD_ONE_BLOCK 1
+#endif
+#if defined(__CUDACC__) && KGV_NOINLINE_POINT && KGV_ADD_ONE_BLOCK
+struct gej_h { gej r; fe h; };
+static __device__ __noinline__ gej_h gej_add_ge_call(gej r, fe bx, fe by) { gej_h o; gej_add_ge_body(r, bx, by, &o.h); o.r = r; return o; }
+KGV_HD void gej_add_ge(gej& r, const fe& bx, const fe& by, fe* hout = nullptr) {
+  gej_h o = gej_add_ge_call(r, bx, by);
+  r = o.r;
+  if (hout) *hout = o.h;
+}
+#elif defined(__CUDACC__) && KGV_NOINLINE_POINT
 static __device__ __noinline__ gej gej_add_ge_call(gej r, fe bx, fe by) { gej_add_ge_body(r, bx, by, nullptr); return r; }
 #if KGV_INLINE_MUL_IN_POINT
 struct gej_h { gej r; fe h; };
