@@ -254,9 +254,10 @@ def run_reference(args, rank, world):
 
 
 # Issue cycles per Schnorr verify per SM sub-partition for the shipping kernel's instruction stream:
-# 1.355e5 IMAD.WIDE x 4.3 cycles + 2.743e5 other instructions x 1 cycle, per warp of 32 verifies (ncu instruction
-# counts, profiles/r01_schnorr_verify_ncu_summary.json; per-instruction costs, profiles/r01_pipe_microbench.txt).
-ISSUE_CYCLES_PER_WARP_VERIFY = 1.355e5 * 4.3 + 2.743e5 * 1.0
+# 1.355e5 IMAD.WIDE x 4.3 cycles + 2.772e5 other instructions x 1 cycle, per warp of 32 verifies (ncu: 412.7 k thread instructions per verify
+# in the final round-2 build, profiles/r02_schnorr_verify_ncu_summary.json - the multiply count is that of the unchanged field arithmetic,
+# profiles/r01_schnorr_verify_ncu_summary.json; per-instruction costs, profiles/r01_pipe_microbench.txt).
+ISSUE_CYCLES_PER_WARP_VERIFY = 1.355e5 * 4.3 + 2.772e5 * 1.0
 SCHEDULERS = 148 * 4
 
 
